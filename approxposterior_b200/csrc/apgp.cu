@@ -1,0 +1,434 @@
+// C-ABI of libapgp (see include/apgp.h): handle bookkeeping, staging copies, launch sequencing.
+#include "../../include/apgp.h"
+#include "apgp_internal.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace apgp;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+  g_err = what;
+  if (ce != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(ce); }
+  return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(APGP_ERR_CUDA, #call, e_); } while (0)
+#define CUI(call) do { int e_ = (call); if (e_ != 0) return fail(APGP_ERR_CUDA, #call, (cudaError_t)e_); } while (0)
+
+static const double TINY2 = 1.25e-12 * 1.25e-12;   // george's default yerr^2, added with exp(white_noise)
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return (int)e;
+    cap = bytes; return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct apgp_handle {
+  int device = 0, num_sms = 0;
+  cudaStream_t stream = nullptr; bool own_stream = false;
+  int N = 0, d = 0, Np = 0, Npad = 0, variant = 0;
+  bool has_training = false, has_hyper = false, factored = false;
+  double mean = 0, amp = 1, white_noise = -12;
+  double log_metric[APGP_MAX_DIM];
+  double logdet = 0, loglik = 0;
+  long long launches = 0;
+  DevBuf X, y, K, Dinv, r, Linv, work, scal, info, hyper, Xs, alphaA, alpha, LinvF, scratch, qscale;
+  DevBuf stage_in, stage_out;          // device staging for on_host calls
+  DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll;   // batched log-likelihood workspace
+  DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
+};
+
+namespace {
+
+__global__ void scale_pad_kernel(const double* __restrict__ a, int N, int Npad, double s, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += gridDim.x * blockDim.x) out[i] = (i < N) ? s * a[i] : 0.0;
+}
+
+struct Guard {  // select the handle's device for the duration of a call
+  int prev = -1;
+  explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void fill_hyper_row(double* row, double mean, double amp, double wn, const double* logM, int d) {
+  row[0] = mean; row[1] = amp; row[2] = exp(wn) + TINY2;
+  for (int i = 0; i < d; ++i) row[3 + i] = exp(-logM[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* apgp_last_error(void) { return g_err.c_str(); }
+int apgp_version(void) { return 100; }
+
+int apgp_create(apgp_handle** out, int device) {
+  if (!out) return fail(APGP_ERR_ARG, "apgp_create: null out");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(APGP_ERR_CUDA, "apgp_create: no CUDA device (libapgp has no CPU fallback)", e);
+  if (device < 0 || device >= ndev) return fail(APGP_ERR_ARG, "apgp_create: bad device index");
+  apgp_handle* h = new apgp_handle();
+  h->device = device;
+  Guard g(device);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { delete h; return fail(APGP_ERR_CUDA, "apgp_create: kernels are built for sm_100a only"); }
+  h->num_sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  const char* v = getenv("APGP_PREDICT_VARIANT");
+  if (v) h->variant = atoi(v) == 1 ? 1 : 0;
+  *out = h;
+  return APGP_OK;
+}
+
+int apgp_destroy(apgp_handle* h) {
+  if (!h) return APGP_OK;
+  Guard g(h->device);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
+                    &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->bK,
+                    &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->s_p0, &h->s_chain, &h->s_logp,
+                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl};
+  for (DevBuf* b : bufs) b->release();
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return APGP_OK;
+}
+
+int apgp_set_stream(apgp_handle* h, void* s) {
+  if (!h) return fail(APGP_ERR_ARG, "null handle");
+  Guard g(h->device);
+  if (s == nullptr) {
+    if (!h->own_stream) { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return APGP_OK;
+  }
+  if (h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = (cudaStream_t)s;
+  return APGP_OK;
+}
+
+int apgp_synchronize(apgp_handle* h) {
+  if (!h) return fail(APGP_ERR_ARG, "null handle");
+  Guard g(h->device);
+  CU(cudaStreamSynchronize(h->stream));
+  return APGP_OK;
+}
+
+long long apgp_launch_count(const apgp_handle* h) { return h ? h->launches : 0; }
+
+int apgp_set_variant(apgp_handle* h, int variant) {
+  if (!h || (variant != 0 && variant != 1)) return fail(APGP_ERR_ARG, "apgp_set_variant");
+  h->variant = variant; h->factored = false;
+  return APGP_OK;
+}
+
+int apgp_set_training(apgp_handle* h, const double* X, const double* y, int N, int d, int on_host) {
+  if (!h || !X || !y) return fail(APGP_ERR_ARG, "apgp_set_training: null argument");
+  if (N < 1 || d < 1 || d > APGP_MAX_DIM) return fail(APGP_ERR_ARG, "apgp_set_training: need N>=1, 1<=d<=32");
+  Guard g(h->device);
+  CUI(h->X.reserve((size_t)N * d * 8));
+  CUI(h->y.reserve((size_t)N * 8));
+  cudaMemcpyKind kind = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  CU(cudaMemcpyAsync(h->X.p, X, (size_t)N * d * 8, kind, h->stream));
+  CU(cudaMemcpyAsync(h->y.p, y, (size_t)N * 8, kind, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->N = N; h->d = d;
+  h->Np = (N + 63) / 64 * 64;
+  h->has_training = true; h->factored = false;
+  return APGP_OK;
+}
+
+int apgp_set_hyper(apgp_handle* h, double mean, double amp, const double* log_metric, double white_noise) {
+  if (!h || !log_metric) return fail(APGP_ERR_ARG, "apgp_set_hyper: null argument");
+  if (!h->has_training) return fail(APGP_ERR_ARG, "apgp_set_hyper: set the training set first (fixes d)");
+  h->mean = mean; h->amp = amp; h->white_noise = white_noise;
+  for (int i = 0; i < h->d; ++i) h->log_metric[i] = log_metric[i];
+  h->has_hyper = true; h->factored = false;
+  return APGP_OK;
+}
+
+int apgp_factorize(apgp_handle* h, double* logdet, double* loglik, int* info) {
+  if (!h) return fail(APGP_ERR_ARG, "null handle");
+  if (!h->has_training || !h->has_hyper) return fail(APGP_ERR_ARG, "apgp_factorize: training set and hyper-parameters required");
+  Guard g(h->device);
+  const int N = h->N, d = h->d, Np = h->Np;
+  const int BN = predict_variant_bn(h->variant);
+  h->Npad = (N + BN - 1) / BN * BN;
+  h->factored = false;
+  if (info) *info = 0;
+  bool finite = isfinite(h->mean) && isfinite(h->amp) && isfinite(h->white_noise);
+  for (int i = 0; i < d; ++i) finite = finite && isfinite(h->log_metric[i]);
+  if (!finite) { if (info) *info = 1; if (loglik) *loglik = -INFINITY; return APGP_NOT_POSDEF; }
+
+  CUI(h->K.reserve((size_t)Np * Np * 8));
+  CUI(h->Dinv.reserve((size_t)Np * 64 * 8));
+  CUI(h->r.reserve((size_t)Np * 8));
+  CUI(h->scal.reserve(4 * 8));
+  CUI(h->info.reserve(4));
+  CUI(h->hyper.reserve((3 + APGP_MAX_DIM) * 8));
+  CUI(h->qscale.reserve(APGP_MAX_DIM * 8));
+
+  double row[3 + APGP_MAX_DIM];
+  fill_hyper_row(row, h->mean, h->amp, h->white_noise, h->log_metric, d);
+  CU(cudaMemcpyAsync(h->hyper.p, row, (3 + d) * 8, cudaMemcpyHostToDevice, h->stream));
+  FactorBatch fb{1, N, Np, h->K.as<double>(), h->Dinv.as<double>(), h->r.as<double>(), h->scal.as<double>(),
+                 h->info.as<int>()};
+  int nl = 0;
+  CUI(launch_build_K(h->X.as<double>(), h->y.as<double>(), N, d, h->hyper.as<double>(), fb, h->stream)); ++nl;
+  CUI(launch_cholesky(fb, h->num_sms, h->stream, &nl));
+  CUI(launch_loglik_finish(fb, h->scal.as<double>() + 1, h->stream)); ++nl;
+  double sc[2]; int inf = 0;
+  CU(cudaMemcpyAsync(sc, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&inf, h->info.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->launches += nl; nl = 0;
+  if (inf != 0) {
+    if (info) *info = inf;
+    if (loglik) *loglik = -INFINITY;
+    return APGP_NOT_POSDEF;
+  }
+  h->logdet = sc[0]; h->loglik = sc[1];
+  if (logdet) *logdet = sc[0];
+  if (loglik) *loglik = sc[1];
+
+  // explicit inverse, alpha, packed operands for the predict kernels
+  CUI(h->Linv.reserve((size_t)Np * Np * 8));
+  CUI(h->work.reserve((size_t)Np * Np * 8));
+  CUI(h->alpha.reserve((size_t)Np * 8));
+  CUI(h->alphaA.reserve((size_t)h->Npad * 8));
+  CUI(h->Xs.reserve((size_t)d * h->Npad * 8));
+  const size_t lf = (size_t)linvf_total_tiles(h->Npad, BN) * BN * 16 * 8;
+  CUI(h->LinvF.reserve(lf));
+  CUI(launch_tri_inverse(h->K.as<double>(), h->Dinv.as<double>(), Np, h->Linv.as<double>(), h->work.as<double>(),
+                         h->stream, &nl));
+  CUI(launch_linvT_matvec(h->Linv.as<double>(), Np, h->r.as<double>(), h->alpha.as<double>(), h->stream)); ++nl;
+  scale_pad_kernel<<<(h->Npad + 255) / 256, 256, 0, h->stream>>>(h->alpha.as<double>(), N, h->Npad, h->amp,
+                                                                 h->alphaA.as<double>()); ++nl;
+  double qs[APGP_MAX_DIM];
+  for (int i = 0; i < d; ++i) qs[i] = sqrt(0.5 * exp(-h->log_metric[i]));
+  CU(cudaMemcpyAsync(h->qscale.p, qs, d * 8, cudaMemcpyHostToDevice, h->stream));
+  CUI(launch_pack_xs(h->X.as<double>(), N, d, h->Npad, h->qscale.as<double>(), h->Xs.as<double>(), h->stream)); ++nl;
+  CUI(launch_pack_linv(h->Linv.as<double>(), Np, N, h->Npad, BN, h->amp, h->LinvF.as<double>(), h->stream)); ++nl;
+  CU(cudaStreamSynchronize(h->stream));
+  h->launches += nl;
+  h->factored = true;
+  return APGP_OK;
+}
+
+static void fill_predict_params(apgp_handle* h, PredictParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.d = h->d; p.N = h->N; p.Npad = h->Npad;
+  p.Xs = h->Xs.as<double>(); p.alphaA = h->alphaA.as<double>(); p.LinvF = h->LinvF.as<double>();
+  for (int i = 0; i < h->d; ++i) p.qscale[i] = sqrt(0.5 * exp(-h->log_metric[i]));
+  p.mean = h->mean; p.amp = h->amp;
+}
+
+int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, double* var, double* util,
+                 const apgp_predict_opts* o, int on_host) {
+  if (!h || !o) return fail(APGP_ERR_ARG, "apgp_predict: null argument");
+  if (!h->factored) return fail(APGP_NOT_COMPUTED, "apgp_predict: GP not computed");
+  if (Q < 0) return fail(APGP_ERR_ARG, "apgp_predict: Q < 0");
+  if (Q == 0) return APGP_OK;
+  if (!Xq) return fail(APGP_ERR_ARG, "apgp_predict: null queries");
+  if ((var || util) && !o->want_var) return fail(APGP_ERR_ARG, "apgp_predict: var/util outputs need want_var=1");
+  if (o->utility < 0 || o->utility > 3) return fail(APGP_ERR_ARG, "apgp_predict: bad utility kind");
+  Guard g(h->device);
+  const int d = h->d;
+  PredictParams p;
+  fill_predict_params(h, p);
+  p.Q = Q;
+  p.has_box = o->has_box; p.utility_kind = o->utility; p.ybest = o->ybest; p.zeta = o->zeta;
+  for (int i = 0; i < d; ++i) { p.lo[i] = o->lo[i]; p.hi[i] = o->hi[i]; }
+  const int nout = (mu ? 1 : 0) + (var ? 1 : 0) + (util ? 1 : 0);
+  if (on_host) {
+    CUI(h->stage_in.reserve((size_t)Q * d * 8));
+    CUI(h->stage_out.reserve((size_t)Q * 8 * (nout ? nout : 1)));
+    CU(cudaMemcpyAsync(h->stage_in.p, Xq, (size_t)Q * d * 8, cudaMemcpyHostToDevice, h->stream));
+    p.Xq = h->stage_in.as<double>();
+    double* o0 = h->stage_out.as<double>();
+    if (mu) { p.mu = o0; o0 += Q; }
+    if (var) { p.var = o0; o0 += Q; }
+    if (util) { p.util = o0; o0 += Q; }
+  } else {
+    p.Xq = Xq; p.mu = mu; p.var = var; p.util = util;
+  }
+  int nl = 0;
+  if (o->want_var) {
+    const size_t sb = predict_scratch_bytes(h->Npad, h->num_sms, h->variant);
+    CUI(h->scratch.reserve(sb));
+    p.scratch = h->scratch.as<double>();
+    CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant, &nl));
+  } else {
+    CUI(launch_predict_mean(p, h->num_sms, h->stream, &nl));
+  }
+  h->launches += nl;
+  if (on_host) {
+    if (mu) CU(cudaMemcpyAsync(mu, p.mu, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (var) CU(cudaMemcpyAsync(var, p.var, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (util) CU(cudaMemcpyAsync(util, p.util, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return APGP_OK;
+}
+
+int apgp_grad_log_likelihood(apgp_handle* h, int fit_amp, double* grad) {
+  if (!h || !grad) return fail(APGP_ERR_ARG, "apgp_grad_log_likelihood: null argument");
+  const int d = h->d;
+  const int P = 1 + (fit_amp ? 1 : 0) + d;
+  for (int i = 0; i < P; ++i) grad[i] = 0.0;
+  if (!h->factored) return APGP_NOT_COMPUTED;      // george: zeros when quiet and not computed
+  Guard g(h->device);
+  CUI(h->bscal.reserve((2 + APGP_MAX_DIM) * 8));
+  int nl = 0;
+  CUI(launch_grad_loglik(h->X.as<double>(), h->N, d, h->Np, h->Linv.as<double>(), h->alpha.as<double>(),
+                         h->hyper.as<double>(), fit_amp, h->work.as<double>(), h->bscal.as<double>(), h->stream, &nl));
+  double out[2 + APGP_MAX_DIM];
+  CU(cudaMemcpyAsync(out, h->bscal.p, (2 + d) * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->launches += nl;
+  int k = 0;
+  grad[k++] = out[0];
+  if (fit_amp) grad[k++] = out[1];
+  for (int i = 0; i < d; ++i) grad[k++] = out[2 + i];
+  return APGP_OK;
+}
+
+int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fit_amp, double white_noise,
+                      double* ll_host) {
+  if (!h || !P_host || !ll_host) return fail(APGP_ERR_ARG, "apgp_loglik_batch: null argument");
+  if (!h->has_training) return fail(APGP_ERR_ARG, "apgp_loglik_batch: no training set");
+  const int d = h->d, N = h->N, Np = h->Np;
+  if (P != 1 + (fit_amp ? 1 : 0) + d) return fail(APGP_ERR_ARG, "apgp_loglik_batch: P != 1 + fit_amp + d");
+  if (R < 1) return APGP_OK;
+  Guard g(h->device);
+  // chunk the restart axis so the workspace stays below ~4 GiB
+  size_t per = (size_t)Np * Np * 8;
+  int Rc = (int)((4ull << 30) / per); if (Rc < 1) Rc = 1; if (Rc > R) Rc = R;
+  CUI(h->bK.reserve(per * Rc));
+  CUI(h->bDinv.reserve((size_t)Rc * Np * 64 * 8));
+  CUI(h->br.reserve((size_t)Rc * Np * 8));
+  CUI(h->bscal.reserve((size_t)(Rc > 2 + APGP_MAX_DIM ? Rc : 2 + APGP_MAX_DIM) * 8));
+  CUI(h->binfo.reserve((size_t)Rc * 4));
+  CUI(h->bhyper.reserve((size_t)Rc * (3 + d) * 8));
+  CUI(h->bll.reserve((size_t)Rc * 8));
+  std::vector<double> rows((size_t)Rc * (3 + d));
+  std::vector<char> bad(R, 0);
+  for (int r0 = 0; r0 < R; r0 += Rc) {
+    const int rc = (R - r0 < Rc) ? (R - r0) : Rc;
+    for (int r = 0; r < rc; ++r) {
+      const double* p = P_host + (size_t)(r0 + r) * P;
+      bool fin = true;
+      for (int i = 0; i < P; ++i) fin = fin && isfinite(p[i]);
+      bad[r0 + r] = fin ? 0 : 1;
+      double amp = fit_amp ? d * exp(p[1]) : 1.0;
+      const double* lm = p + 1 + (fit_amp ? 1 : 0);
+      double* row = rows.data() + (size_t)r * (3 + d);
+      if (fin) fill_hyper_row(row, p[0], amp, white_noise, lm, d);
+      else { row[0] = 0; row[1] = 1; row[2] = 1; for (int i = 0; i < d; ++i) row[3 + i] = 1; }
+    }
+    CU(cudaMemcpyAsync(h->bhyper.p, rows.data(), (size_t)rc * (3 + d) * 8, cudaMemcpyHostToDevice, h->stream));
+    FactorBatch fb{rc, N, Np, h->bK.as<double>(), h->bDinv.as<double>(), h->br.as<double>(), h->bscal.as<double>(),
+                   h->binfo.as<int>()};
+    int nl = 0;
+    CUI(launch_build_K(h->X.as<double>(), h->y.as<double>(), N, d, h->bhyper.as<double>(), fb, h->stream)); ++nl;
+    CUI(launch_cholesky(fb, h->num_sms, h->stream, &nl));
+    CUI(launch_loglik_finish(fb, h->bll.as<double>(), h->stream)); ++nl;
+    CU(cudaMemcpyAsync(ll_host + r0, h->bll.p, (size_t)rc * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches += nl;
+  }
+  for (int r = 0; r < R; ++r) if (bad[r] || !isfinite(ll_host[r])) ll_host[r] = -INFINITY;
+  return APGP_OK;
+}
+
+int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* o, const double* p0, double* chain, double* logp,
+                     double* blob, int* naccept, int on_host) {
+  if (!h || !o || !p0 || !chain || !logp || !blob || !naccept) return fail(APGP_ERR_ARG, "apgp_sampler_run: null argument");
+  if (!h->factored) return fail(APGP_NOT_COMPUTED, "apgp_sampler_run: GP not computed");
+  if (o->nens < 1 || o->nwalkers < 2 || (o->nwalkers & 1) || o->nwalkers > 1024 || o->nsteps < 1 || o->thin < 1)
+    return fail(APGP_ERR_ARG, "apgp_sampler_run: need nens>=1, even 2<=nwalkers<=1024, nsteps>=1, thin>=1");
+  Guard g(h->device);
+  const int d = h->d;
+  const size_t W = (size_t)o->nens * o->nwalkers;
+  const size_t nst = (size_t)(o->nsteps / o->thin);
+  const size_t Ns = o->nwalkers / 2;
+  const bool replay = o->replay_zz != nullptr;
+  if (replay && (!o->replay_inds || !o->replay_rint || !o->replay_logu))
+    return fail(APGP_ERR_ARG, "apgp_sampler_run: replay needs all four buffers");
+  SamplerParams p;
+  memset(&p, 0, sizeof(p));
+  p.nens = o->nens; p.nwalk = o->nwalkers; p.d = d; p.nsteps = o->nsteps; p.N = h->N; p.Npad = h->Npad;
+  p.Xs = h->Xs.as<double>(); p.alphaA = h->alphaA.as<double>();
+  for (int i = 0; i < d; ++i) { p.qscale[i] = sqrt(0.5 * exp(-h->log_metric[i])); p.lo[i] = o->lo[i]; p.hi[i] = o->hi[i]; }
+  p.mean = h->mean; p.lnprior_const = o->lnprior_const; p.a = o->a; p.seed = o->seed; p.thin = o->thin;
+  if (on_host) {
+    CUI(h->s_p0.reserve(W * d * 8)); CUI(h->s_chain.reserve(nst * W * d * 8));
+    CUI(h->s_logp.reserve(nst * W * 8)); CUI(h->s_blob.reserve(nst * W * 8)); CUI(h->s_nacc.reserve(W * 4));
+    CU(cudaMemcpyAsync(h->s_p0.p, p0, W * d * 8, cudaMemcpyHostToDevice, h->stream));
+    p.p0 = h->s_p0.as<double>(); p.chain = h->s_chain.as<double>(); p.logp = h->s_logp.as<double>();
+    p.blob = h->s_blob.as<double>(); p.naccept = h->s_nacc.as<int>();
+    if (replay) {
+      const size_t ns = (size_t)o->nens * o->nsteps;
+      CUI(h->s_ri.reserve(ns * o->nwalkers * 4)); CUI(h->s_rz.reserve(ns * 2 * Ns * 8));
+      CUI(h->s_rr.reserve(ns * 2 * Ns * 4)); CUI(h->s_rl.reserve(ns * 2 * Ns * 8));
+      CU(cudaMemcpyAsync(h->s_ri.p, o->replay_inds, ns * o->nwalkers * 4, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->s_rz.p, o->replay_zz, ns * 2 * Ns * 8, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->s_rr.p, o->replay_rint, ns * 2 * Ns * 4, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->s_rl.p, o->replay_logu, ns * 2 * Ns * 8, cudaMemcpyHostToDevice, h->stream));
+      p.r_inds = h->s_ri.as<int>(); p.r_zz = h->s_rz.as<double>(); p.r_rint = h->s_rr.as<int>(); p.r_logu = h->s_rl.as<double>();
+    }
+  } else {
+    p.p0 = p0; p.chain = chain; p.logp = logp; p.blob = blob; p.naccept = naccept;
+    p.r_inds = o->replay_inds; p.r_zz = o->replay_zz; p.r_rint = o->replay_rint; p.r_logu = o->replay_logu;
+  }
+  int nl = 0;
+  CUI(launch_sampler(p, h->stream, &nl));
+  h->launches += nl;
+  if (on_host) {
+    CU(cudaMemcpyAsync(chain, p.chain, nst * W * d * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(logp, p.logp, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(blob, p.blob, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(naccept, p.naccept, W * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return APGP_OK;
+}
+
+int apgp_get_alpha(apgp_handle* h, double* alpha) {
+  if (!h || !alpha) return fail(APGP_ERR_ARG, "null argument");
+  if (!h->factored) return fail(APGP_NOT_COMPUTED, "GP not computed");
+  Guard g(h->device);
+  CU(cudaMemcpyAsync(alpha, h->alpha.p, (size_t)h->N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return APGP_OK;
+}
+
+static int get_square(apgp_handle* h, const DevBuf& b, double* out) {
+  if (!h || !out) return fail(APGP_ERR_ARG, "null argument");
+  if (!h->factored) return fail(APGP_NOT_COMPUTED, "GP not computed");
+  Guard g(h->device);
+  CU(cudaMemcpy2DAsync(out, (size_t)h->N * 8, b.p, (size_t)h->Np * 8, (size_t)h->N * 8, h->N, cudaMemcpyDeviceToHost,
+                       h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->N; ++i)
+    for (int j = i + 1; j < h->N; ++j) out[(size_t)i * h->N + j] = 0.0;
+  return APGP_OK;
+}
+int apgp_get_linv(apgp_handle* h, double* linv) { return get_square(h, h->Linv, linv); }
+int apgp_get_chol(apgp_handle* h, double* L) { return get_square(h, h->K, L); }
+
+}  // extern "C"

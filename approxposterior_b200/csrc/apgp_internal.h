@@ -1,0 +1,92 @@
+// Internal (C++) interface between the libapgp translation units.  Not part of the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace apgp {
+
+// ---- predict ---------------------------------------------------------------------
+struct PredictParams {
+  const double* Xq;        // [Q][d] queries, row-major (device)
+  long long Q;
+  int d;
+  int N;                   // true number of training points
+  int Npad;                // padded to a multiple of the variance kernel's BN
+  const double* Xs;        // [d][Npad] training inputs, SoA, pre-scaled by sqrt(0.5/M_i), zero padded
+  const double* alphaA;    // [Npad]  A * K^{-1}(y-m), zero padded
+  const double* LinvF;     // fragment-tiled A * L^{-1} (see common.cuh)
+  double* scratch;         // [grid][BM*Npad] per-CTA K* panels (L2-resident working set)
+  double qscale[APGP_MAXD];
+  double lo[APGP_MAXD];
+  double hi[APGP_MAXD];
+  int has_box;             // apply box prior gate lo <= q <= hi (utility -> +inf outside)
+  double mean;             // constant mean m
+  double amp;              // k** = A
+  double* mu;              // [Q] out (may be null)
+  double* var;             // [Q] out (may be null)
+  double* util;            // [Q] out (may be null)
+  int utility_kind;        // 0 none, 1 AGP, 2 BAPE, 3 Jones
+  double ybest, zeta;
+};
+
+int predict_variant_bn(int variant);   // block-row height BN of the LinvF tiling used by a kernel variant
+
+// returns cudaError_t as int; *launches incremented by the number of kernel launches issued
+int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches);
+int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, int* launches);
+size_t predict_scratch_bytes(int Npad, int num_sms, int variant);
+int launch_pack_linv(const double* Linv, int ld, int N, int Npad, int BN, double amp, double* LinvF, cudaStream_t st);
+int launch_pack_xs(const double* X, int N, int d, int Npad, const double* qscale_dev, double* Xs, cudaStream_t st);
+
+// ---- factor (batched blocked Cholesky on 64x64 tiles) ------------------------------
+struct FactorBatch {
+  int R;                   // batch size (restarts); 1 for the single predict GP
+  int N;                   // true size
+  int Np;                  // padded to multiple of 64
+  double* K;               // [R][Np][Np] row-major; lower triangle in/out (L on exit)
+  double* Dinv;            // [R][Np/64][64][64] inverses of the diagonal blocks of L
+  double* r;               // [R][Np] rhs (y - mean) in, z = L^{-1} r out
+  double* logdet;          // [R] out: 2*sum(log L_ii)
+  int* info;               // [R] out: 0 ok, k+1 = not positive definite at pivot k
+};
+// hyper[R][3 + d]: mean, amp, noise_var, invM_0..invM_{d-1}
+int launch_build_K(const double* X, const double* y, int N, int d, const double* hyper, const FactorBatch& fb, cudaStream_t st);
+int launch_cholesky(const FactorBatch& fb, int num_sms, cudaStream_t st, int* launches);
+// explicit inverse of the lower-triangular factor (single matrix): Linv[Np][Np]
+int launch_tri_inverse(const double* L, const double* Dinv, int Np, double* Linv, double* work, cudaStream_t st, int* launches);
+// alpha = L^{-T} z  using the explicit inverse
+int launch_linvT_matvec(const double* Linv, int Np, const double* z, double* alpha, cudaStream_t st);
+int launch_loglik_finish(const FactorBatch& fb, double* ll, cudaStream_t st);
+// gradient pieces: Kinv = Linv^T Linv (lower), then tr-products
+int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv, const double* alpha,
+                       const double* hyper_dev, int fit_amp, double* work /*[Np*Np]*/, double* grad_dev, cudaStream_t st,
+                       int* launches);
+
+// ---- sampler ---------------------------------------------------------------------
+struct SamplerParams {
+  int nens, nwalk, d, nsteps, N, Npad;
+  const double* Xs;        // [d][Npad] scaled SoA
+  const double* alphaA;    // [Npad]
+  double qscale[APGP_MAXD];
+  double lo[APGP_MAXD], hi[APGP_MAXD];
+  double mean;
+  double lnprior_const;
+  double a;                // stretch scale
+  unsigned long long seed;
+  const double* p0;        // [nens*nwalk][d]
+  double* chain;           // [nsteps][nens*nwalk][d]
+  double* logp;            // [nsteps][nens*nwalk]
+  double* blob;            // [nsteps][nens*nwalk]
+  int* naccept;            // [nens*nwalk]
+  double* final_state;     // [nens*nwalk][d] (may be null)
+  // replay buffers (all null => Philox); layout per ensemble e:
+  const int* r_inds;       // [nens][nsteps][nwalk] colour 0/1
+  const double* r_zz;      // [nens][nsteps][2][nwalk/2]
+  const int* r_rint;       // [nens][nsteps][2][nwalk/2]
+  const double* r_logu;    // [nens][nsteps][2][nwalk/2]
+  int thin;                // store every `thin` steps (>=1)
+};
+int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches);
+
+}  // namespace apgp

@@ -1,0 +1,460 @@
+// Factor path for sm_100a: covariance build, batched blocked Cholesky, triangular inverse,
+// log-likelihood and its gradient.  Everything works on 64x64 tiles multiplied on the FP64
+// tensor pipe (DMMA.8x8x4) and is batched over a leading "restart" axis so that the R
+// hyper-parameter vectors of gpUtils.optimizeGP's restarts factor side by side.
+//
+// Replaces (reference call sites):
+//   george.GP.compute / recompute            gpUtils.py:178,244,254  approx.py:717
+//   george.GP.log_likelihood(y, quiet=True)  gpUtils.py:78,247
+//   george.GP.grad_log_likelihood            gpUtils.py:110
+// george's BasicSolver does K = kernel(X) + (yerr^2 + exp(white_noise)) I, scipy cholesky,
+// log|K| = 2 sum log L_ii, ll = -1/2 (N log 2pi + log|K|) - 1/2 r^T K^{-1} r.
+//
+// Padding: N is padded to Np (multiple of 64) with an identity block, so L and L^{-1} pad with
+// the identity and the rhs with zeros; nothing downstream needs edge handling.
+#include "apgp_internal.h"
+#include <math.h>
+
+namespace apgp {
+namespace {
+
+constexpr int T = 64;          // tile edge
+constexpr int LDS_ = 68;       // padded smem leading dimension: conflict-free DMMA fragment loads
+constexpr int GT = 128;        // threads per tile group: 4 warps, each a 32x32 sub-tile
+constexpr size_t TILE_SMEM = (size_t)2 * T * LDS_ * sizeof(double);
+constexpr size_t DIAG_SMEM = (size_t)(2 * T * (T + 1) + T) * sizeof(double);
+
+// ---- tile movers ------------------------------------------------------------------------
+// dst[r][c] (smem, ld 68) = src[r*ld + c]          (row-major 64x64 block)
+__device__ __forceinline__ void load_tile_n(double* dst, const double* __restrict__ src, int ld, int tid) {
+#pragma unroll 4
+  for (int e = tid; e < T * (T / 2); e += GT) {
+    int r = e >> 5, c2 = (e & 31) * 2;
+    double2 v = *reinterpret_cast<const double2*>(src + (size_t)r * ld + c2);
+    dst[r * LDS_ + c2] = v.x; dst[r * LDS_ + c2 + 1] = v.y;
+  }
+}
+// dst[r][c] = src[c*ld + r]                        (transpose while staging)
+__device__ __forceinline__ void load_tile_t(double* dst, const double* __restrict__ src, int ld, int tid) {
+#pragma unroll 4
+  for (int e = tid; e < T * (T / 2); e += GT) {
+    int c = e >> 5, r2 = (e & 31) * 2;
+    double2 v = *reinterpret_cast<const double2*>(src + (size_t)c * ld + r2);
+    dst[r2 * LDS_ + c] = v.x; dst[(r2 + 1) * LDS_ + c] = v.y;
+  }
+}
+
+struct Acc { double v[4][4][2]; };
+
+__device__ __forceinline__ void acc_zero(Acc& a) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a.v[i][j][0] = 0.0; a.v[i][j][1] = 0.0; }
+}
+
+// acc += As(64x64, [m][k]) * Bs(64x64, [n][k])^T ; warp (wm,wn) owns rows wm*32.., cols wn*32..
+__device__ __forceinline__ void tile_mma(const double* As, const double* Bs, Acc& acc, int wm, int wn, int lane) {
+  const double* ap = As + (wm * 32 + (lane >> 2)) * LDS_ + (lane & 3);
+  const double* bp = Bs + (wn * 32 + (lane >> 2)) * LDS_ + (lane & 3);
+#pragma unroll 4
+  for (int k4 = 0; k4 < T / 4; ++k4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a[i] = ap[i * 8 * LDS_ + k4 * 4]; b[i] = bp[i * 8 * LDS_ + k4 * 4]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+  }
+}
+
+// C[r*ld + c] = beta*C + alpha*acc     (64x64 block)
+__device__ __forceinline__ void store_acc(double* __restrict__ C, int ld, const Acc& acc, double alpha, double beta,
+                                          int wm, int wn, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = wm * 32 + i * 8 + (lane >> 2), c = wn * 32 + j * 8 + 2 * (lane & 3);
+      double2* p = reinterpret_cast<double2*>(C + (size_t)r * ld + c);
+      double2 o;
+      if (beta != 0.0) { o = *p; o.x = beta * o.x + alpha * acc.v[i][j][0]; o.y = beta * o.y + alpha * acc.v[i][j][1]; }
+      else { o.x = alpha * acc.v[i][j][0]; o.y = alpha * acc.v[i][j][1]; }
+      *p = o;
+    }
+}
+
+// ---- covariance build -------------------------------------------------------------------
+// hyper row: [mean, amp, noise_var, invM_0 .. invM_{d-1}]
+__global__ void build_K_kernel(const double* __restrict__ X, const double* __restrict__ y, int N, int d, int Np,
+                               const double* __restrict__ hyper, double* __restrict__ K, double* __restrict__ r,
+                               double* __restrict__ logdet, int* __restrict__ info) {
+  const int rr = blockIdx.y;
+  const double* h = hyper + (size_t)rr * (3 + d);
+  const int nb = Np / T;
+  // lower-triangular tile index -> (bi, bj)
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  int bj = t - bi * (bi + 1) / 2;
+  (void)nb;
+  double* Kr = K + (size_t)rr * Np * Np;
+  const double amp = h[1], noise = h[2];
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    int i = bi * T + (e >> 6), j = bj * T + (e & 63);
+    double v;
+    if (i < N && j < N) {
+      double s = 0.0;
+      for (int c = 0; c < d; ++c) {
+        double df = X[(size_t)i * d + c] - X[(size_t)j * d + c];
+        s += df * df * h[3 + c];
+      }
+      v = amp * exp(-0.5 * s);
+      if (i == j) v += noise;
+    } else {
+      v = (i == j) ? 1.0 : 0.0;
+    }
+    Kr[(size_t)i * Np + j] = v;
+  }
+  if (bj == 0) {
+    for (int e = threadIdx.x; e < T; e += blockDim.x) {
+      int i = bi * T + e;
+      r[(size_t)rr * Np + i] = (i < N) ? (y[i] - h[0]) : 0.0;
+    }
+  }
+  if (t == 0 && threadIdx.x == 0) { logdet[rr] = 0.0; info[rr] = 0; }
+}
+
+// ---- step k, diagonal block: D = chol(A_kk), Dinv = D^{-1}, z_k = Dinv r_k, logdet += 2 sum log D_ii
+__global__ void __launch_bounds__(T) chol_diag_kernel(FactorBatch fb, int k) {
+  extern __shared__ __align__(16) double dsm[];
+  double (*S)[T + 1] = reinterpret_cast<double (*)[T + 1]>(dsm);
+  double (*Xi)[T + 1] = reinterpret_cast<double (*)[T + 1]>(dsm + T * (T + 1));
+  double* rs = dsm + 2 * T * (T + 1);
+  const int rr = blockIdx.x, tid = threadIdx.x;
+  const int Np = fb.Np;
+  double* A = fb.K + (size_t)rr * Np * Np + (size_t)k * T * Np + k * T;
+  for (int e = tid; e < T * T; e += T) { int i = e >> 6, j = e & 63; S[i][j] = (j <= i) ? A[(size_t)i * Np + j] : 0.0; }
+  __syncthreads();
+  for (int j = 0; j < T; ++j) {
+    const double dj = S[j][j];
+    __syncthreads();
+    double s;
+    if (dj > 0.0 && dj < INFINITY) s = sqrt(dj);
+    else { s = 1.0; if (tid == 0) atomicCAS(&fb.info[rr], 0, k * T + j + 1); }
+    const double inv = 1.0 / s;
+    // thread tid owns row tid
+    if (tid == j) S[j][j] = s;
+    double lij = 0.0;
+    if (tid > j) { lij = S[tid][j] * inv; S[tid][j] = lij; }
+    __syncthreads();
+    if (tid > j) {
+      for (int c = j + 1; c <= tid; ++c) S[tid][c] -= lij * S[c][j];
+    }
+    __syncthreads();
+  }
+  // inverse: thread c solves D x = e_c (column c of D^{-1})
+  {
+    const int c = tid;
+    for (int i = 0; i < T; ++i) {
+      double acc = (i == c) ? 1.0 : 0.0;
+      for (int j = c; j < i; ++j) acc -= S[i][j] * Xi[j][c];
+      Xi[i][c] = (i >= c) ? acc / S[i][i] : 0.0;
+    }
+  }
+  __syncthreads();
+  double* Dg = fb.Dinv + ((size_t)rr * (Np / T) + k) * T * T;
+  for (int e = tid; e < T * T; e += T) { int i = e >> 6, j = e & 63; A[(size_t)i * Np + j] = S[i][j]; Dg[e] = Xi[i][j]; }
+  // z_k = Dinv * r_k ; logdet
+  double* rk = fb.r + (size_t)rr * Np + k * T;
+  rs[tid] = rk[tid];
+  __syncthreads();
+  double z = 0.0;
+  for (int j = 0; j <= tid; ++j) z += Xi[tid][j] * rs[j];
+  rk[tid] = z;
+  double lg = log(S[tid][tid]);
+  __syncthreads();
+  rs[tid] = lg;
+  __syncthreads();
+  if (tid == 0) { double tot = 0.0; for (int j = 0; j < T; ++j) tot += rs[j]; fb.logdet[rr] += 2.0 * tot; }
+}
+
+// ---- step k, panel: L_ik = A_ik * Dinv_k^T ; r_i -= L_ik z_k        grid (nb-k-1, R)
+__global__ void __launch_bounds__(GT) chol_panel_kernel(FactorBatch fb, int k) {
+  extern __shared__ __align__(16) double sm[];
+  double* As = sm; double* Bs = sm + T * LDS_;
+  const int rr = blockIdx.y, bi = k + 1 + blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+  const int Np = fb.Np;
+  double* Kr = fb.K + (size_t)rr * Np * Np;
+  double* Aik = Kr + (size_t)bi * T * Np + k * T;
+  const double* Dg = fb.Dinv + ((size_t)rr * (Np / T) + k) * T * T;
+  load_tile_n(As, Aik, Np, tid);
+  load_tile_n(Bs, Dg, T, tid);
+  __syncthreads();
+  Acc acc; acc_zero(acc);
+  tile_mma(As, Bs, acc, wm, wn, lane);
+  __syncthreads();
+  store_acc(Aik, Np, acc, 1.0, 0.0, wm, wn, lane);
+  // stash L_ik in smem (reuse As) for the rhs update
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = wm * 32 + i * 8 + (lane >> 2), c = wn * 32 + j * 8 + 2 * (lane & 3);
+      As[r * LDS_ + c] = acc.v[i][j][0]; As[r * LDS_ + c + 1] = acc.v[i][j][1];
+    }
+  double* zk = fb.r + (size_t)rr * Np + k * T;
+  if (tid < T) Bs[tid] = zk[tid];
+  __syncthreads();
+  if (tid < T) {
+    double s = 0.0;
+    for (int c = 0; c < T; ++c) s += As[tid * LDS_ + c] * Bs[c];
+    fb.r[(size_t)rr * Np + bi * T + tid] -= s;
+  }
+}
+
+// ---- step k, trailing update: A_ij -= L_ik L_jk^T  for i >= j > k     grid (pairs, R)
+__global__ void __launch_bounds__(GT) chol_update_kernel(FactorBatch fb, int k) {
+  extern __shared__ __align__(16) double sm[];
+  double* As = sm; double* Bs = sm + T * LDS_;
+  const int rr = blockIdx.y, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+  int t = blockIdx.x;
+  int a = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= t) ++a;
+  while (a * (a + 1) / 2 > t) --a;
+  const int b = t - a * (a + 1) / 2;
+  const int bi = k + 1 + a, bj = k + 1 + b;
+  const int Np = fb.Np;
+  double* Kr = fb.K + (size_t)rr * Np * Np;
+  load_tile_n(As, Kr + (size_t)bi * T * Np + k * T, Np, tid);
+  load_tile_n(Bs, Kr + (size_t)bj * T * Np + k * T, Np, tid);
+  __syncthreads();
+  Acc acc; acc_zero(acc);
+  tile_mma(As, Bs, acc, wm, wn, lane);
+  store_acc(Kr + (size_t)bi * T * Np + bj * T, Np, acc, -1.0, 1.0, wm, wn, lane);
+}
+
+// ---- generic 64-tile GEMM used by the triangular inverse and K^{-1} -----------------------
+// C(tile mi,nj) = alpha * sum_{kt in [k0,k1)} opA(mi,kt) * opB(kt,nj)
+struct GemmDesc {
+  const double* A; int lda; int ta;   // ta=0: A[(m)*lda + k]   ta=1: A[(k)*lda + m]
+  const double* B; int ldb; int tb;   // tb=0: B[(k)*ldb + n]   tb=1: B[(n)*ldb + k]
+  double* C; int ldc;
+  double alpha;
+  int mt, nt, kt;                     // tiles
+  int tri;                            // 0: full k range; 1: k in [nj, kt) (B lower-tri, NN); 2: k in [0, mi] (A lower-tri);
+                                      // 3: k in [max(mi,nj), kt) (A^T A of lower-tri), only mi>=nj computed
+  long strideA, strideB, strideC;     // batch strides (blockIdx.y)
+};
+__global__ void __launch_bounds__(GT) gemm_tile_kernel(GemmDesc g) {
+  extern __shared__ __align__(16) double sm[];
+  double* As = sm; double* Bs = sm + T * LDS_;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+  const int mi = blockIdx.x / g.nt, nj = blockIdx.x % g.nt;
+  const double* A = g.A + (size_t)blockIdx.y * g.strideA;
+  const double* B = g.B + (size_t)blockIdx.y * g.strideB;
+  double* C = g.C + (size_t)blockIdx.y * g.strideC;
+  int k0 = 0, k1 = g.kt;
+  if (g.tri == 1) k0 = nj;
+  else if (g.tri == 2) k1 = min(g.kt, mi + 1);
+  else if (g.tri == 3) { if (mi < nj) return; k0 = mi; }
+  Acc acc; acc_zero(acc);
+  for (int kt = k0; kt < k1; ++kt) {
+    if (g.ta) load_tile_t(As, A + (size_t)kt * T * g.lda + mi * T, g.lda, tid);
+    else load_tile_n(As, A + (size_t)mi * T * g.lda + kt * T, g.lda, tid);
+    if (g.tb) load_tile_n(Bs, B + (size_t)nj * T * g.ldb + kt * T, g.ldb, tid);
+    else load_tile_t(Bs, B + (size_t)kt * T * g.ldb + nj * T, g.ldb, tid);
+    __syncthreads();
+    tile_mma(As, Bs, acc, wm, wn, lane);
+    __syncthreads();
+  }
+  store_acc(C + (size_t)mi * T * g.ldc + nj * T, g.ldc, acc, g.alpha, 0.0, wm, wn, lane);
+}
+
+__global__ void init_linv_kernel(const double* __restrict__ Dinv, int Np, double* __restrict__ Linv) {
+  // zero everything, then drop the inverted diagonal blocks in place
+  const long total = (long)Np * Np;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int i = (int)(idx / Np), j = (int)(idx - (long)i * Np);
+    double v = 0.0;
+    if ((i / T) == (j / T)) v = Dinv[((size_t)(i / T) * T + (i % T)) * T + (j % T)];
+    Linv[idx] = v;
+  }
+}
+
+// alpha[j] = sum_{i>=j} Linv[i][j] z[i]      grid Np/64, block 256 = 64 columns x 4 row groups
+__global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restrict__ Linv, int Np,
+                                                           const double* __restrict__ z, double* __restrict__ alpha) {
+  __shared__ double part[4][T];
+  const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int j = blockIdx.x * T + c;
+  double s = 0.0;
+  for (int i = blockIdx.x * T + g; i < Np; i += 4) s += Linv[(size_t)i * Np + j] * z[i];
+  part[g][c] = s;
+  __syncthreads();
+  if (g == 0) alpha[j] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+}
+
+__global__ void loglik_finish_kernel(FactorBatch fb, double* __restrict__ ll) {
+  const int rr = blockIdx.x;
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < fb.Np; i += blockDim.x) { double z = fb.r[(size_t)rr * fb.Np + i]; s += z * z; }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) {
+    double v = -0.5 * red[0] - 0.5 * fb.logdet[rr] - 0.5 * fb.N * 1.8378770664093454836;  // log(2 pi)
+    if (fb.info[rr] != 0 || !(v == v) || v == INFINITY || v == -INFINITY) v = -INFINITY;
+    ll[rr] = v;
+  }
+}
+
+// gradient reduction over the lower triangle of G = alpha alpha^T - K^{-1}:
+//   g_c   = 1/2 sum_ab G_ab Kk_ab            (d/d log_constant, dK = K_kernel)
+//   g_i   = 1/2 sum_ab G_ab Kk_ab * 1/2 D_i^2 / M_i
+// out[0] = sum alpha ; out[1] = g_c ; out[2+i] = g_i       (host drops out[1] when !fit_amp)
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restrict__ X, int N, int d, int Np,
+                                                          const double* __restrict__ Kinv,
+                                                          const double* __restrict__ alpha,
+                                                          const double* __restrict__ hyper, double* __restrict__ out) {
+  __shared__ double red[256];
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  const double amp = hyper[1];
+  double accs[APGP_MAXD + 1];
+  for (int c = 0; c <= d; ++c) accs[c] = 0.0;
+  for (int e = threadIdx.x; e < T * T; e += 256) {
+    int i = bi * T + (e >> 6), j = bj * T + (e & 63);
+    if (i < N && j <= i) {
+      double s = 0.0;
+      double df2[APGP_MAXD];
+      for (int c = 0; c < d; ++c) {
+        double df = X[(size_t)i * d + c] - X[(size_t)j * d + c];
+        df2[c] = 0.5 * df * df * hyper[3 + c];
+        s += df2[c];
+      }
+      double kk = amp * exp(-s);
+      double G = alpha[i] * alpha[j] - Kinv[(size_t)i * Np + j];
+      double w = (i == j) ? 0.5 : 1.0;        // off-diagonal pairs appear twice in the full trace
+      double gk = w * G * kk;
+      accs[0] += gk;
+      for (int c = 0; c < d; ++c) accs[1 + c] += gk * df2[c];
+    }
+  }
+  for (int c = 0; c <= d; ++c) {
+    red[threadIdx.x] = accs[c];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) atomicAdd(&out[1 + c], red[0]);
+    __syncthreads();
+  }
+  if (t == 0) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < N; i += 256) s += alpha[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) atomicAdd(&out[0], red[0]);
+  }
+}
+
+bool g_attr_done = false;
+int ensure_attrs() {
+  if (g_attr_done) return 0;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM); if (e) return (int)e;
+  e = cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
+  e = cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
+  e = cudaFuncSetAttribute(gemm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
+  g_attr_done = true;
+  return 0;
+}
+
+}  // namespace
+
+int launch_build_K(const double* X, const double* y, int N, int d, const double* hyper, const FactorBatch& fb,
+                   cudaStream_t st) {
+  const int nb = fb.Np / T;
+  dim3 grid(nb * (nb + 1) / 2, fb.R);
+  build_K_kernel<<<grid, 256, 0, st>>>(X, y, N, d, fb.Np, hyper, fb.K, fb.r, fb.logdet, fb.info);
+  return (int)cudaGetLastError();
+}
+
+int launch_cholesky(const FactorBatch& fb, int num_sms, cudaStream_t st, int* launches) {
+  (void)num_sms;
+  int e = ensure_attrs(); if (e) return e;
+  const int nb = fb.Np / T;
+  for (int k = 0; k < nb; ++k) {
+    chol_diag_kernel<<<fb.R, T, DIAG_SMEM, st>>>(fb, k);
+    if (launches) ++*launches;
+    const int rem = nb - k - 1;
+    if (rem > 0) {
+      chol_panel_kernel<<<dim3(rem, fb.R), GT, TILE_SMEM, st>>>(fb, k);
+      chol_update_kernel<<<dim3(rem * (rem + 1) / 2, fb.R), GT, TILE_SMEM, st>>>(fb, k);
+      if (launches) *launches += 2;
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+// Recursive-doubling inverse of a lower-triangular matrix whose diagonal 64-blocks are already
+// inverted:  [L11 0; L21 L22]^{-1} = [X11 0; -X22 (L21 X11)  X22].
+int launch_tri_inverse(const double* L, const double* Dinv, int Np, double* Linv, double* work, cudaStream_t st,
+                       int* launches) {
+  int e = ensure_attrs(); if (e) return e;
+  const int nb = Np / T;
+  init_linv_kernel<<<148 * 4, 256, 0, st>>>(Dinv, Np, Linv);
+  if (launches) ++*launches;
+  for (int s = 1; s < nb; s *= 2) {
+    // pairs p: first block tiles [2ps, 2ps+s), second [2ps+s, min(2ps+2s, nb))
+    for (int p0 = 0; p0 + s < nb; p0 += 2 * s) {
+      const int r2 = ((p0 + 2 * s <= nb) ? s : (nb - p0 - s));      // tiles in second block
+      const double* L21 = L + (size_t)(p0 + s) * T * Np + (size_t)p0 * T;
+      const double* X11 = Linv + (size_t)p0 * T * Np + (size_t)p0 * T;
+      const double* X22 = Linv + (size_t)(p0 + s) * T * Np + (size_t)(p0 + s) * T;
+      double* X21 = Linv + (size_t)(p0 + s) * T * Np + (size_t)p0 * T;
+      double* Tm = work + (size_t)(p0 + s) * T * Np + (size_t)p0 * T;
+      GemmDesc g1{L21, Np, 0, X11, Np, 0, Tm, Np, 1.0, r2, s, s, 1, 0, 0, 0};
+      gemm_tile_kernel<<<dim3(r2 * s, 1), GT, TILE_SMEM, st>>>(g1);
+      GemmDesc g2{X22, Np, 0, Tm, Np, 0, X21, Np, -1.0, r2, s, r2, 2, 0, 0, 0};
+      gemm_tile_kernel<<<dim3(r2 * s, 1), GT, TILE_SMEM, st>>>(g2);
+      if (launches) *launches += 2;
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+int launch_linvT_matvec(const double* Linv, int Np, const double* z, double* alpha, cudaStream_t st) {
+  linvT_matvec_kernel<<<Np / T, 256, 0, st>>>(Linv, Np, z, alpha);
+  return (int)cudaGetLastError();
+}
+
+int launch_loglik_finish(const FactorBatch& fb, double* ll, cudaStream_t st) {
+  loglik_finish_kernel<<<fb.R, 256, 0, st>>>(fb, ll);
+  return (int)cudaGetLastError();
+}
+
+int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv, const double* alpha,
+                       const double* hyper_dev, int fit_amp, double* work, double* grad_dev, cudaStream_t st,
+                       int* launches) {
+  (void)fit_amp;
+  int e = ensure_attrs(); if (e) return e;
+  const int nb = Np / T;
+  // Kinv (lower tiles) = Linv^T Linv
+  GemmDesc g{Linv, Np, 1, Linv, Np, 0, work, Np, 1.0, nb, nb, nb, 3, 0, 0, 0};
+  gemm_tile_kernel<<<dim3(nb * nb, 1), GT, TILE_SMEM, st>>>(g);
+  cudaMemsetAsync(grad_dev, 0, sizeof(double) * (2 + d), st);
+  grad_reduce_kernel<<<nb * (nb + 1) / 2, 256, 0, st>>>(X, N, d, Np, work, alpha, hyper_dev, grad_dev);
+  if (launches) *launches += 2;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace apgp

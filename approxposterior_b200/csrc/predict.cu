@@ -1,0 +1,420 @@
+// Fused GP predict for sm_100a: mean, variance and acquisition utility for a batch of queries.
+//
+// Replaces, for a whole batch of queries at once, what the reference does one query at a time:
+//   george.GP.predict(y, x, return_var=True)   called from approxposterior/utility.py:131,178,224
+//   george.GP.predict(y, x, return_var=False)  called from approxposterior/approx.py:178-180
+//   + the AGP/BAPE/Jones epilogues of approxposterior/utility.py:136,183,229-244
+//
+//   mu(q)  = m + sum_j E[q,j] * (A alpha_j)                E[q,j] = exp(-sum_i (xs_ij - qs_i)^2)
+//   var(q) = A - sum_i W[q,i]^2,   W = E . (A L^{-1})^T     (lower-triangular => only k <= i)
+//
+// Kernel structure (persistent, one CTA per SM, 8 consumer warps + 1 TMA producer warp):
+//   phase 1  the consumer warps build the K* panel E[BM x N] of the CTA's query tile on the fly
+//            from the (scaled, SoA) training set staged in shared memory, accumulate the mean,
+//            and park the panel -- already in DMMA A-fragment order -- in a per-CTA scratch
+//            slab that lives in L2.
+//   phase 2  triangular GEMM on the FP64 tensor pipe (DMMA.8x8x4): for every block-row of
+//            A L^{-1} the producer warp streams 16-wide k-steps (A tile from the slab, B tile
+//            from the fragment-tiled L^{-1}) through an NSTAGE mbarrier ring with 1-D bulk TMA
+//            (cp.async.bulk, SASS UBLKCP); the consumer warps issue DMMAs straight from the
+//            fragment-ordered tiles (conflict-free LDS.64) into register accumulators and
+//            square-reduce them into per-row sums at the end of each block-row.
+//   epilogue var = A - rowsum, box-prior gate, utility, coalesced stores.
+// The exponentials are evaluated once per (query, training point): DMMA and DFMA share one
+// FP64 pipe on B200 (profiles/r01_fp64_pipe_probe.txt), so recomputing K* per output block
+// would come straight out of the GEMM's budget.
+#include "apgp_internal.h"
+
+namespace apgp {
+
+namespace {
+
+constexpr int BK = 16;
+constexpr int NCONS_WARPS = 8;
+constexpr int NCONS = NCONS_WARPS * 32;
+constexpr int NTHREADS = NCONS + 32;
+
+template <int BM, int BN, int NSTAGE>
+struct VarCfg {
+  static constexpr int WARPS_M = BM / 32;
+  static constexpr int WARPS_N = BN / 64;
+  static_assert(WARPS_M * WARPS_N == NCONS_WARPS, "8 consumer warps, warp tile 32x64");
+  static constexpr int A_TILE = BM * BK;                 // doubles
+  static constexpr int B_TILE = BN * BK;
+  static constexpr int STAGE = A_TILE + B_TILE;
+  static constexpr int RING = NSTAGE * STAGE;            // doubles, reused as the phase-1 staging area
+  static size_t smem_bytes(int d) {
+    return (size_t)RING * 8 + (size_t)d * BM * 8 /*qs*/ + (size_t)BM * 8 /*mu_s*/ +
+           (size_t)WARPS_N * BM * 8 /*ss_s*/ + 2 * NSTAGE * 8 /*barriers*/ + 128;
+  }
+};
+
+template <int BM, int BN, int NSTAGE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+predict_var_kernel(const __grid_constant__ PredictParams p) {
+  using C = VarCfg<BM, BN, NSTAGE>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  double* qs = ring + C::RING;                          // [d][BM] scaled queries
+  double* mu_s = qs + (size_t)p.d * BM;                 // [BM]
+  double* ss_s = mu_s + BM;                             // [WARPS_N][BM]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ss_s + C::WARPS_N * BM);
+  uint64_t* empty = full + NSTAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int d = p.d, Npad = p.Npad;
+  const int nblk = Npad / BN;
+  const long long ntiles = (p.Q + BM - 1) / BM;
+  double* panel = p.scratch + (size_t)blockIdx.x * BM * Npad;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  uint32_t it = 0;   // ring position, identical sequence in producer and consumers
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long q0 = tile * BM;
+
+    // ------------------------------------------------------------ phase 1: K* panel + mean
+    if (warp < NCONS_WARPS) {
+      for (int e = tid; e < d * BM; e += NCONS) {
+        int i = e / BM, m = e - i * BM;
+        long long q = q0 + m;
+        qs[e] = (q < p.Q) ? p.Xq[q * d + i] * p.qscale[i] : 0.0;
+      }
+      // chunk of training columns staged in the (idle) ring: xs[d][JCH] + alpha[JCH]
+      int JCH = (C::RING / (d + 1)) & ~15;
+      if (JCH > Npad) JCH = Npad;
+      double mu_part[BM / 64] = {};
+      for (int j0 = 0; j0 < Npad; j0 += JCH) {
+        const int jn = min(JCH, Npad - j0);
+        named_bar_sync(1, NCONS);                      // previous chunk fully consumed / qs visible
+        for (int e = tid; e < (d + 1) * jn; e += NCONS) {
+          int i = e / jn, j = e - i * jn;
+          ring[i * JCH + j] = (i < d) ? p.Xs[(size_t)i * Npad + j0 + j] : p.alphaA[j0 + j];
+        }
+        named_bar_sync(1, NCONS);
+        const double* al = ring + d * JCH;
+#pragma unroll
+        for (int r = 0; r < BM / 64; ++r) {
+          const int mb = warp + r * NCONS_WARPS;
+          const int m = mb * 8 + (lane >> 2);
+          double macc = 0.0;
+          for (int jb = 0; jb < jn; jb += 16) {         // 4 k4-blocks per trip
+            const int jj = jb + (lane & 3);
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (int i = 0; i < d; ++i) {
+              const double qv = qs[i * BM + m];
+              const double* xr = ring + i * JCH + jj;
+              double d0 = xr[0] - qv, d1 = xr[4] - qv, d2 = xr[8] - qv, d3 = xr[12] - qv;
+              s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+            }
+            double e0 = exp(-s0), e1 = exp(-s1), e2 = exp(-s2), e3 = exp(-s3);
+            macc = fma(e0, al[jj], macc); macc = fma(e1, al[jj + 4], macc);
+            macc = fma(e2, al[jj + 8], macc); macc = fma(e3, al[jj + 12], macc);
+            double* dst = panel + ((size_t)((j0 + jb) >> 2) * (BM / 8) + mb) * 32 + lane;
+            dst[0] = e0; dst[(BM / 8) * 32] = e1; dst[2 * (BM / 8) * 32] = e2; dst[3 * (BM / 8) * 32] = e3;
+          }
+          mu_part[r] += macc;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < BM / 64; ++r) {
+        double v = mu_part[r];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if ((lane & 3) == 0) mu_s[(warp + r * NCONS_WARPS) * 8 + (lane >> 2)] = v;
+      }
+      fence_proxy_async();                             // panel stores -> visible to the TMA reads below
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ phase 2: triangular DMMA GEMM
+    if (warp == NCONS_WARPS) {
+      if (lane == 0) {
+        for (int ib = 0; ib < nblk; ++ib) {
+          const int nk = (ib + 1) * (BN / BK);
+          const double* bsrc = p.LinvF + (size_t)linvf_tile_index(ib, 0, BN) * C::B_TILE;
+          for (int kb = 0; kb < nk; ++kb, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (it / NSTAGE) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            double* dstA = ring + (size_t)s * C::STAGE;
+            mbar_arrive_expect_tx(&full[s], C::STAGE * 8);
+            bulk_g2s(dstA, panel + (size_t)kb * C::A_TILE, C::A_TILE * 8, &full[s]);
+            bulk_g2s(dstA + C::A_TILE, bsrc + (size_t)kb * C::B_TILE, C::B_TILE * 8, &full[s]);
+          }
+        }
+      }
+    } else {
+      const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+      double rowss[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int ib = 0; ib < nblk; ++ib) {
+        double acc[4][8][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+        const int nk = (ib + 1) * (BN / BK);
+        const int kdiag = ib * (BN / BK);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1u;
+          mbar_wait(&full[s], ph);
+          const double* As = ring + (size_t)s * C::STAGE + (wm * 4) * 32 + lane;
+          const double* Bs = ring + (size_t)s * C::STAGE + C::A_TILE + wn * 32 + lane;
+          if (kb < kdiag) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              double a[4], b[8];
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb) a[mb] = As[(k4 * (BM / 8) + mb) * 32];
+#pragma unroll
+              for (int nb = 0; nb < 8; ++nb) b[nb] = Bs[(k4 * (BN / 8) + nb * C::WARPS_N) * 32];
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+            }
+          } else {
+            // diagonal block: n8 fragment (columns n0..n0+7 of W) only sees k <= n
+            const int kloc = (kb - kdiag) * BK;          // k offset inside the diagonal block
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              double a[4];
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb) a[mb] = As[(k4 * (BM / 8) + mb) * 32];
+#pragma unroll
+              for (int nb = 0; nb < 8; ++nb) {
+                const int n0 = (nb * C::WARPS_N + wn) * 8;
+                if (kloc + k4 * 4 <= n0 + 7) {
+                  const double b = Bs[(k4 * (BN / 8) + nb * C::WARPS_N) * 32];
+#pragma unroll
+                  for (int mb = 0; mb < 4; ++mb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) {
+            sacc = fma(acc[mb][nb][0], acc[mb][nb][0], sacc);
+            sacc = fma(acc[mb][nb][1], acc[mb][nb][1], sacc);
+          }
+          rowss[mb] += sacc;
+        }
+      }
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        double v = rowss[mb];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if ((lane & 3) == 0) ss_s[wn * BM + wm * 32 + mb * 8 + (lane >> 2)] = v;
+      }
+      named_bar_sync(1, NCONS);
+      if (tid < BM) {
+        const long long q = q0 + tid;
+        if (q < p.Q) {
+          double tot = 0.0;
+#pragma unroll
+          for (int w = 0; w < C::WARPS_N; ++w) tot += ss_s[w * BM + tid];
+          const double mu = p.mean + mu_s[tid];
+          const double var = p.amp - tot;
+          if (p.mu) p.mu[q] = mu;
+          if (p.var) p.var[q] = var;
+          if (p.util) {
+            bool ok = true;
+            if (p.has_box) {
+              for (int i = 0; i < d; ++i) {
+                const double x = p.Xq[q * d + i];
+                ok = ok && (x >= p.lo[i]) && (x <= p.hi[i]);
+              }
+            }
+            p.util[q] = ok ? utility_eval(p.utility_kind, mu, var, p.ybest, p.zeta) : INFINITY;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mean-only predict (the emcee lnprob form, approx.py:178-180): one query per thread, training
+// set streamed through shared memory in SoA chunks; exp-bound (no GEMM).
+// ---------------------------------------------------------------------------------------------
+constexpr int MEAN_THREADS = 256;
+constexpr int MEAN_QPT = 2;                       // queries per thread
+__global__ void __launch_bounds__(MEAN_THREADS)
+predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
+  extern __shared__ __align__(16) double sm[];
+  const int d = p.d, Npad = p.Npad;
+  double* xs = sm;                                // [d+1][JCH]
+  double* qs = sm + (size_t)(d + 1) * JCH;        // [d][MEAN_QPT*MEAN_THREADS]
+  constexpr int QB = MEAN_THREADS * MEAN_QPT;
+  const int tid = threadIdx.x;
+  const long long ntiles = (p.Q + QB - 1) / QB;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long q0 = tile * QB;
+    __syncthreads();
+    for (int e = tid; e < d * QB; e += MEAN_THREADS) {
+      int m = e / d, i = e - m * d;               // coalesced read of Xq rows
+      long long q = q0 + m;
+      qs[i * QB + m] = (q < p.Q) ? p.Xq[q * d + i] * p.qscale[i] : 0.0;
+    }
+    double acc[MEAN_QPT] = {};
+    for (int j0 = 0; j0 < Npad; j0 += JCH) {
+      const int jn = min(JCH, Npad - j0);
+      __syncthreads();
+      for (int e = tid; e < (d + 1) * jn; e += MEAN_THREADS) {
+        int i = e / jn, j = e - i * jn;
+        xs[i * JCH + j] = (i < d) ? p.Xs[(size_t)i * Npad + j0 + j] : p.alphaA[j0 + j];
+      }
+      __syncthreads();
+      const double* al = xs + (size_t)d * JCH;
+      for (int j = 0; j < jn; j += 4) {
+        double s[MEAN_QPT][4] = {};
+        for (int i = 0; i < d; ++i) {
+          const double* xr = xs + i * JCH + j;
+          const double x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
+#pragma unroll
+          for (int u = 0; u < MEAN_QPT; ++u) {
+            const double qv = qs[i * QB + u * MEAN_THREADS + tid];
+            double d0 = x0 - qv, d1 = x1 - qv, d2 = x2 - qv, d3 = x3 - qv;
+            s[u][0] = fma(d0, d0, s[u][0]); s[u][1] = fma(d1, d1, s[u][1]);
+            s[u][2] = fma(d2, d2, s[u][2]); s[u][3] = fma(d3, d3, s[u][3]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < MEAN_QPT; ++u) {
+          acc[u] = fma(exp(-s[u][0]), al[j], acc[u]);
+          acc[u] = fma(exp(-s[u][1]), al[j + 1], acc[u]);
+          acc[u] = fma(exp(-s[u][2]), al[j + 2], acc[u]);
+          acc[u] = fma(exp(-s[u][3]), al[j + 3], acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < MEAN_QPT; ++u) {
+      const long long q = q0 + u * MEAN_THREADS + tid;
+      if (q < p.Q && p.mu) p.mu[q] = p.mean + acc[u];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packers (run once per factorisation)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_linv_kernel(const double* __restrict__ Linv, int ld, int N, int Npad, int BN, double amp,
+                                 double* __restrict__ out, long total) {
+  const long tile_elems = (long)BN * 16;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long t = idx / tile_elems;
+    int w = (int)(idx - t * tile_elems);
+    // invert t = (BN/16) * ib(ib+1)/2 + kb
+    const int per = BN / 16;
+    int ib = (int)((sqrt(8.0 * (double)(t / per) + 1.0) - 1.0) * 0.5);
+    while ((long)per * ((long)(ib + 1) * (ib + 2) / 2) <= t) ++ib;
+    while ((long)per * ((long)ib * (ib + 1) / 2) > t) --ib;
+    int kb = (int)(t - (long)per * ((long)ib * (ib + 1) / 2));
+    int k4 = w / (BN * 4);
+    int r = w - k4 * (BN * 4);
+    int n8 = r >> 5, l = r & 31;
+    int n = ib * BN + n8 * 8 + (l >> 2);
+    int k = kb * 16 + k4 * 4 + (l & 3);
+    double v = 0.0;
+    if (n < N && k <= n) v = amp * Linv[(size_t)n * ld + k];
+    out[idx] = v;
+  }
+}
+
+__global__ void pack_xs_kernel(const double* __restrict__ X, int N, int d, int Npad, const double* __restrict__ qscale,
+                               double* __restrict__ Xs) {
+  long total = (long)d * Npad;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int i = (int)(idx / Npad), j = (int)(idx - (long)i * Npad);
+    Xs[idx] = (j < N) ? X[(size_t)j * d + i] * qscale[i] : 0.0;
+  }
+}
+
+template <int BM, int BN, int NSTAGE>
+int launch_var_t(const PredictParams& p, int num_sms, cudaStream_t st) {
+  using C = VarCfg<BM, BN, NSTAGE>;
+  const size_t smem = C::smem_bytes(p.d);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(predict_var_kernel<BM, BN, NSTAGE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  long long ntiles = (p.Q + BM - 1) / BM;
+  int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  if (grid < 1) return 0;
+  predict_var_kernel<BM, BN, NSTAGE><<<grid, NTHREADS, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+static inline int variant_bm(int v) { return v == 1 ? 128 : 64; }
+static inline int variant_bn(int v) { return v == 1 ? 128 : 256; }
+int predict_variant_bn(int variant) { return variant_bn(variant); }
+
+size_t predict_scratch_bytes(int Npad, int num_sms, int variant) {
+  return (size_t)num_sms * variant_bm(variant) * Npad * 8;
+}
+
+int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches) {
+  if (p.Q <= 0) return 0;
+  if (launches) ++*launches;
+  if (variant == 1) return launch_var_t<128, 128, 5>(p, num_sms, st);
+  return launch_var_t<64, 256, 4>(p, num_sms, st);
+}
+
+int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, int* launches) {
+  if (p.Q <= 0) return 0;
+  constexpr int QB = MEAN_THREADS * MEAN_QPT;
+  const size_t qs_bytes = (size_t)p.d * QB * 8;
+  int JCH = (int)(((96 * 1024 - qs_bytes) / 8) / (p.d + 1)) & ~3;
+  if (JCH > p.Npad) JCH = p.Npad;
+  if (JCH < 4) return (int)cudaErrorInvalidValue;
+  const size_t smem = (size_t)(p.d + 1) * JCH * 8 + qs_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(predict_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  long long ntiles = (p.Q + QB - 1) / QB;
+  long long cap = (long long)num_sms * 2;
+  int grid = (int)(ntiles < cap ? ntiles : cap);
+  predict_mean_kernel<<<grid, MEAN_THREADS, smem, st>>>(p, JCH);
+  if (launches) ++*launches;
+  return (int)cudaGetLastError();
+}
+
+int launch_pack_linv(const double* Linv, int ld, int N, int Npad, int BN, double amp, double* LinvF, cudaStream_t st) {
+  long total = linvf_total_tiles(Npad, BN) * (long)BN * 16;
+  int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+  pack_linv_kernel<<<grid, 256, 0, st>>>(Linv, ld, N, Npad, BN, amp, LinvF, total);
+  return (int)cudaGetLastError();
+}
+
+int launch_pack_xs(const double* X, int N, int d, int Npad, const double* qscale_dev, double* Xs, cudaStream_t st) {
+  long total = (long)d * Npad;
+  int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+  pack_xs_kernel<<<grid, 256, 0, st>>>(X, N, d, Npad, qscale_dev, Xs);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace apgp

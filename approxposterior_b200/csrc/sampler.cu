@@ -1,0 +1,214 @@
+// Device-resident affine-invariant ensemble sampler (Goodman & Weare stretch move, red/blue
+// split) over the GP-surrogate posterior mean.  One CTA owns one independent ensemble for the
+// whole chain; ensembles never talk to each other, so a grid of CTAs needs no grid-wide sync.
+//
+// Replaces emcee.EnsembleSampler(...).sample(...) as driven from reference approx.py:839-847
+// with log_prob_fn = ApproxPosterior._gpll (approx.py:148-189):
+//   lnprob(q) = -inf                          if q non-finite or outside the (box) prior
+//             = m + k*(q)^T alpha             otherwise (mean-only predict, approx.py:178-180)
+//   blob      = lnprior (nan when rejected)   (approx.py:188, blobs_dtype approx.py:843)
+// Per iteration (emcee 3.0.x RedBlueMove/StretchMove): shuffle colours, then for each colour
+//   zz = ((a-1)u+1)^2/a ; q = c[r] - (c[r]-s) zz ; accept iff (d-1)ln zz + lp(q) - lp(s) > ln u'.
+// Random draws come from Philox4x32-10, or from replay buffers recorded by the CPU oracle so
+// that chains can be compared draw-for-draw.
+#include "apgp_internal.h"
+
+namespace apgp {
+namespace {
+
+struct Smem {
+  double* xs;      // [d+1][Npad] (alphaA is row d) or null when it does not fit
+  double* coords;  // [nw][d]
+  double* lp;      // [nw]
+  double* blob;    // [nw]
+  double* q;       // [nw][d]   proposals (initial pass evaluates all nw walkers)
+  double* nlp;     // [nw]
+  double* fac;     // [nw]
+  double* logu;    // [nw]
+  int* colour;     // [nw]
+  int* sidx;       // [nw]
+  int* cidx;       // [nw]
+  int* ok;         // [nw]
+};
+
+// lnprob for the `np` rows of sm.q (warp per row, lanes over training points)
+__device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int d = p.d, Npad = p.Npad;
+  for (int i = warp; i < np; i += nwarps) {
+    double acc = 0.0;
+    const int oki = sm.ok[i];
+    __syncwarp();
+    if (oki) {
+      if (sm.xs) {
+        const double* al = sm.xs + (size_t)d * Npad;
+        for (int j = lane; j < p.N; j += 32) {
+          double s = 0.0;
+          for (int c = 0; c < d; ++c) { double df = sm.xs[c * Npad + j] - sm.q[i * d + c] * p.qscale[c]; s = fma(df, df, s); }
+          acc = fma(exp(-s), al[j], acc);
+        }
+      } else {
+        for (int j = lane; j < p.N; j += 32) {
+          double s = 0.0;
+          for (int c = 0; c < d; ++c) { double df = p.Xs[(size_t)c * Npad + j] - sm.q[i * d + c] * p.qscale[c]; s = fma(df, df, s); }
+          acc = fma(exp(-s), p.alphaA[j], acc);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0) {
+      double mu = p.mean + acc;
+      bool fin = oki && (mu == mu) && (fabs(mu) < INFINITY);
+      sm.nlp[i] = fin ? mu : -INFINITY;
+      sm.ok[i] = fin ? 1 : 0;
+    }
+  }
+}
+
+__device__ __forceinline__ int prior_ok(const SamplerParams& p, const double* x) {
+  int ok = 1;
+  for (int c = 0; c < p.d; ++c) {
+    double v = x[c];
+    ok = ok && (v == v) && (v >= p.lo[c]) && (v <= p.hi[c]);
+  }
+  return ok;
+}
+
+__global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ SamplerParams p, int xs_in_smem) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const int nw = p.nwalk, d = p.d, Ns = nw / 2, Npad = p.Npad;
+  const long W = (long)p.nens * nw;
+  Smem sm;
+  double* f = reinterpret_cast<double*>(raw);
+  sm.xs = nullptr;
+  if (xs_in_smem) { sm.xs = f; f += (size_t)(d + 1) * Npad; }
+  sm.coords = f; f += nw * d;
+  sm.lp = f; f += nw;
+  sm.blob = f; f += nw;
+  sm.q = f; f += nw * d;
+  sm.nlp = f; f += nw;
+  sm.fac = f; f += nw;
+  sm.logu = f; f += nw;
+  int* ip = reinterpret_cast<int*>(f);
+  sm.colour = ip; ip += nw;
+  sm.sidx = ip; ip += nw;
+  sm.cidx = ip; ip += nw;
+  sm.ok = ip; ip += nw;
+
+  if (xs_in_smem) {
+    for (int idx = tid; idx < (d + 1) * Npad; idx += blockDim.x)
+      sm.xs[idx] = (idx < d * Npad) ? p.Xs[idx] : p.alphaA[idx - d * Npad];
+  }
+  for (int idx = tid; idx < nw * d; idx += blockDim.x) {
+    double v = p.p0[(size_t)e * nw * d + idx];
+    sm.coords[idx] = v; sm.q[idx] = v;
+  }
+  __syncthreads();
+  for (int w = tid; w < nw; w += blockDim.x) sm.ok[w] = prior_ok(p, sm.q + w * d);
+  __syncthreads();
+  eval_rows(p, sm, nw);
+  __syncthreads();
+  for (int w = tid; w < nw; w += blockDim.x) { sm.lp[w] = sm.nlp[w]; sm.blob[w] = sm.ok[w] ? p.lnprior_const : NAN; }
+  __syncthreads();
+
+  Philox rng; rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
+  const bool replay = p.r_zz != nullptr;
+
+  for (int step = 0; step < p.nsteps; ++step) {
+    // ---- colours
+    if (replay) {
+      for (int w = tid; w < nw; w += blockDim.x) sm.colour[w] = p.r_inds[((size_t)e * p.nsteps + step) * nw + w];
+    } else if (tid == 0) {
+      for (int w = 0; w < nw; ++w) sm.colour[w] = w & 1;
+      for (int i = nw - 1; i >= 1; --i) {          // Fisher-Yates
+        uint32_t o[4]; rng.gen((uint32_t)e, (uint32_t)step, 0x10000u, (uint32_t)i, o);
+        int j = (int)(((uint64_t)o[0] * (uint64_t)(i + 1)) >> 32);
+        int t = sm.colour[i]; sm.colour[i] = sm.colour[j]; sm.colour[j] = t;
+      }
+    }
+    __syncthreads();
+    for (int split = 0; split < 2; ++split) {
+      if (tid == 0) {
+        int a = 0, b = 0;
+        for (int w = 0; w < nw; ++w) { if (sm.colour[w] == split) sm.sidx[a++] = w; else sm.cidx[b++] = w; }
+      }
+      __syncthreads();
+      for (int i = tid; i < Ns; i += blockDim.x) {
+        double zz, lu; int r;
+        if (replay) {
+          size_t off = (((size_t)e * p.nsteps + step) * 2 + split) * Ns + i;
+          zz = p.r_zz[off]; r = p.r_rint[off]; lu = p.r_logu[off];
+        } else {
+          uint32_t o[4], o2[4];
+          rng.gen((uint32_t)e, (uint32_t)step, (uint32_t)split, (uint32_t)i, o);
+          rng.gen((uint32_t)e, (uint32_t)step, (uint32_t)(split + 2), (uint32_t)i, o2);
+          double u = u01_from_bits(o[0], o[1]);
+          double t = (p.a - 1.0) * u + 1.0;
+          zz = t * t / p.a;
+          lu = log(u01_from_bits(o[2], o[3]));
+          r = (int)(((uint64_t)o2[0] * (uint64_t)Ns) >> 32);
+        }
+        const double* cs = sm.coords + sm.cidx[r] * d;
+        const double* ss = sm.coords + sm.sidx[i] * d;
+        for (int c = 0; c < d; ++c) sm.q[i * d + c] = cs[c] - (cs[c] - ss[c]) * zz;
+        sm.fac[i] = (d - 1.0) * log(zz);
+        sm.logu[i] = lu;
+        sm.ok[i] = prior_ok(p, sm.q + i * d);
+      }
+      __syncthreads();
+      eval_rows(p, sm, Ns);
+      __syncthreads();
+      for (int i = tid, k = 0; i < Ns; i += blockDim.x, ++k) {
+        const int j = sm.sidx[i];
+        const double diff = sm.fac[i] + sm.nlp[i] - sm.lp[j];
+        if (diff > sm.logu[i]) {
+          for (int c = 0; c < d; ++c) sm.coords[j * d + c] = sm.q[i * d + c];
+          sm.lp[j] = sm.nlp[i];
+          sm.blob[j] = sm.ok[i] ? p.lnprior_const : NAN;
+          atomicAdd(&p.naccept[(size_t)e * nw + j], 1);
+        }
+      }
+      __syncthreads();
+    }
+    if ((step + 1) % p.thin == 0) {
+      const long srow = (step + 1) / p.thin - 1;
+      for (int idx = tid; idx < nw * d; idx += blockDim.x)
+        p.chain[(srow * W + (size_t)e * nw) * d + idx] = sm.coords[idx];
+      for (int w = tid; w < nw; w += blockDim.x) {
+        p.logp[srow * W + (size_t)e * nw + w] = sm.lp[w];
+        p.blob[srow * W + (size_t)e * nw + w] = sm.blob[w];
+      }
+    }
+    // no sync needed: next writes to coords happen after the next __syncthreads chain
+  }
+  if (p.final_state) {
+    __syncthreads();
+    for (int idx = tid; idx < nw * d; idx += blockDim.x) p.final_state[(size_t)e * nw * d + idx] = sm.coords[idx];
+  }
+}
+
+}  // namespace
+
+int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
+  if (p.nwalk < 2 || (p.nwalk & 1) || p.nwalk > 1024 || p.nens < 1) return (int)cudaErrorInvalidValue;
+  const size_t small = (size_t)p.nwalk * (2 * p.d + 5) * 8 + (size_t)p.nwalk * 4 * 4 + 64;
+  const size_t xs_bytes = (size_t)(p.d + 1) * p.Npad * 8;
+  int xs_in_smem = (small + xs_bytes <= 200 * 1024) ? 1 : 0;
+  const size_t smem = small + (xs_in_smem ? xs_bytes : 0);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  int Ns = p.nwalk / 2;
+  int nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : 8;
+  cudaMemsetAsync(p.naccept, 0, sizeof(int) * (size_t)p.nens * p.nwalk, st);
+  sampler_kernel<<<p.nens, nwarps * 32, smem, st>>>(p, xs_in_smem);
+  if (launches) ++*launches;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace apgp

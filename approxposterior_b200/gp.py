@@ -1,0 +1,324 @@
+"""``GP``: the george.GP duck type approxposterior drives, backed by libapgp on a B200.
+
+Surface kept (reference call sites):
+  ctor      ``GP(kernel=, fit_mean=True, mean=, white_noise=, fit_white_noise=False)``  gpUtils.py:176-177, approx.py:712-715
+  compute / recompute / computed                                                     gpUtils.py:178,244,254; utility.py:130
+  predict(y, t, return_cov=False, return_var=False|True)                             approx.py:178-180; utility.py:131,178,224
+  log_likelihood(y, quiet=True) / grad_log_likelihood(y, quiet=True)                 gpUtils.py:78,110,247
+  get/set_parameter_vector, get_parameter_names, len()                               gpUtils.py:74,227,243; approx.py:431,706,716
+  kernel / mean / white_noise attributes                                             approx.py:712-714
+
+Batched extras (the data-parallel form of the same calls):
+  predict(..) accepts any number of query rows, NumPy (host) or torch CUDA tensors;
+  ``predict_utility`` fuses the AGP/BAPE/Jones epilogue and the box-prior gate;
+  ``log_likelihood_batch`` evaluates many hyper-parameter vectors at once;
+  ``run_ensembles`` runs the device-resident stretch-move sampler.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .kernels import ExpSquaredKernel, Product
+
+__all__ = ["GP"]
+
+
+def _default_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+def _is_torch(a):
+    return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
+
+
+class GP(object):
+    def __init__(self, kernel=None, fit_mean=False, mean=0.0, white_noise=-12.0, fit_white_noise=False,
+                 device=None, **kwargs):
+        if kernel is None or not isinstance(kernel, (ExpSquaredKernel, Product)):
+            raise NotImplementedError("the B200 engine supports ExpSquaredKernel, optionally scaled by a constant")
+        if fit_white_noise:
+            raise NotImplementedError("white noise is frozen on this path (fit_white_noise=False, gpUtils.py:177)")
+        if kwargs.get("solver") is not None:
+            raise NotImplementedError("only the dense (BasicSolver-equivalent) factorisation is implemented")
+        mean = float(np.asarray(mean))
+        self.kernel = kernel
+        self.fit_mean = bool(fit_mean)
+        self.mean = float(mean)
+        self.white_noise = float(white_noise)
+        self.fit_white_noise = False
+        self.computed = False
+        self._dirty = True
+        self._x = None
+        self._y = None
+        self._device = _default_device() if device is None else int(device)
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.apgp_create(C.byref(h), self._device), "apgp_create")
+        self._h = h
+        self._logdet = np.nan
+        self._loglik = -np.inf
+        self._training_uploaded = False
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.apgp_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ parameters
+    def __len__(self):
+        return (1 if self.fit_mean else 0) + len(self.kernel)
+
+    def get_parameter_names(self):
+        names = ("mean:value",) if self.fit_mean else ()
+        return names + tuple("kernel:" + n for n in self.kernel.get_parameter_names())
+
+    def get_parameter_vector(self):
+        head = [self.mean] if self.fit_mean else []
+        return np.concatenate([head, self.kernel.get_parameter_vector()]).astype(np.float64)
+
+    def set_parameter_vector(self, p):
+        p = np.asarray(p, dtype=np.float64).ravel()
+        if p.size != len(self):
+            raise ValueError("dimension mismatch: expected %d parameters, got %d" % (len(self), p.size))
+        k = 0
+        if self.fit_mean:
+            self.mean = float(p[0])
+            k = 1
+        self.kernel.set_parameter_vector(p[k:])
+        self._dirty = True
+
+    @property
+    def ndim(self):
+        return self.kernel.ndim
+
+    @property
+    def log_determinant(self):
+        return self._logdet
+
+    @property
+    def launch_count(self):
+        return int(self._lib.apgp_launch_count(self._h))
+
+    # ------------------------------------------------------------------ factorisation
+    def _parse(self, t):
+        t = np.asarray(t, dtype=np.float64)
+        if t.ndim == 0:
+            t = t.reshape(1, 1)
+        elif t.ndim == 1:
+            t = t.reshape(-1, 1)
+        if t.ndim != 2 or t.shape[1] != self.ndim:
+            raise ValueError("dimension mismatch")
+        return np.ascontiguousarray(t)
+
+    def compute(self, x, yerr=None, y=None, **kwargs):
+        """george.GP.compute(x).  ``y`` is an optional hint (george only sees y at predict time);
+        when it is omitted the factorisation is finished on the first call that supplies y."""
+        self._x = self._parse(x)
+        self._y = None if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+        if self._y is not None and self._y.size != self._x.shape[0]:
+            raise ValueError("dimension mismatch")
+        self._training_uploaded = False
+        self._dirty = True
+        self.computed = False
+        self.recompute()
+
+    def _upload_training(self):
+        y = self._y if self._y is not None else np.zeros(self._x.shape[0])
+        _lib.check(self._lib.apgp_set_training(self._h, _lib.ptr(self._x), _lib.ptr(y), self._x.shape[0],
+                                               self.ndim, 1), "apgp_set_training")
+        self._training_uploaded = True
+
+    def recompute(self, quiet=False, **kwargs):
+        if not self._dirty and self.computed:
+            return True
+        if self._x is None:
+            raise RuntimeError("You need to compute the model first")
+        if not self._training_uploaded:
+            self._upload_training()
+        logM = np.ascontiguousarray(self.kernel.log_M, dtype=np.float64)
+        _lib.check(self._lib.apgp_set_hyper(self._h, self.mean, float(self.kernel.amplitude), _lib.ptr(logM),
+                                            self.white_noise), "apgp_set_hyper")
+        logdet, ll, info = C.c_double(), C.c_double(), C.c_int()
+        st = _lib.check(self._lib.apgp_factorize(self._h, C.byref(logdet), C.byref(ll), C.byref(info)),
+                        "apgp_factorize")
+        if st == _lib.APGP_NOT_POSDEF:
+            self.computed = False
+            self._loglik = -np.inf
+            if quiet:
+                return False
+            raise np.linalg.LinAlgError("covariance matrix is not positive definite (pivot %d)" % info.value)
+        self._logdet, self._loglik = logdet.value, ll.value
+        self.computed = True
+        self._dirty = False
+        return True
+
+    def _sync_y(self, y):
+        """Make the device-side y (hence alpha and the stored log-likelihood) match ``y``."""
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+        if self._x is None:
+            raise RuntimeError("You need to compute the model first")
+        if y.size != self._x.shape[0]:
+            raise ValueError("dimension mismatch")
+        if self._y is None or not np.array_equal(y, self._y):
+            self._y = y.copy()
+            self._training_uploaded = False
+            self._dirty = True
+
+    # ------------------------------------------------------------------ predict
+    def _predict_raw(self, t, want_var, utility=None, bounds=None, ybest=0.0, zeta=0.01, want_mu=True):
+        opts = _lib.PredictOpts()
+        opts.want_var = 1 if want_var else 0
+        opts.utility = _lib.UTIL_KINDS[utility]
+        opts.ybest, opts.zeta = float(ybest), float(zeta)
+        if bounds is not None:
+            opts.has_box = 1
+            _lib.fill_bounds(opts.lo, opts.hi, bounds, self.ndim)
+        if _is_torch(t):
+            import torch
+            if not t.is_cuda or t.dtype != torch.float64:
+                raise ValueError("torch queries must be float64 CUDA tensors")
+            if t.dim() != 2 or t.shape[1] != self.ndim:
+                raise ValueError("dimension mismatch")
+            t = t.contiguous()
+            Q = t.shape[0]
+            mk = lambda: torch.empty(Q, dtype=torch.float64, device=t.device)
+            on_host = 0
+            # order the engine's stream after the producer of `t`, and torch after the engine
+            _lib.check(self._lib.apgp_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)),
+                       "apgp_set_stream")
+        else:
+            t = self._parse(t)
+            Q = t.shape[0]
+            mk = lambda: np.empty(Q, dtype=np.float64)
+            on_host = 1
+        mu = mk() if want_mu else None
+        var = mk() if want_var else None
+        util = mk() if utility not in (None, "none") else None
+        _lib.check(self._lib.apgp_predict(self._h, _lib.ptr(t), Q, _lib.ptr(mu), _lib.ptr(var), _lib.ptr(util),
+                                          C.byref(opts), on_host), "apgp_predict")
+        return mu, var, util
+
+    def predict(self, y, t, return_cov=True, return_var=False, **kwargs):
+        """george.GP.predict; only the forms approxposterior uses (return_cov=False) are provided."""
+        if return_cov and not return_var:
+            raise NotImplementedError("predictive covariance matrices are not used by approxposterior "
+                                      "(approx.py:178-180, utility.py:131); pass return_cov=False")
+        self._sync_y(y)
+        self.recompute()
+        mu, var, _ = self._predict_raw(t, want_var=bool(return_var))
+        if return_var:
+            return mu, var
+        return mu
+
+    def predict_utility(self, y, t, utility, bounds=None, zeta=0.01):
+        """(mu, var, util) for every row of ``t`` with the reference's utility epilogue fused in
+        (utility.py:136,183,229-244) and ``+inf`` outside ``bounds`` (the priorFn gate)."""
+        self._sync_y(y)
+        self.recompute()
+        return self._predict_raw(t, True, utility=str(utility).lower(), bounds=bounds,
+                                 ybest=float(np.max(self._y)), zeta=zeta)
+
+    # ------------------------------------------------------------------ likelihood
+    def log_likelihood(self, y, quiet=False):
+        self._sync_y(y)
+        if not self.recompute(quiet=quiet):
+            return -np.inf
+        ll = self._loglik
+        return ll if np.isfinite(ll) else -np.inf
+
+    lnlikelihood = log_likelihood
+
+    def nll(self, vector, y, quiet=True):
+        self.set_parameter_vector(vector)
+        return -self.log_likelihood(y, quiet=quiet)
+
+    def grad_log_likelihood(self, y, quiet=False):
+        self._sync_y(y)
+        if not self.recompute(quiet=quiet):
+            return np.zeros(len(self))
+        fit_amp = 1 if self.kernel.fit_amp else 0
+        g = np.zeros(1 + fit_amp + self.ndim)
+        _lib.check(self._lib.apgp_grad_log_likelihood(self._h, fit_amp, _lib.ptr(g)), "apgp_grad_log_likelihood")
+        return g if self.fit_mean else g[1:]
+
+    def log_likelihood_batch(self, P, y):
+        """log-likelihood of ``y`` for every row of ``P`` (george parameter-vector layout) in one
+        batched device pass; ``-inf`` where the covariance is not positive definite
+        (the quiet=True convention of gpUtils._nll, gpUtils.py:78-79).  Leaves the GP untouched."""
+        P = np.ascontiguousarray(np.atleast_2d(np.asarray(P, dtype=np.float64)))
+        if P.shape[1] != len(self):
+            raise ValueError("dimension mismatch")
+        self._sync_y(y)
+        if not self._training_uploaded:
+            self._upload_training()
+        fit_amp = 1 if self.kernel.fit_amp else 0
+        if not self.fit_mean:
+            P = np.ascontiguousarray(np.hstack([np.full((P.shape[0], 1), self.mean), P]))
+        ll = np.empty(P.shape[0])
+        _lib.check(self._lib.apgp_loglik_batch(self._h, _lib.ptr(P), P.shape[0], P.shape[1], fit_amp,
+                                               self.white_noise, _lib.ptr(ll)), "apgp_loglik_batch")
+        return ll
+
+    # ------------------------------------------------------------------ sampler
+    def run_ensembles(self, y, p0, nsteps, bounds, nens=1, a=2.0, seed=0, thin=1, lnprior_const=0.0, replay=None):
+        """Device-resident stretch-move sampling of the surrogate posterior mean (emcee as driven
+        from approx.py:839-847).  ``p0`` is (nens*nwalkers, ndim); returns dict(chain, log_prob,
+        blobs, naccepted) with chain shaped (nsteps//thin, nens*nwalkers, ndim)."""
+        self._sync_y(y)
+        self.recompute()
+        p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, self.ndim))
+        W = p0.shape[0]
+        if W % nens:
+            raise ValueError("p0 rows must be a multiple of nens")
+        nw = W // nens
+        o = _lib.SamplerOpts()
+        o.nens, o.nwalkers, o.nsteps, o.thin = int(nens), int(nw), int(nsteps), int(thin)
+        o.a, o.seed, o.lnprior_const = float(a), int(seed) & (2**64 - 1), float(lnprior_const)
+        _lib.fill_bounds(o.lo, o.hi, bounds, self.ndim)
+        keep = []
+        if replay is not None:
+            ri = np.ascontiguousarray(replay["inds"], dtype=np.int32)
+            rz = np.ascontiguousarray(replay["zz"], dtype=np.float64)
+            rr = np.ascontiguousarray(replay["rint"], dtype=np.int32)
+            rl = np.ascontiguousarray(replay["logu"], dtype=np.float64)
+            keep = [ri, rz, rr, rl]
+            o.replay_inds, o.replay_zz, o.replay_rint, o.replay_logu = (_lib.ptr(ri), _lib.ptr(rz), _lib.ptr(rr),
+                                                                         _lib.ptr(rl))
+        ns = nsteps // thin
+        chain = np.empty((ns, W, self.ndim))
+        logp = np.empty((ns, W))
+        blob = np.empty((ns, W))
+        nacc = np.zeros(W, dtype=np.int32)
+        _lib.check(self._lib.apgp_sampler_run(self._h, C.byref(o), _lib.ptr(p0), _lib.ptr(chain), _lib.ptr(logp),
+                                              _lib.ptr(blob), _lib.ptr(nacc), 1), "apgp_sampler_run")
+        del keep
+        return dict(chain=chain, log_prob=logp, blobs=blob, naccepted=nacc)
+
+    # ------------------------------------------------------------------ diagnostics (tests)
+    def _alpha(self):
+        a = np.empty(self._x.shape[0])
+        _lib.check(self._lib.apgp_get_alpha(self._h, _lib.ptr(a)), "apgp_get_alpha")
+        return a
+
+    def _linv(self):
+        n = self._x.shape[0]
+        a = np.empty((n, n))
+        _lib.check(self._lib.apgp_get_linv(self._h, _lib.ptr(a)), "apgp_get_linv")
+        return a
+
+    def _chol(self):
+        n = self._x.shape[0]
+        a = np.empty((n, n))
+        _lib.check(self._lib.apgp_get_chol(self._h, _lib.ptr(a)), "apgp_get_chol")
+        return a

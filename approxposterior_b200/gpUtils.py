@@ -1,0 +1,127 @@
+"""Gaussian-process utilities: mirror of reference ``approxposterior/gpUtils.py`` on the B200 engine.
+
+Same names, arguments and error behaviour as the reference functions (file:line cited per
+function); the GP object is ``approxposterior_b200.GP`` instead of ``george.GP`` and the
+restarts of ``optimizeGP`` are evaluated side by side on the device.
+"""
+import numpy as np
+from scipy.optimize import minimize
+
+from . import kernels
+from ._lockstep import run_lockstep
+from .gp import GP
+
+__all__ = ["defaultHyperPrior", "defaultGP", "optimizeGP"]
+
+
+def defaultHyperPrior(p):
+    """Flat prior keeping every log hyper-parameter in [-20, 20]; the mean (p[0]) is free.
+    Reference gpUtils.py:22-43."""
+    p = np.asarray(p, dtype=np.float64)
+    if np.any(np.fabs(p)[1:] > 20):
+        return -np.inf
+    return 0.0
+
+
+def _nll(p, gp, y, priorFn=None):
+    """Negative log-likelihood of y under gp at hyper-parameters p (reference gpUtils.py:46-80):
+    +inf if the prior rejects p, the covariance is singular, or the likelihood is not finite."""
+    if priorFn is not None:
+        if not np.isfinite(priorFn(p)):
+            return np.inf
+    try:
+        gp.set_parameter_vector(p)
+    except np.linalg.LinAlgError:
+        return np.inf
+    ll = gp.log_likelihood(y, quiet=True)
+    return -ll if np.isfinite(ll) else np.inf
+
+
+def _grad_nll(p, gp, y, priorFn=None):
+    """Gradient of ``_nll`` (reference gpUtils.py:83-111)."""
+    if priorFn is not None:
+        if not np.isfinite(priorFn(p)):
+            return np.full_like(p, np.inf)
+    gp.set_parameter_vector(p)
+    return -gp.grad_log_likelihood(y, quiet=True)
+
+
+def _nll_batch(P, gp, y, priorFn=None):
+    """``_nll`` for a list of parameter vectors with one batched device evaluation."""
+    P = [np.asarray(p, dtype=np.float64) for p in P]
+    ok = np.array([priorFn is None or np.isfinite(priorFn(p)) for p in P], dtype=bool)
+    out = np.full(len(P), np.inf)
+    if np.any(ok):
+        ll = gp.log_likelihood_batch(np.array([p for p, k in zip(P, ok) if k]), y)
+        out[ok] = np.where(np.isfinite(ll), -ll, np.inf)
+    return out
+
+
+def defaultGP(theta, y, order=None, white_noise=-12, fitAmp=False):
+    """ExpSquared GP with a fitted constant mean and frozen white noise, factorised on theta.
+    Reference gpUtils.py:114-181 (consumes one ``np.random.randn(ndim)`` for the initial metric).
+    ``order`` (the reference's optional LinearKernel term) is outside the engine's scope."""
+    theta = np.asarray(theta).squeeze()
+    y = np.asarray(y).squeeze()
+    ndim = 1 if theta.ndim <= 1 else theta.shape[-1]
+
+    initialMetric = np.fabs(np.random.randn(ndim))
+    kernel = kernels.ExpSquaredKernel(metric=initialMetric, ndim=ndim)
+    if fitAmp:
+        kernel = np.var(y) * kernel
+    if order is not None:
+        raise NotImplementedError("defaultGP(order=...) adds a LinearKernel (gpUtils.py:169-173); the B200 engine "
+                                  "covers the ExpSquared path only")
+    gp = GP(kernel=kernel, fit_mean=True, mean=np.median(y), white_noise=white_noise, fit_white_noise=False)
+    gp.compute(theta, y=np.atleast_1d(y))
+    return gp
+
+
+def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=None, p0=None,
+               gpHyperPrior=defaultHyperPrior, batched=True):
+    """Maximise the marginal likelihood over nGPRestarts starts (reference gpUtils.py:184-257).
+
+    Start points are drawn exactly as the reference draws them (one ``np.random.randn()`` per
+    kernel parameter per restart, gpUtils.py:227; ``seed`` is accepted and unused, as there).
+    With ``batched`` (default) and a derivative-free method the restarts advance in lock step and
+    every round of objective calls is one ``log_likelihood_batch`` launch; gradient methods use
+    the single-GP ``grad_log_likelihood`` path sequentially.
+    """
+    y = np.asarray(y, dtype=np.float64)
+    npar = len(gp.get_parameter_vector())
+    x0s = []
+    for _ in range(nGPRestarts):
+        if p0 is None:
+            x0 = [np.median(y)] + [np.random.randn() for _ in range(npar - 1)]
+        else:
+            x0 = np.array(p0) + np.min(p0) * 1.0e-3 * np.random.randn(len(p0))
+        x0s.append(np.asarray(x0, dtype=np.float64))
+
+    derivative_free = method in ["nelder-mead", "powell", "cg"]
+    use_batch = batched and derivative_free and hasattr(gp, "log_likelihood_batch")
+
+    if use_batch:
+        def worker(wid, f):
+            return minimize(f, x0s[wid], method=method, jac=None, bounds=None, options=options)["x"]
+
+        res, ev = run_lockstep(nGPRestarts, lambda P: _nll_batch(P, gp, y, gpHyperPrior), worker)
+        optimizeGP.last_stats = dict(batches=ev.nbatches, evals=ev.nevals)
+        mll = list(gp.log_likelihood_batch(np.array(res), y))
+    else:
+        res, mll = [], []
+        jac = None if derivative_free else _grad_nll
+        for x0 in x0s:
+            resii = minimize(_nll, x0, args=(gp, y, gpHyperPrior), method=method, jac=jac, bounds=None,
+                             options=options)["x"]
+            res.append(resii)
+            gp.set_parameter_vector(resii)
+            gp.recompute(quiet=True)
+            mll.append(gp.log_likelihood(y, quiet=True))
+
+    ind = np.argmax(mll)
+    gp.set_parameter_vector(res[ind])
+    gp.recompute()
+    return gp
+
+
+optimizeGP.last_stats = None

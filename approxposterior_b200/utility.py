@@ -1,0 +1,207 @@
+"""Acquisition utilities and their multistart minimiser: mirror of reference ``utility.py``.
+
+Scalar functions keep the reference's signatures ``fn(theta, y, gp, priorFn)`` and return values
+(+inf outside the prior, the naive ``logsubexp``, Jones returning 0.0 when std <= 0).  On an
+``approxposterior_b200.GP`` the (mu, var) -> utility epilogue is evaluated inside the fused predict
+kernel; ``utilityBatch`` and ``minimizeObjective`` push all live optimiser restarts -- or a whole
+candidate cloud -- through one launch.
+"""
+import numpy as np
+from scipy.optimize import minimize
+from scipy.special import ndtr
+
+from ._lockstep import run_lockstep
+
+__all__ = ["logsubexp", "AGPUtility", "BAPEUtility", "JonesUtility", "minimizeObjective", "klNumerical",
+           "utilityBatch", "scanUtility"]
+
+
+def klNumerical(x, p, q):
+    """Monte-Carlo KL estimate mean(log p/q) over samples x ~ p (reference utility.py:26-66)."""
+    try:
+        res = np.sum(np.log(p(x) / q(x))) / len(x)
+    except ValueError:
+        raise ValueError("ERROR: inf/NaN encountered.  q(x) = 0 likely occured.")
+    return res
+
+
+def logsubexp(x1, x2):
+    """log(exp(x1) - exp(x2)), written as the reference writes it (utility.py:69-89)."""
+    if x1 <= x2:
+        return -np.inf
+    else:
+        return x1 + np.log(1.0 - np.exp(x2 - x1))
+
+
+def _mu_var(theta, y, gp, kind):
+    """(mu, var, util-or-None) of one point; util comes from the device epilogue when available."""
+    if not gp.computed:
+        raise RuntimeError("ERROR: Need to compute GP before using it!")
+    t = np.asarray(theta, dtype=np.float64).reshape(1, -1)
+    if hasattr(gp, "predict_utility"):
+        mu, var, u = gp.predict_utility(y, t, kind)
+        return mu[0], var[0], u[0]
+    mu, var = gp.predict(y, t, return_var=True)
+    return np.asarray(mu).ravel()[0], np.asarray(var).ravel()[0], None
+
+
+def AGPUtility(theta, y, gp, priorFn):
+    """Negative AGP utility -(mu + 0.5 ln(2 pi e var)) (reference utility.py:99-142)."""
+    if not np.isfinite(priorFn(theta)):
+        return np.inf
+    mu, var, u = _mu_var(theta, y, gp, "agp")
+    if u is None:
+        u = -(mu + 0.5 * np.log(2.0 * np.pi * np.e * var))
+    return u
+
+
+def BAPEUtility(theta, y, gp, priorFn):
+    """Negative log BAPE utility -((2 mu + var) + logsubexp(var, 0)) (reference utility.py:145-189)."""
+    if not np.isfinite(priorFn(theta)):
+        return np.inf
+    mu, var, u = _mu_var(theta, y, gp, "bape")
+    if u is None:
+        u = -((2.0 * mu + var) + logsubexp(var, 0.0))
+    return u
+
+
+def JonesUtility(theta, y, gp, priorFn, zeta=0.01):
+    """Negative expected improvement (reference utility.py:192-250)."""
+    if not np.isfinite(priorFn(theta)):
+        return np.inf
+    if not gp.computed:
+        raise RuntimeError("ERROR: Need to compute GP before using it!")
+    t = np.asarray(theta, dtype=np.float64).reshape(1, -1)
+    if hasattr(gp, "predict_utility"):
+        return gp.predict_utility(y, t, "jones", zeta=zeta)[2][0]
+    mu, var = gp.predict(y, t, return_var=True)
+    mu, var = np.asarray(mu).ravel()[0], np.asarray(var).ravel()[0]
+    std = np.sqrt(var)
+    yBest = np.max(y)
+    if std > 0:
+        z = (mu - yBest - zeta) / std
+    else:
+        return 0.0
+    return -((mu - yBest - zeta) * ndtr(z) + std * np.exp(-0.5 * z * z) / np.sqrt(2.0 * np.pi))
+
+
+_KIND = {AGPUtility: "agp", BAPEUtility: "bape", JonesUtility: "jones"}
+
+
+def utilityBatch(thetas, y, gp, priorFn, kind, bounds=None, zeta=0.01):
+    """Utility of many points with one launch.  ``priorFn`` (any Python callable) gates on the host
+    exactly as the scalar functions do; pass ``bounds`` instead to gate inside the kernel."""
+    T = np.ascontiguousarray(np.atleast_2d(np.asarray(thetas, dtype=np.float64)))
+    _, _, u = gp.predict_utility(y, T, kind, bounds=bounds, zeta=zeta)
+    if priorFn is not None:
+        bad = np.array([not np.isfinite(priorFn(t)) for t in T], dtype=bool)
+        u = np.where(bad, np.inf, u)
+    return u
+
+
+def scanUtility(gp, y, kind, bounds, nCandidates=1 << 20, seed=None, zeta=0.01, device_out=False, candidates=None):
+    """Evaluate the utility on a cloud of ``nCandidates`` uniform draws from the box ``bounds`` on the
+    device and return (thetaBest, utilBest, candidates, utilities).  This is the data-parallel
+    replacement for the handful of Nelder-Mead restarts of minimizeObjective (BASELINE config 3:
+    1M multistart candidates per iteration)."""
+    import torch
+    dev = torch.device("cuda", gp._device)
+    d = gp.ndim
+    if candidates is None:
+        g = torch.Generator(device=dev)
+        if seed is not None:
+            g.manual_seed(int(seed))
+        lo = torch.tensor([b[0] for b in bounds], dtype=torch.float64, device=dev)
+        hi = torch.tensor([b[1] for b in bounds], dtype=torch.float64, device=dev)
+        cand = lo + (hi - lo) * torch.rand((int(nCandidates), d), dtype=torch.float64, device=dev, generator=g)
+    else:
+        cand = candidates
+    gp._sync_y(y)
+    gp.recompute()
+    mu, var, u = gp._predict_raw(cand, True, utility=kind, bounds=bounds, ybest=float(np.max(y)), zeta=zeta)
+    u_clean = torch.where(torch.isnan(u), torch.full_like(u, float("inf")), u)
+    ibest = int(torch.argmin(u_clean))
+    best = cand[ibest].cpu().numpy()
+    ubest = float(u[ibest])
+    if device_out:
+        return best, ubest, cand, u
+    return best, ubest, cand.cpu().numpy(), u.cpu().numpy()
+
+
+def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-mead", options=None, bounds=None,
+                      theta0=None, args=None, maxIters=100, batched=True):
+    """Multistart local minimisation of ``fn`` (reference utility.py:253-372).
+
+    Protocol kept from the reference: Nelder-Mead ``{"adaptive": True}`` by default; bounds are only
+    forwarded for methods " l-bfgs-b" (sic) and "tnc"; each restart starts from ``sampleFn(1)`` (or
+    a perturbed ``theta0``), and is retried from a fresh prior sample, up to ``maxIters`` times,
+    until its optimum is finite and allowed by ``priorFn``; the best of the restarts is returned.
+    When ``fn`` is one of the three utilities and ``gp`` is the B200 GP, the restarts run in lock
+    step and each round of objective calls is one fused predict+utility launch.
+    """
+    if str(method).lower() == "nelder-mead" and options is None:
+        options = {"adaptive": True}
+    if str(method).lower() in [" l-bfgs-b", "tnc"]:
+        pass
+    else:
+        bounds = None
+    if args is None:
+        args = ()
+
+    if theta0 is not None:
+        theta0 = np.asarray(theta0).squeeze()
+        ndim = theta0.ndim
+        if ndim <= 0:
+            ndim = 1
+
+    def draw():
+        return np.asarray(sampleFn(1), dtype=np.float64).ravel()
+
+    starts = []
+    for _ in range(nRestarts):
+        if theta0 is None:
+            starts.append(draw())
+        else:
+            starts.append(np.atleast_1d(theta0 + np.min(theta0) * 1.0e-3 * np.random.randn(ndim)).ravel())
+
+    kind = _KIND.get(fn)
+    use_batch = batched and kind is not None and hasattr(gp, "predict_utility") and nRestarts > 1
+
+    def solve(f, t0, redraw):
+        ii = 0
+        while True:
+            if ii >= maxIters:
+                errMsg = "ERROR: Cannot find a valid solution. Current iterations: %d\n" % ii
+                errMsg += "Maximum iterations: %d\n" % maxIters
+                raise RuntimeError(errMsg)
+            tmp = minimize(f, t0, bounds=bounds, method=method, options=options)["x"]
+            if np.all(np.isfinite(tmp)):
+                if np.isfinite(priorFn(tmp)):
+                    return tmp, f(tmp)
+            t0 = redraw()
+            ii += 1
+
+    if use_batch:
+        import threading
+        rng_lock = threading.Lock()
+        zeta = 0.01
+
+        def batch_fn(thetas):
+            return utilityBatch(np.array(thetas), y, gp, priorFn, kind, zeta=zeta)
+
+        def redraw():
+            with rng_lock:
+                return draw()
+
+        out, ev = run_lockstep(nRestarts, batch_fn, lambda wid, f: solve(f, starts[wid], redraw))
+        minimizeObjective.last_stats = dict(batches=ev.nbatches, evals=ev.nevals)
+    else:
+        out = [solve(lambda x: fn(x, *args), t0, draw) for t0 in starts]
+
+    res = [o[0] for o in out]
+    objective = [o[1] for o in out]
+    bestInd = np.argmin(objective)
+    return np.array(res)[bestInd], objective[bestInd]
+
+
+minimizeObjective.last_stats = None

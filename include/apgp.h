@@ -1,0 +1,132 @@
+/* libapgp -- C-ABI of the B200-native GP-surrogate engine behind approxposterior's hot path.
+ *
+ * Every entry point replaces one call the reference (dflemin3/approxposterior v0.4) makes into
+ * george / emcee; the reference call site is cited on each declaration (paths relative to the
+ * reference repo).  The reference has no FFI of its own (pure Python over george's pybind11
+ * module), so this header *is* the boundary a maintainer would bind with ctypes -- see
+ * INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw pointers + sizes, int status returns; no C++ types cross.
+ *   - status 0 = ok; > 0 = data condition (APGP_NOT_POSDEF, ...); < 0 = CUDA/argument error, text
+ *     via apgp_last_error().
+ *   - all arrays are fp64, C-contiguous.  Arguments named *_dev are device pointers on the
+ *     handle's device; `on_host` flags say whether bulk buffers are host (the library stages the
+ *     H2D/D2H copies on the handle's stream) or device pointers.  Small parameter vectors
+ *     (hyper-parameters, bounds) are always host pointers.
+ *   - a handle is bound to one device and one stream; it is not thread-safe.
+ *   - there is no CPU fallback: every function fails (status < 0) without a CUDA device.
+ */
+#ifndef APGP_H_
+#define APGP_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APGP_OK 0
+#define APGP_NOT_POSDEF 1        /* covariance not positive definite (george: LinAlgError) */
+#define APGP_NOT_COMPUTED 2      /* predict/log-likelihood before a successful factorisation */
+#define APGP_ERR_ARG (-1)
+#define APGP_ERR_CUDA (-2)
+#define APGP_ERR_NOMEM (-3)
+
+#define APGP_MAX_DIM 32
+
+#define APGP_UTIL_NONE 0
+#define APGP_UTIL_AGP 1          /* utility.py:99-142  */
+#define APGP_UTIL_BAPE 2         /* utility.py:145-189 */
+#define APGP_UTIL_JONES 3        /* utility.py:192-250 */
+
+typedef struct apgp_handle apgp_handle;
+
+const char* apgp_last_error(void);
+int apgp_version(void);
+
+/* lifecycle -- george.GP(...) construction at gpUtils.py:176-177 and approx.py:712-715 */
+int apgp_create(apgp_handle** out, int device);
+int apgp_destroy(apgp_handle* h);
+int apgp_set_stream(apgp_handle* h, void* cuda_stream);           /* cudaStream_t; NULL = library-owned stream */
+int apgp_synchronize(apgp_handle* h);
+long long apgp_launch_count(const apgp_handle* h);                /* kernels launched so far by this handle */
+
+/* training set -- george.GP.compute(x) at gpUtils.py:178, approx.py:717 (x part) and the `y`
+ * argument of predict/log_likelihood.  X is [N][d] row-major, y is [N]. */
+int apgp_set_training(apgp_handle* h, const double* X, const double* y, int N, int d, int on_host);
+
+/* hyper-parameters -- george.GP.set_parameter_vector(p) at gpUtils.py:74,243,253; approx.py:716.
+ *   mean        constant mean (p[0])
+ *   amp         effective kernel amplitude A = ndim*exp(log_constant), 1.0 without `a*kernel`
+ *   log_metric  [d] log M_i, M_i the squared length scale of ExpSquaredKernel (gpUtils.py:160)
+ *   white_noise frozen log-variance added to diag(K) (gpUtils.py:176-177; default -12) */
+int apgp_set_hyper(apgp_handle* h, double mean, double amp, const double* log_metric, double white_noise);
+
+/* factorise -- george.GP.compute/recompute (gpUtils.py:178,244,254; approx.py:717):
+ * K = A exp(-1/2 r^2_M) + (e^{wn} + TINY^2) I ; blocked Cholesky; alpha; explicit L^{-1}.
+ * Returns APGP_NOT_POSDEF (and *info = 1-based failing pivot) when K is not positive definite.
+ * *logdet = log|K|, *loglik = log-likelihood of the stored y (george.GP.log_likelihood,
+ * gpUtils.py:78,247); either may be NULL. */
+int apgp_factorize(apgp_handle* h, double* logdet, double* loglik, int* info);
+
+typedef struct apgp_predict_opts {
+  int want_var;                  /* 0: mean only (approx.py:178-180); 1: mean+variance (utility.py:131,178,224) */
+  int utility;                   /* APGP_UTIL_*; needs want_var=1 */
+  int has_box;                   /* 1: utility = +inf outside [lo,hi] (the priorFn gate, utility.py:126,173,219) */
+  double lo[APGP_MAX_DIM];
+  double hi[APGP_MAX_DIM];
+  double ybest;                  /* Jones: max(y) (utility.py:232) */
+  double zeta;                   /* Jones: exploration parameter (utility.py:192, default 0.01) */
+} apgp_predict_opts;
+
+/* batched george.GP.predict(y, Xq, return_cov=False, return_var=want_var) + utility epilogue.
+ * Xq [Q][d]; mu/var/util [Q], each may be NULL.  on_host: Xq and outputs are host buffers. */
+int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, double* var, double* util,
+                 const apgp_predict_opts* opts, int on_host);
+
+/* george.GP.grad_log_likelihood(y, quiet=True) at gpUtils.py:110.  grad (host) has 1+fit_amp+d
+ * entries ordered [mean, (log_constant), log M_0..]; zeros when the GP is not computed. */
+int apgp_grad_log_likelihood(apgp_handle* h, int fit_amp, double* grad);
+
+/* Batched log-likelihood for R hyper-parameter vectors at once -- what gpUtils._nll (gpUtils.py:46-80)
+ * evaluates one at a time inside optimizeGP's restarts (gpUtils.py:223-247).
+ * P_host [R][P], rows in george order [mean, (log_constant), log M_0 .. log M_{d-1}], P = 1+fit_amp+d.
+ * ll_host [R]: log-likelihood, -inf when not positive definite / non-finite (quiet=True semantics).
+ * Does not disturb the handle's current factorisation. */
+int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fit_amp, double white_noise,
+                      double* ll_host);
+
+typedef struct apgp_sampler_opts {
+  int nens;                      /* independent ensembles */
+  int nwalkers;                  /* walkers per ensemble (even, >= 2) */
+  int nsteps;
+  int thin;                      /* store every thin-th step (>= 1) */
+  double a;                      /* stretch scale (emcee default 2.0) */
+  unsigned long long seed;       /* Philox key */
+  double lo[APGP_MAX_DIM];       /* box prior (approx.py:171-173 with a uniform lnprior) */
+  double hi[APGP_MAX_DIM];
+  double lnprior_const;          /* value stored in the "lnprior" blob for accepted points */
+  /* optional replay of recorded draws (all NULL => Philox); host or device like the bulk buffers:
+   * inds [nens][nsteps][nwalkers] int32, zz/logu [nens][nsteps][2][nwalkers/2] fp64, rint same shape int32 */
+  const int* replay_inds;
+  const double* replay_zz;
+  const int* replay_rint;
+  const double* replay_logu;
+} apgp_sampler_opts;
+
+/* emcee.EnsembleSampler(nwalkers, ndim, log_prob_fn=_gpll).sample(initial_state, iterations)
+ * as driven from approx.py:839-847.  p0 [nens*nwalkers][d];
+ * chain [nsteps/thin][nens*nwalkers][d], logp/blob [nsteps/thin][nens*nwalkers], naccept [nens*nwalkers] int32. */
+int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double* p0, double* chain, double* logp,
+                     double* blob, int* naccept, int on_host);
+
+/* test/diagnostic accessors (host outputs): alpha [N], Linv [N][N] row-major (lower), L likewise */
+int apgp_get_alpha(apgp_handle* h, double* alpha);
+int apgp_get_linv(apgp_handle* h, double* linv);
+int apgp_get_chol(apgp_handle* h, double* L);
+/* select the variance-kernel tiling: 0 = 64x256 (default), 1 = 128x128.  Call before factorize. */
+int apgp_set_variant(apgp_handle* h, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APGP_H_ */
