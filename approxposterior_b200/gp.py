@@ -195,8 +195,9 @@ class GP(object):
             mk = lambda: torch.empty(Q, dtype=torch.float64, device=t.device)
             on_host = 0
             # order the engine's stream after the producer of `t`, and torch after the engine
-            _lib.check(self._lib.apgp_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)),
-                       "apgp_set_stream")
+            # (torch's default stream has handle 0; cudaStreamLegacy == 0x1 names it explicitly)
+            sh = torch.cuda.current_stream(t.device).cuda_stream or 1
+            _lib.check(self._lib.apgp_set_stream(self._h, C.c_void_p(sh)), "apgp_set_stream")
         else:
             t = self._parse(t)
             Q = t.shape[0]
