@@ -1,0 +1,193 @@
+"""``EnsembleSampler``: the slice of emcee's surface that approxposterior drives
+(reference approx.py:839-847, mcmcUtils.py:198, approx.py:479), backed by the B200 engine.
+
+Two engines:
+  "device"   the whole chain runs inside one CUDA kernel (GP.run_ensembles): stretch move, red/blue
+             split, box prior, mean-only surrogate predict, accept/reject and chain storage all on the
+             GPU with Philox draws.  Needs a box prior (``bounds``) and the surrogate GP.  ``nens``
+             independent ensembles of ``nwalkers`` walkers run side by side.
+  "host-rng" emcee 3.0.x's draw order is replayed on the host with NumPy's legacy RandomState
+             (choice, shuffle, rand, randint, rand per walker) so a seeded run follows the reference's
+             RNG flow; each half-step's proposals are evaluated in ONE batched call to
+             ``log_prob_fn`` (vectorised: takes (Ns, ndim), returns (lp[Ns], blob[Ns])).
+"""
+import numpy as np
+
+__all__ = ["EnsembleSampler", "integrated_time", "AutocorrError"]
+
+
+class AutocorrError(Exception):
+    def __init__(self, tau, *args, **kwargs):
+        self.tau = tau
+        super(AutocorrError, self).__init__(*args, **kwargs)
+
+
+def _next_pow_two(n):
+    i = 1
+    while i < n:
+        i = i << 1
+    return i
+
+
+def _acf_1d_batch(x):
+    """Normalised autocorrelation of every column of x[n_t, n_w] via FFT."""
+    n_t = x.shape[0]
+    n = _next_pow_two(n_t)
+    f = np.fft.fft(x - np.mean(x, axis=0), n=2 * n, axis=0)
+    acf = np.fft.ifft(f * np.conjugate(f), axis=0)[:n_t].real
+    return acf / acf[0]
+
+
+def integrated_time(x, c=5, tol=50, quiet=False):
+    """Integrated autocorrelation time per dimension, emcee's estimator (Sokal window with c=5;
+    autocorrelation averaged over walkers).  x is (n_t, n_w, n_d)."""
+    x = np.atleast_1d(x)
+    if x.ndim == 1:
+        x = x[:, np.newaxis, np.newaxis]
+    if x.ndim == 2:
+        x = x[:, :, np.newaxis]
+    if x.ndim != 3:
+        raise ValueError("invalid dimensions")
+    n_t, n_w, n_d = x.shape
+    tau_est = np.empty(n_d)
+    for d in range(n_d):
+        f = np.mean(_acf_1d_batch(x[:, :, d]), axis=1)
+        taus = 2.0 * np.cumsum(f) - 1.0
+        m = np.arange(len(taus)) < c * taus
+        window = np.argmin(m) if np.any(m) else len(taus) - 1
+        tau_est[d] = taus[window]
+    flag = tol * tau_est > n_t
+    if np.any(flag) and not quiet:
+        raise AutocorrError(tau_est, "The chain is shorter than %d times the integrated autocorrelation time" % tol)
+    return tau_est
+
+
+class _State(object):
+    def __init__(self, coords, log_prob, blobs):
+        self.coords, self.log_prob, self.blobs = coords, log_prob, blobs
+
+
+class EnsembleSampler(object):
+    def __init__(self, nwalkers, ndim, log_prob_fn=None, backend=None, args=None, kwargs=None, blobs_dtype=None,
+                 a=2.0, engine="host-rng", gp=None, y=None, bounds=None, lnprior_const=0.0, nens=1, seed=None,
+                 **unused):
+        if nwalkers % 2 or nwalkers < 2 * ndim:
+            raise ValueError("emcee requires an even number of walkers, at least twice the dimension")
+        self.nwalkers, self.ndim, self.a = int(nwalkers), int(ndim), float(a)
+        self.log_prob_fn = log_prob_fn
+        self.engine = engine
+        self.gp, self.y, self.bounds, self.lnprior_const = gp, y, bounds, lnprior_const
+        self.nens = int(nens)
+        self.backend = backend
+        self.blobs_dtype = blobs_dtype
+        # emcee copies the *global* NumPy state at construction
+        self._random = np.random.RandomState()
+        self._random.set_state(np.random.get_state())
+        self._seed = seed
+        if engine == "device" and (gp is None or y is None or bounds is None):
+            raise ValueError("engine='device' needs gp, y and bounds (box prior)")
+        if engine == "host-rng" and log_prob_fn is None:
+            raise ValueError("engine='host-rng' needs a vectorised log_prob_fn")
+        self._chain = self._logp = self._blobs = None
+        self.naccepted = None
+        self.iteration = 0
+
+    # ------------------------------------------------------------------ running
+    def _run_device(self, p0, nsteps):
+        seed = self._seed if self._seed is not None else int(self._random.randint(0, 2 ** 31 - 1))
+        out = self.gp.run_ensembles(self.y, p0, nsteps, self.bounds, nens=self.nens, a=self.a, seed=seed,
+                                    lnprior_const=self.lnprior_const)
+        return out["chain"], out["log_prob"], out["blobs"], out["naccepted"].astype(np.int64)
+
+    def _run_host(self, p0, nsteps):
+        rng, a = self._random, self.a
+        coords = np.array(p0, dtype=np.float64, copy=True)
+        nw, nd = coords.shape
+        Ns = nw // 2
+        lp, blob = self.log_prob_fn(coords)
+        lp = np.array(lp, dtype=np.float64)
+        blob = np.array(blob, dtype=np.float64)
+        if np.any(np.isnan(lp)):
+            raise ValueError("The initial log_prob was NaN")
+        chain = np.empty((nsteps, nw, nd)); lps = np.empty((nsteps, nw)); blobs = np.empty((nsteps, nw))
+        nacc = np.zeros(nw, dtype=np.int64)
+        all_inds = np.arange(nw)
+        for it in range(nsteps):
+            rng.choice(1, p=[1.0])
+            inds = all_inds % 2
+            rng.shuffle(inds)
+            for split in (0, 1):
+                S1 = inds == split
+                s, c = coords[S1], coords[~S1]
+                zz = ((a - 1.0) * rng.rand(Ns) + 1.0) ** 2.0 / a
+                factors = (nd - 1.0) * np.log(zz)
+                rint = rng.randint(len(c), size=(Ns,))
+                q = c[rint] - (c[rint] - s) * zz[:, None]
+                nlp, nblob = self.log_prob_fn(q)
+                nlp = np.asarray(nlp, dtype=np.float64)
+                logu = np.log(rng.rand(Ns))        # same stream as Ns scalar rand() calls
+                acc = (factors + nlp - lp[S1]) > logu
+                jj = all_inds[S1][acc]
+                coords[jj] = q[acc]; lp[jj] = nlp[acc]; blob[jj] = np.asarray(nblob)[acc]
+                nacc[jj] += 1
+            chain[it] = coords; lps[it] = lp; blobs[it] = blob
+        return chain, lps, blobs, nacc
+
+    def run_mcmc(self, initial_state, nsteps, **kwargs):
+        p0 = np.asarray(getattr(initial_state, "coords", initial_state), dtype=np.float64)
+        p0 = p0.reshape(-1, self.ndim)
+        if p0.shape[0] != self.nwalkers * (self.nens if self.engine == "device" else 1):
+            raise ValueError("incompatible input dimensions")
+        run = self._run_device if self.engine == "device" else self._run_host
+        chain, lp, blobs, nacc = run(p0, int(nsteps))
+        if self._chain is None:
+            self._chain, self._logp, self._blobs, self.naccepted = chain, lp, blobs, nacc
+        else:
+            self._chain = np.concatenate([self._chain, chain]); self._logp = np.concatenate([self._logp, lp])
+            self._blobs = np.concatenate([self._blobs, blobs]); self.naccepted = self.naccepted + nacc
+        self.iteration += int(nsteps)
+        if self.backend is not None:
+            np.savez(str(self.backend), chain=self._chain, log_prob=self._logp, blobs=self._blobs,
+                     accepted=self.naccepted)
+        return _State(self._chain[-1], self._logp[-1], self._blobs[-1])
+
+    def sample(self, initial_state, iterations=1, **kwargs):
+        """Generator form used at approx.py:846 (``for _ in sampler.sample(**mcmcKwargs): pass``).  The
+        chain is produced in one go on first advance; one (final-state) item is yielded per iteration."""
+        state = self.run_mcmc(initial_state, iterations)
+        for _ in range(int(iterations)):
+            yield state
+
+    # ------------------------------------------------------------------ results
+    def _get(self, arr, discard=0, flat=False, thin=1):
+        if arr is None:
+            raise AttributeError("you must run the sampler before accessing the results")
+        v = arr[discard + thin - 1::thin]
+        if flat:
+            v = v.reshape((-1,) + v.shape[2:])
+        return v
+
+    def get_chain(self, discard=0, flat=False, thin=1):
+        return self._get(self._chain, discard, flat, thin)
+
+    def get_log_prob(self, discard=0, flat=False, thin=1):
+        return self._get(self._logp, discard, flat, thin)
+
+    def get_blobs(self, discard=0, flat=False, thin=1):
+        b = self._get(self._blobs, discard, flat, thin)
+        if self.blobs_dtype is not None:
+            out = np.empty(b.shape, dtype=self.blobs_dtype)
+            out[out.dtype.names[0]] = b
+            return out
+        return b
+
+    @property
+    def chain(self):            # emcee legacy layout (nwalkers, nsteps, ndim)
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / float(self.iteration)
+
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)

@@ -129,7 +129,7 @@ def scanUtility(gp, y, kind, bounds, nCandidates=1 << 20, seed=None, zeta=0.01, 
 
 
 def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-mead", options=None, bounds=None,
-                      theta0=None, args=None, maxIters=100, batched=True):
+                      theta0=None, args=None, maxIters=100, batched=True, _start=None):
     """Multistart local minimisation of ``fn`` (reference utility.py:253-372).
 
     Protocol kept from the reference: Nelder-Mead ``{"adaptive": True}`` by default; bounds are only
@@ -164,8 +164,13 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
         else:
             starts.append(np.atleast_1d(theta0 + np.min(theta0) * 1.0e-3 * np.random.randn(ndim)).ravel())
 
+    if _start is not None:          # engine extension: polish a known-good candidate (scanUtility)
+        starts[0] = np.asarray(_start, dtype=np.float64).ravel()
+
     kind = _KIND.get(fn)
-    use_batch = batched and kind is not None and hasattr(gp, "predict_utility") and nRestarts > 1
+    fn_batch = getattr(fn, "batch", None)      # any objective may bring its own batched form
+    use_batch = batched and nRestarts > 1 and (fn_batch is not None or
+                                               (kind is not None and hasattr(gp, "predict_utility")))
 
     def solve(f, t0, redraw):
         ii = 0
@@ -187,6 +192,8 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
         zeta = 0.01
 
         def batch_fn(thetas):
+            if fn_batch is not None:
+                return fn_batch(np.array(thetas))
             return utilityBatch(np.array(thetas), y, gp, priorFn, kind, zeta=zeta)
 
         def redraw():

@@ -317,8 +317,8 @@ def run_gpu(args):
                         "api": "GP.predict_utility(y, host ndarray, 'bape', bounds) -> (mu, var, util) host ndarrays"},
                 "gpu_launches": int(launches),
                 "clocks": clk,
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak * 1e-3, "unit": "TFLOP/s",
-                             "frac": achieved / (peak * 1e-3), "traffic": None,
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak, "traffic": None,
                              "kernel": "predict_var_kernel (fused K* panel + DMMA triangular GEMM + utility)",
                              "kernel_ms": kernel_ms,
                              "flops_per_eval": flops_per_eval(N_TRAIN, DIM),

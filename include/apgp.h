@@ -123,7 +123,7 @@ int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double
 int apgp_get_alpha(apgp_handle* h, double* alpha);
 int apgp_get_linv(apgp_handle* h, double* linv);
 int apgp_get_chol(apgp_handle* h, double* L);
-/* select the variance-kernel tiling: 0 = 64x256 (default), 1 = 128x128.  Call before factorize. */
+/* select the variance-kernel tiling: 0 = 64x256, 1 = 128x128 (default).  Call before factorize. */
 int apgp_set_variant(apgp_handle* h, int variant);
 
 #ifdef __cplusplus

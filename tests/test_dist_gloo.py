@@ -1,0 +1,64 @@
+"""world_size-2 gloo tests (CPU) of the sharding helpers used on the N>1 GPU path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from approxposterior_b200 import dist as apd
+        assert apd.world() == (rank, ws)
+        # candidate scan: every rank scores its own block of one global candidate list
+        rng = np.random.default_rng(5)
+        cand = rng.uniform(-5, 5, size=(1001, 3))
+        score = np.sum((cand - 1.0) ** 2, axis=1)
+        score[17] = np.nan
+        lo, hi = apd.shard_bounds(len(cand), rank, ws)
+        s_loc = np.where(np.isnan(score[lo:hi]), np.inf, score[lo:hi])
+        i_loc = int(np.argmin(s_loc))
+        theta, best, owner = apd.gather_best(s_loc[i_loc], cand[lo + i_loc])
+        i_glob = int(np.nanargmin(score))
+        ok1 = np.array_equal(theta, cand[i_glob]) and best == score[i_glob]
+        # chains: walkers concatenate in rank order
+        chain_loc = np.full((4, 6, 2), float(rank))
+        full = apd.gather_concat(chain_loc, axis=1)
+        ok2 = full.shape == (4, 6 * ws, 2) and all(np.all(full[:, 6 * r:6 * (r + 1)] == r) for r in range(ws))
+        # restarts: arg-max of the marginal likelihood over all ranks, -inf/NaN never win
+        p_loc = np.array([[rank, 1.0], [rank, 2.0]])
+        mll = np.array([-10.0 + rank, np.nan if rank == 0 else -np.inf])
+        pbest, mbest = apd.best_restart_sharded(p_loc, mll)
+        ok3 = mbest == -10.0 + (ws - 1) and pbest[0] == ws - 1 and pbest[1] == 1.0
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharding_helpers_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(r[0] for r in res) == [0, 1]
+    for r in res:
+        assert r[1:] == (True, True, True), r

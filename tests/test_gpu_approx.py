@@ -1,0 +1,141 @@
+"""GPU tests of the reference-facing API (ApproxPosterior / gpUtils / utility on the B200 engine).
+They read like the reference's own tests (approxposterior/tests/*.py) with the same seeds, fixtures
+and tolerances."""
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+
+pytestmark = pytest.mark.gpu
+
+
+def _rosen_setup(m0, fitAmp, extra=None):
+    from approxposterior_b200 import gpUtils, likelihood as lh
+    np.random.seed(57)
+    theta = np.array(lh.rosenbrockSample(m0))
+    if extra is not None:
+        theta = np.array(list(theta) + extra)
+    y = np.array([lh.rosenbrockLnlike(t) + lh.rosenbrockLnprior(t) for t in theta])
+    gp = gpUtils.defaultGP(theta, y, fitAmp=fitAmp)
+    return theta, y, gp
+
+
+@pytest.mark.parametrize("fitAmp,gold", [
+    (True, [-31.02658091, 9.78479362, -1.0552327, -1.16092752]),       # reference tests/test_InitGP.py:43
+    (False, [-31.02658091, -1.0552327, -1.16092752]),                  # reference tests/test_InitGP.py:76
+])
+def test_init_gp(fitAmp, gold):
+    _, _, gp = _rosen_setup(50, fitAmp)
+    assert np.allclose(gold, gp.get_parameter_vector())
+    assert gp.computed and len(gp.get_parameter_names()) == len(gold)
+
+
+@pytest.mark.parametrize("fitAmp,gold", [
+    (True, [19.99668368, 4.18856645, 10.78000803]),                    # reference tests/test_OptimizeGP.py:50
+    (False, [-1.54256578, 3.24723589]),                                # reference tests/test_OptimizeGP.py:91
+])
+def test_optimize_gp(fitAmp, gold):
+    from approxposterior_b200 import gpUtils
+    theta, y, gp = _rosen_setup(50, fitAmp)
+    gp = gpUtils.optimizeGP(gp, theta, y, seed=57, nGPRestarts=5, method="powell")
+    assert np.allclose(gp.get_parameter_vector()[1:], gold, rtol=1.0e-2), gp.get_parameter_vector()
+    st = gpUtils.optimizeGP.last_stats
+    assert st["batches"] < st["evals"]            # restarts really shared launches
+
+
+def test_optimize_gp_gradient_method():
+    from approxposterior_b200 import gpUtils
+    theta, y, gp = _rosen_setup(50, False)
+    ll0 = gp.log_likelihood(y)
+    gp = gpUtils.optimizeGP(gp, theta, y, nGPRestarts=2, method="l-bfgs-b")
+    assert gp.log_likelihood(y) > ll0
+
+
+def test_find_next_point_no_amp():
+    """reference tests/test_findNewPoint.py:64-107."""
+    from approxposterior_b200 import approx, likelihood as lh
+    theta, y, gp = _rosen_setup(50, False, extra=[[-5, 5], [5, 5]])
+    bounds = ((-5, 5), (-5, 5))
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lh.rosenbrockLnprior, lnlike=lh.rosenbrockLnlike,
+                                priorSample=lh.rosenbrockSample, bounds=bounds, algorithm="bape")
+    thetaT = ap.findNextPoint(computeLnLike=False, bounds=bounds, seed=57, verbose=False)
+    assert np.allclose(thetaT, [0.79813416, 0.85542199], rtol=1.0e-3), thetaT
+
+
+def test_find_next_point_scan_mode_beats_restarts():
+    """Device-side candidate scan (config 3 style) finds a utility at least as good as 5 restarts."""
+    from approxposterior_b200 import approx, likelihood as lh, utility as ut
+    theta, y, gp = _rosen_setup(50, False, extra=[[-5, 5], [5, 5]])
+    bounds = ((-5, 5), (-5, 5))
+    prior = lh.BoxPrior(bounds)
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=prior, lnlike=lh.rosenbrockLnlike,
+                                priorSample=lh.rosenbrockSample, bounds=bounds, algorithm="bape")
+    t_scan = ap.findNextPoint(computeLnLike=False, verbose=False, scanCandidates=200000)
+    t_ref = ap.findNextPoint(computeLnLike=False, verbose=False)
+    u_scan = ut.BAPEUtility(t_scan, y, gp, prior)
+    u_ref = ut.BAPEUtility(t_ref, y, gp, prior)
+    assert np.isfinite(u_scan) and u_scan <= u_ref + 1e-6 * abs(u_ref)
+
+
+def test_map_amp():
+    """reference tests/test_MAP.py:16-66."""
+    from approxposterior_b200 import approx, gpUtils, likelihood as lh
+    np.random.seed(57)
+    theta = np.array(lh.sphereSample(20))
+    y = np.array([lh.sphereLnlike(t) + lh.sphereLnprior(t) for t in theta])
+    gp = gpUtils.defaultGP(theta, y, fitAmp=True)
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lh.sphereLnprior, lnlike=lh.sphereLnlike,
+                                priorSample=lh.sphereSample, bounds=[(-5, 5), (-5, 5)], algorithm="jones")
+    ap.optGP(seed=57, method="powell", nGPRestarts=3)
+    ap.findNextPoint(numNewPoints=5, nGPRestarts=3, cache=False, verbose=False)
+    testMAP, testVal = ap.findMAP(nRestarts=15)
+    assert np.allclose([0.0, 0.0], testMAP, atol=1.0e-3), testMAP
+    assert np.allclose(0.0, testVal, atol=1.0e-3), testVal
+
+
+def test_1d_bayes_opt():
+    """reference tests/test_1DBayesOpt.py:16-75."""
+    from approxposterior_b200 import approx, gpUtils, likelihood as lh
+    np.random.seed(57)
+    fn = lambda x: -(lh.testBOFn(x) + lh.testBOFnLnPrior(x))
+    trueSoln = minimize(fn, np.atleast_1d(lh.testBOFnSample(1)), method="nelder-mead")
+    theta = lh.testBOFnSample(3)
+    y = np.array([lh.testBOFn(t) + lh.testBOFnLnPrior(t) for t in theta])
+    gp = gpUtils.defaultGP(theta, y, fitAmp=True)
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lh.testBOFnLnPrior, lnlike=lh.testBOFn,
+                                priorSample=lh.testBOFnSample, bounds=[[-1, 2]], algorithm="jones")
+    soln = ap.bayesOpt(nmax=10, tol=1.0e-3, seed=57, verbose=False, cache=False, gpMethod="powell", optGPEveryN=1,
+                       nGPRestarts=3, nMinObjRestarts=5, initGPOpt=True, minObjMethod="nelder-mead", findMAP=True,
+                       gpHyperPrior=gpUtils.defaultHyperPrior)
+    assert np.allclose(soln["thetaBest"], trueSoln["x"], rtol=5.0e-2)
+    assert np.allclose(soln["valBest"], -trueSoln["fun"], rtol=5.0e-2)
+    assert np.allclose(soln["thetaMAPBest"], trueSoln["x"], rtol=5.0e-2)
+    assert np.allclose(soln["valMAPBest"], -trueSoln["fun"], rtol=5.0e-2)
+
+
+@pytest.mark.parametrize("engine", ["device", "host-rng"])
+def test_run_posterior(engine, tmp_path):
+    """reference tests/test_APRun.py:17-75 (shortened): BAPE on the Rosenbrock posterior; marginal means
+    within one "sigma" of the known values."""
+    from approxposterior_b200 import approx, gpUtils, likelihood as lh
+    bounds = [(-5, 5), (-5, 5)]
+    np.random.seed(57)
+    theta = lh.rosenbrockSample(50)
+    y = np.array([lh.rosenbrockLnlike(t) + lh.rosenbrockLnprior(t) for t in theta])
+    gp = gpUtils.defaultGP(theta, y, white_noise=-12, fitAmp=False)
+    prior = lh.BoxPrior(bounds) if engine == "device" else lh.rosenbrockLnprior
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=prior, lnlike=lh.rosenbrockLnlike,
+                                priorSample=lh.rosenbrockSample, bounds=bounds, algorithm="bape")
+    nsteps = 5000 if engine == "device" else 1500
+    ap.run(m=10, nmax=2, estBurnin=True, nGPRestarts=2, mcmcKwargs={"iterations": nsteps},
+           samplerKwargs={"nwalkers": 20}, cache=True, runName=str(tmp_path / "apRun"), thinChains=False,
+           verbose=False, optGPEveryN=5, seed=57, timing=True, onlyLastMCMC=True)
+    assert len(ap.y) == 70 and ap.theta.shape == (70, 2)
+    assert len(ap.trainingTime) == 2 and len(ap.mcmcTime) == 1
+    samples = ap.sampler.get_chain(discard=ap.iburns[-1], flat=True, thin=ap.ithins[-1])
+    assert np.all(np.abs(samples) <= 5.0)
+    # posterior of exp(-rosen/100) on [-5,5]^2: means ~ (0.0, 1.3), widths (1.5, 1.75) -- reference :66-73
+    z = np.fabs(np.mean(samples, axis=0) - np.array([0.04, 1.31])) / np.array([1.5, 1.75])
+    assert np.all(z < 1), (np.mean(samples, axis=0), z)
+    assert (tmp_path / "apRunAPFModelCache.npz").exists() and (tmp_path / "apRunAPGP.npz").exists()
+    blobs = ap.sampler.get_blobs()
+    assert blobs.dtype.names == ("lnprior",)
