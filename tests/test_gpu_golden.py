@@ -110,7 +110,7 @@ def test_full_size_properties():
 
 
 def test_sampler_many_ensembles_deterministic_and_in_bounds():
-    g = np.load(GOLDEN[0])
+    g = np.load(os.path.join(HERE, "golden", "golden_n96_d2.npz"))
     gp, _ = _gp_from(g)
     y = g["y"]
     bounds = [(-5.0, 5.0)] * 2
