@@ -90,7 +90,7 @@ int apgp_create(apgp_handle** out, int device) {
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   const char* v = getenv("APGP_PREDICT_VARIANT");
-  if (v) h->variant = atoi(v) == 0 ? 0 : 1;
+  if (v) { int vv = atoi(v); h->variant = (vv == 0) ? 0 : 1; }
   *out = h;
   return APGP_OK;
 }
@@ -131,7 +131,7 @@ int apgp_synchronize(apgp_handle* h) {
 long long apgp_launch_count(const apgp_handle* h) { return h ? h->launches : 0; }
 
 int apgp_set_variant(apgp_handle* h, int variant) {
-  if (!h || (variant != 0 && variant != 1)) return fail(APGP_ERR_ARG, "apgp_set_variant");
+  if (!h || variant < 0 || variant > 1) return fail(APGP_ERR_ARG, "apgp_set_variant");
   h->variant = variant; h->factored = false;
   return APGP_OK;
 }
@@ -426,6 +426,16 @@ static int get_square(apgp_handle* h, const DevBuf& b, double* out) {
   CU(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < h->N; ++i)
     for (int j = i + 1; j < h->N; ++j) out[(size_t)i * h->N + j] = 0.0;
+  return APGP_OK;
+}
+int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out) {
+  if (!h || !s || !out || n < 1) return fail(APGP_ERR_ARG, "apgp_debug_exp_neg");
+  Guard g(h->device);
+  CUI(h->stage_in.reserve((size_t)n * 8)); CUI(h->stage_out.reserve((size_t)n * 8));
+  CU(cudaMemcpyAsync(h->stage_in.p, s, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  CUI(launch_exp_neg_test(h->stage_in.as<double>(), n, h->stage_out.as<double>(), h->stream));
+  CU(cudaMemcpyAsync(out, h->stage_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return APGP_OK;
 }
 int apgp_get_linv(apgp_handle* h, double* linv) { return get_square(h, h->Linv, linv); }

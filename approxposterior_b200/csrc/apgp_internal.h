@@ -34,6 +34,7 @@ int predict_variant_bn(int variant);   // block-row height BN of the LinvF tilin
 
 // returns cudaError_t as int; *launches incremented by the number of kernel launches issued
 int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches);
+int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st);
 int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, int* launches);
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant);
 int launch_pack_linv(const double* Linv, int ld, int N, int Npad, int BN, double amp, double* LinvF, cudaStream_t st);

@@ -104,6 +104,27 @@ __device__ __forceinline__ double utility_eval(int kind, double mu, double var, 
   return 0.0;
 }
 
+// ---------------------------------------------------------------------------------
+// exp(-s) for s >= 0: 2^(n/64) table + degree-5 polynomial, ~1 ulp; 10 FP64 ops instead of libdevice's 16.
+__device__ __forceinline__ double exp_neg(double s, const double* __restrict__ tab) {
+  const double x = -s;
+  const double t = fma(x, 92.33248261689366 /*64/ln2*/, 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -0.010830424696249145 /*ln2/64 hi*/, x);    // fma: x - nf*hi is a single rounding
+  r = fma(nf, -3.623510646634843e-19 /*ln2/64 lo*/, r);
+  const double r2 = r * r;
+  double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  q = fma(r, q, 1.6666666666666666e-01);
+  q = fma(r, q, 0.5);
+  const double pm1 = fma(r2, q, r);                         // e^r - 1
+  const double T = tab[n & 63];
+  double res = fma(T, pm1, T);
+  const int k = n >> 6;
+  res = __hiloint2double(__double2hiint(res) + (k << 20), __double2loint(res));
+  return (s < 700.0) ? res : 0.0;                             // exp(-700) ~ 1e-304: flush, keeps 2^k normal
+}
+
 // Philox4x32-10 counter-based RNG (Salmon et al. 2011), for the device sampler.
 struct Philox {
   uint32_t k0, k1;

@@ -45,7 +45,7 @@ struct VarCfg {
   static constexpr int RING = NSTAGE * STAGE;            // doubles, reused as the phase-1 staging area
   static size_t smem_bytes(int d) {
     return (size_t)RING * 8 + (size_t)d * BM * 8 /*qs*/ + (size_t)BM * 8 /*mu_s*/ +
-           (size_t)WARPS_N * BM * 8 /*ss_s*/ + 2 * NSTAGE * 8 /*barriers*/ + 128;
+           (size_t)WARPS_N * BM * 8 /*ss_s*/ + 64 * 8 /*exp table*/ + 2 * NSTAGE * 8 /*barriers*/ + 128;
   }
 };
 
@@ -58,7 +58,8 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
   double* qs = ring + C::RING;                          // [d][BM] scaled queries
   double* mu_s = qs + (size_t)p.d * BM;                 // [BM]
   double* ss_s = mu_s + BM;                             // [WARPS_N][BM]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ss_s + C::WARPS_N * BM);
+  double* etab = ss_s + C::WARPS_N * BM;                // [64] 2^(j/64) for exp_neg
+  uint64_t* full = reinterpret_cast<uint64_t*>(etab + 64);
   uint64_t* empty = full + NSTAGE;
 
   const int tid = threadIdx.x;
@@ -67,6 +68,7 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
   const int nblk = Npad / BN;
   const long long ntiles = (p.Q + BM - 1) / BM;
   double* panel = p.scratch + (size_t)blockIdx.x * BM * Npad;
+  if (tid < 64) etab[tid] = exp2((double)tid * (1.0 / 64.0));
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS_WARPS); }
@@ -89,7 +91,8 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
       // chunk of training columns staged in the (idle) ring: xs[d][JCH] + alpha[JCH]
       int JCH = (C::RING / (d + 1)) & ~15;
       if (JCH > Npad) JCH = Npad;
-      double mu_part[BM / 64] = {};
+      constexpr int R = BM / 64;                       // m8 blocks per warp: their exp chains interleave (4R-way ILP)
+      double mu_part[R] = {};
       for (int j0 = 0; j0 < Npad; j0 += JCH) {
         const int jn = min(JCH, Npad - j0);
         named_bar_sync(1, NCONS);                      // previous chunk fully consumed / qs visible
@@ -99,31 +102,38 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
         }
         named_bar_sync(1, NCONS);
         const double* al = ring + d * JCH;
+        double macc[R] = {};
+        for (int jb = 0; jb < jn; jb += 16) {           // 4 k4-blocks per trip
+          const int jj = jb + (lane & 3);
+          double s[R][4] = {};
+          for (int i = 0; i < d; ++i) {
+            const double* xr = ring + i * JCH + jj;
+            const double x0 = xr[0], x1 = xr[4], x2 = xr[8], x3 = xr[12];
 #pragma unroll
-        for (int r = 0; r < BM / 64; ++r) {
-          const int mb = warp + r * NCONS_WARPS;
-          const int m = mb * 8 + (lane >> 2);
-          double macc = 0.0;
-          for (int jb = 0; jb < jn; jb += 16) {         // 4 k4-blocks per trip
-            const int jj = jb + (lane & 3);
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int i = 0; i < d; ++i) {
-              const double qv = qs[i * BM + m];
-              const double* xr = ring + i * JCH + jj;
-              double d0 = xr[0] - qv, d1 = xr[4] - qv, d2 = xr[8] - qv, d3 = xr[12] - qv;
-              s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+            for (int r = 0; r < R; ++r) {
+              const double qv = qs[i * BM + (warp + r * NCONS_WARPS) * 8 + (lane >> 2)];
+              const double d0 = x0 - qv, d1 = x1 - qv, d2 = x2 - qv, d3 = x3 - qv;
+              s[r][0] = fma(d0, d0, s[r][0]); s[r][1] = fma(d1, d1, s[r][1]);
+              s[r][2] = fma(d2, d2, s[r][2]); s[r][3] = fma(d3, d3, s[r][3]);
             }
-            double e0 = exp(-s0), e1 = exp(-s1), e2 = exp(-s2), e3 = exp(-s3);
-            macc = fma(e0, al[jj], macc); macc = fma(e1, al[jj + 4], macc);
-            macc = fma(e2, al[jj + 8], macc); macc = fma(e3, al[jj + 12], macc);
+          }
+          const double a0 = al[jj], a1 = al[jj + 4], a2 = al[jj + 8], a3 = al[jj + 12];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int mb = warp + r * NCONS_WARPS;
+            const double e0 = exp_neg(s[r][0], etab), e1 = exp_neg(s[r][1], etab);
+            const double e2 = exp_neg(s[r][2], etab), e3 = exp_neg(s[r][3], etab);
+            macc[r] = fma(e0, a0, macc[r]); macc[r] = fma(e1, a1, macc[r]);
+            macc[r] = fma(e2, a2, macc[r]); macc[r] = fma(e3, a3, macc[r]);
             double* dst = panel + ((size_t)((j0 + jb) >> 2) * (BM / 8) + mb) * 32 + lane;
             dst[0] = e0; dst[(BM / 8) * 32] = e1; dst[2 * (BM / 8) * 32] = e2; dst[3 * (BM / 8) * 32] = e3;
           }
-          mu_part[r] += macc;
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r) mu_part[r] += macc[r];
       }
 #pragma unroll
-      for (int r = 0; r < BM / 64; ++r) {
+      for (int r = 0; r < R; ++r) {
         double v = mu_part[r];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -346,6 +356,13 @@ __global__ void pack_xs_kernel(const double* __restrict__ X, int N, int d, int N
   }
 }
 
+__global__ void exp_neg_test_kernel(const double* __restrict__ s, int n, double* __restrict__ out) {
+  __shared__ double tab[64];
+  if (threadIdx.x < 64) tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = exp_neg(s[i], tab);
+}
+
 template <int BM, int BN, int NSTAGE>
 int launch_var_t(const PredictParams& p, int num_sms, cudaStream_t st) {
   using C = VarCfg<BM, BN, NSTAGE>;
@@ -366,12 +383,14 @@ int launch_var_t(const PredictParams& p, int num_sms, cudaStream_t st) {
 
 }  // namespace
 
-static inline int variant_bm(int v) { return v == 1 ? 128 : 64; }
-static inline int variant_bn(int v) { return v == 1 ? 128 : 256; }
+// variants: 0 = 64x256, 1 = 128x128 (default).  Two other schedules (warp-specialised builders, inline
+// builder) were measured slower and are archived with their profiles under profiles/r01_schedules_tried/.
+static inline int variant_bm(int v) { return v == 0 ? 64 : 128; }
+static inline int variant_bn(int v) { return v == 0 ? 256 : 128; }
 int predict_variant_bn(int variant) { return variant_bn(variant); }
 
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant) {
-  return (size_t)num_sms * variant_bm(variant) * Npad * 8;
+  return (size_t)num_sms * variant_bm(variant) * Npad * 8 ;
 }
 
 int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches) {
@@ -407,6 +426,11 @@ int launch_pack_linv(const double* Linv, int ld, int N, int Npad, int BN, double
   long total = linvf_total_tiles(Npad, BN) * (long)BN * 16;
   int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
   pack_linv_kernel<<<grid, 256, 0, st>>>(Linv, ld, N, Npad, BN, amp, LinvF, total);
+  return (int)cudaGetLastError();
+}
+
+int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st) {
+  exp_neg_test_kernel<<<64, 256, 0, st>>>(s, n, out);
   return (int)cudaGetLastError();
 }
 

@@ -123,6 +123,8 @@ int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double
 int apgp_get_alpha(apgp_handle* h, double* alpha);
 int apgp_get_linv(apgp_handle* h, double* linv);
 int apgp_get_chol(apgp_handle* h, double* L);
+/* exp(-s), s >= 0, as evaluated inside the fused predict kernel (table + degree-5 polynomial); host buffers */
+int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out);
 /* select the variance-kernel tiling: 0 = 64x256, 1 = 128x128 (default).  Call before factorize. */
 int apgp_set_variant(apgp_handle* h, int variant);
 

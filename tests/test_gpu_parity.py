@@ -190,3 +190,19 @@ def test_sampler_philox_statistics():
         assert 0.6 < a[:, c].std() / b[:, c].std() < 1.6
         assert stats.ks_2samp(a[:, c], b[:, c]).statistic < 0.2
     assert np.all(a >= -5) and np.all(a <= 5)
+
+
+def test_kernel_exp_matches_libm():
+    """The table+polynomial exp(-s) used inside the fused predict kernel: <= 2 ulp against numpy."""
+    import ctypes as C
+    from approxposterior_b200 import GP, kernels, _lib
+    gp = GP(kernel=kernels.ExpSquaredKernel([1.0], ndim=1))
+    rng = np.random.default_rng(0)
+    s = np.concatenate([rng.uniform(0, 700, 200000), rng.uniform(0, 3, 200000), [0.0, 1e-300, 1e-12, 699.999, 700.0, 750.0, 1e6]])
+    out = np.empty_like(s)
+    _lib.check(gp._lib.apgp_debug_exp_neg(gp._h, _lib.ptr(s), s.size, _lib.ptr(out)), "apgp_debug_exp_neg")
+    ref = np.exp(-s)
+    live = s < 700.0
+    rel = np.abs(out[live] - ref[live]) / ref[live]
+    assert rel.max() < 4.5e-16, rel.max()
+    assert np.all(out[~live] == 0.0)
