@@ -247,10 +247,13 @@ class ApproxPosterior(object):
                     if not hasattr(self, "gpPar"):
                         self.gpPar = list()
                     self.gpPar.append(currentHype)
-                self.gp = GP(kernel=self.gp.kernel, fit_mean=True, mean=self.gp.mean,
-                             white_noise=self.gp.white_noise, fit_white_noise=False)
-                self.gp.set_parameter_vector(currentHype)
-                self.gp.compute(self.theta, y=self.y)
+                if hasattr(self.gp, "rebuild"):          # foreign george-like GP (tests inject the CPU oracle)
+                    self.gp = self.gp.rebuild(currentHype, self.theta, self.y)
+                else:
+                    self.gp = GP(kernel=self.gp.kernel, fit_mean=True, mean=self.gp.mean,
+                                 white_noise=self.gp.white_noise, fit_white_noise=False)
+                    self.gp.set_parameter_vector(currentHype)
+                    self.gp.compute(self.theta, y=self.y)
                 if ii % optGPEveryN == 0:
                     self.optGP(seed=seed, method=gpMethod, options=gpOptions, p0=gpP0, nGPRestarts=nGPRestarts,
                                gpHyperPrior=gpHyperPrior)

@@ -315,14 +315,17 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
   if (P != 1 + (fit_amp ? 1 : 0) + d) return fail(APGP_ERR_ARG, "apgp_loglik_batch: P != 1 + fit_amp + d");
   if (R < 1) return APGP_OK;
   Guard g(h->device);
-  // chunk the restart axis so the workspace stays below ~4 GiB
+  const bool small = loglik_small_smem(N, d) <= 220 * 1024 && !getenv("APGP_LOGLIK_TILED");
+  // chunk the restart axis so the tiled path's workspace stays below ~4 GiB
   size_t per = (size_t)Np * Np * 8;
-  int Rc = (int)((4ull << 30) / per); if (Rc < 1) Rc = 1; if (Rc > R) Rc = R;
-  CUI(h->bK.reserve(per * Rc));
-  CUI(h->bDinv.reserve((size_t)Rc * Np * 64 * 8));
-  CUI(h->br.reserve((size_t)Rc * Np * 8));
-  CUI(h->bscal.reserve((size_t)(Rc > 2 + APGP_MAX_DIM ? Rc : 2 + APGP_MAX_DIM) * 8));
-  CUI(h->binfo.reserve((size_t)Rc * 4));
+  int Rc = small ? R : (int)((4ull << 30) / per); if (Rc < 1) Rc = 1; if (Rc > R) Rc = R;
+  if (!small) {
+    CUI(h->bK.reserve(per * Rc));
+    CUI(h->bDinv.reserve((size_t)Rc * Np * 64 * 8));
+    CUI(h->br.reserve((size_t)Rc * Np * 8));
+    CUI(h->binfo.reserve((size_t)Rc * 4));
+  }
+  CUI(h->bscal.reserve((size_t)(Rc > 2 + APGP_MAXD ? Rc : 2 + APGP_MAXD) * 8));
   CUI(h->bhyper.reserve((size_t)Rc * (3 + d) * 8));
   CUI(h->bll.reserve((size_t)Rc * 8));
   std::vector<double> rows((size_t)Rc * (3 + d));
@@ -341,12 +344,18 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
       else { row[0] = 0; row[1] = 1; row[2] = 1; for (int i = 0; i < d; ++i) row[3 + i] = 1; }
     }
     CU(cudaMemcpyAsync(h->bhyper.p, rows.data(), (size_t)rc * (3 + d) * 8, cudaMemcpyHostToDevice, h->stream));
-    FactorBatch fb{rc, N, Np, h->bK.as<double>(), h->bDinv.as<double>(), h->br.as<double>(), h->bscal.as<double>(),
-                   h->binfo.as<int>()};
     int nl = 0;
-    CUI(launch_build_K(h->X.as<double>(), h->y.as<double>(), N, d, h->bhyper.as<double>(), fb, h->stream)); ++nl;
-    CUI(launch_cholesky(fb, h->num_sms, h->stream, &nl));
-    CUI(launch_loglik_finish(fb, h->bll.as<double>(), h->stream)); ++nl;
+    if (small) {
+      // one restart per CTA, everything in shared memory: a single launch per optimiser round
+      CUI(launch_loglik_small(h->X.as<double>(), h->y.as<double>(), N, d, h->bhyper.as<double>(), rc,
+                              h->bll.as<double>(), h->stream)); ++nl;
+    } else {
+      FactorBatch fb{rc, N, Np, h->bK.as<double>(), h->bDinv.as<double>(), h->br.as<double>(), h->bscal.as<double>(),
+                     h->binfo.as<int>()};
+      CUI(launch_build_K(h->X.as<double>(), h->y.as<double>(), N, d, h->bhyper.as<double>(), fb, h->stream)); ++nl;
+      CUI(launch_cholesky(fb, h->num_sms, h->stream, &nl));
+      CUI(launch_loglik_finish(fb, h->bll.as<double>(), h->stream)); ++nl;
+    }
     CU(cudaMemcpyAsync(ll_host + r0, h->bll.p, (size_t)rc * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->launches += nl;

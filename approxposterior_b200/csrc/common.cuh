@@ -122,7 +122,7 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ t
   double res = fma(T, pm1, T);
   const int k = n >> 6;
   res = __hiloint2double(__double2hiint(res) + (k << 20), __double2loint(res));
-  return (s < 700.0) ? res : 0.0;                             // exp(-700) ~ 1e-304: flush, keeps 2^k normal
+  return (s >= 700.0) ? 0.0 : res;                            // exp(-700) ~ 1e-304: flush (keeps 2^k normal); NaN propagates
 }
 
 // Philox4x32-10 counter-based RNG (Salmon et al. 2011), for the device sampler.

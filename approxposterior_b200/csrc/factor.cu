@@ -366,6 +366,76 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restri
   }
 }
 
+
+// ---- one restart per CTA: covariance build + Cholesky + forward solve + log-likelihood, all in shared
+//      memory (packed lower triangle).  Used when N(N+1)/2 + N(d+2) doubles fit in 220 KB (N <= ~224).
+//      Replaces one gpUtils._nll evaluation (gpUtils.py:46-80) per CTA.
+__global__ void __launch_bounds__(256) loglik_small_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                           int N, int d, const double* __restrict__ hyper,
+                                                           double* __restrict__ ll_out) {
+  extern __shared__ __align__(16) double sm[];
+  double* K = sm;                                   // packed lower: K[i(i+1)/2 + j], j <= i
+  double* xs = K + (size_t)N * (N + 1) / 2;         // [N][d]
+  double* r = xs + (size_t)N * d;                   // [N] residual -> z
+  double* col = r + N;                              // [N] current column of L
+  __shared__ double red[256];
+  __shared__ int bad;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* h = hyper + (size_t)blockIdx.x * (3 + d);
+  const double mean = h[0], amp = h[1], noise = h[2];
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < N * d; e += 256) xs[e] = X[e];
+  for (int i = tid; i < N; i += 256) r[i] = y[i] - mean;
+  __syncthreads();
+  // covariance, row i handled by one warp at a time
+  for (int i = warp; i < N; i += 8) {
+    double* Ki = K + (size_t)i * (i + 1) / 2;
+    for (int j = lane; j <= i; j += 32) {
+      double s = 0.0;
+      for (int c = 0; c < d; ++c) { double df = xs[i * d + c] - xs[j * d + c]; s += df * df * h[3 + c]; }
+      double v = amp * exp(-0.5 * s);
+      if (i == j) v += noise;
+      Ki[j] = v;
+    }
+  }
+  __syncthreads();
+  double logdet = 0.0;                               // tracked by every thread identically
+  for (int j = 0; j < N; ++j) {
+    const double dj = K[(size_t)j * (j + 1) / 2 + j];
+    double s;
+    if (dj > 0.0 && dj < INFINITY) s = sqrt(dj);
+    else { s = 1.0; if (tid == 0) bad = 1; }
+    logdet += log(s);
+    const double inv = 1.0 / s;
+    const double zj = r[j] * inv;                    // forward substitution rides along
+    __syncthreads();                                 // everyone has read K_jj and r_j
+    if (tid == 0) r[j] = zj;
+    for (int i = j + 1 + tid; i < N; i += 256) {
+      const double l = K[(size_t)i * (i + 1) / 2 + j] * inv;
+      col[i] = l;
+      r[i] -= l * zj;
+    }
+    __syncthreads();
+    // trailing update K[i][c] -= L[i][j] L[c][j],  j < c <= i ; warp per row, lanes over c
+    for (int i = j + 1 + warp; i < N; i += 8) {
+      double* Ki = K + (size_t)i * (i + 1) / 2;
+      const double li = col[i];
+      for (int cc = j + 1 + lane; cc <= i; cc += 32) Ki[cc] -= li * col[cc];
+    }
+    __syncthreads();
+  }
+  double part = 0.0;
+  for (int i = tid; i < N; i += 256) part += r[i] * r[i];
+  red[tid] = part;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  if (tid == 0) {
+    double v = -0.5 * red[0] - logdet - 0.5 * N * 1.8378770664093454836;
+    if (bad || !(v == v) || v == INFINITY || v == -INFINITY) v = -INFINITY;
+    ll_out[blockIdx.x] = v;
+  }
+}
+
 bool g_attr_done = false;
 int ensure_attrs() {
   if (g_attr_done) return 0;
@@ -374,6 +444,7 @@ int ensure_attrs() {
   e = cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(gemm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
+  e = cudaFuncSetAttribute(loglik_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); if (e) return (int)e;
   g_attr_done = true;
   return 0;
 }
@@ -429,6 +500,15 @@ int launch_tri_inverse(const double* L, const double* Dinv, int Np, double* Linv
       if (launches) *launches += 2;
     }
   }
+  return (int)cudaGetLastError();
+}
+
+size_t loglik_small_smem(int N, int d) { return ((size_t)N * (N + 1) / 2 + (size_t)N * (d + 2)) * sizeof(double); }
+
+int launch_loglik_small(const double* X, const double* y, int N, int d, const double* hyper, int R, double* ll,
+                        cudaStream_t st) {
+  int e = ensure_attrs(); if (e) return e;
+  loglik_small_kernel<<<R, 256, loglik_small_smem(N, d), st>>>(X, y, N, d, hyper, ll);
   return (int)cudaGetLastError();
 }
 

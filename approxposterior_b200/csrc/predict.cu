@@ -270,6 +270,8 @@ predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
   const int d = p.d, Npad = p.Npad;
   double* xs = sm;                                // [d+1][JCH]
   double* qs = sm + (size_t)(d + 1) * JCH;        // [d][MEAN_QPT*MEAN_THREADS]
+  __shared__ double etab[64];
+  if (threadIdx.x < 64) etab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));
   constexpr int QB = MEAN_THREADS * MEAN_QPT;
   const int tid = threadIdx.x;
   const long long ntiles = (p.Q + QB - 1) / QB;
@@ -306,10 +308,10 @@ predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
         }
 #pragma unroll
         for (int u = 0; u < MEAN_QPT; ++u) {
-          acc[u] = fma(exp(-s[u][0]), al[j], acc[u]);
-          acc[u] = fma(exp(-s[u][1]), al[j + 1], acc[u]);
-          acc[u] = fma(exp(-s[u][2]), al[j + 2], acc[u]);
-          acc[u] = fma(exp(-s[u][3]), al[j + 3], acc[u]);
+          acc[u] = fma(exp_neg(s[u][0], etab), al[j], acc[u]);
+          acc[u] = fma(exp_neg(s[u][1], etab), al[j + 1], acc[u]);
+          acc[u] = fma(exp_neg(s[u][2], etab), al[j + 2], acc[u]);
+          acc[u] = fma(exp_neg(s[u][3], etab), al[j + 3], acc[u]);
         }
       }
     }

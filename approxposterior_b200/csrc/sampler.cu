@@ -25,6 +25,7 @@ struct Smem {
   double* nlp;     // [nw]
   double* fac;     // [nw]
   double* logu;    // [nw]
+  const double* etab;  // [64] 2^(j/64) for exp_neg
   int* colour;     // [nw]
   int* sidx;       // [nw]
   int* cidx;       // [nw]
@@ -45,13 +46,13 @@ __device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np) {
         for (int j = lane; j < p.N; j += 32) {
           double s = 0.0;
           for (int c = 0; c < d; ++c) { double df = sm.xs[c * Npad + j] - sm.q[i * d + c] * p.qscale[c]; s = fma(df, df, s); }
-          acc = fma(exp(-s), al[j], acc);
+          acc = fma(exp_neg(s, sm.etab), al[j], acc);
         }
       } else {
         for (int j = lane; j < p.N; j += 32) {
           double s = 0.0;
           for (int c = 0; c < d; ++c) { double df = p.Xs[(size_t)c * Npad + j] - sm.q[i * d + c] * p.qscale[c]; s = fma(df, df, s); }
-          acc = fma(exp(-s), p.alphaA[j], acc);
+          acc = fma(exp_neg(s, sm.etab), p.alphaA[j], acc);
         }
       }
 #pragma unroll
@@ -81,6 +82,9 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
   const int nw = p.nwalk, d = p.d, Ns = nw / 2, Npad = p.Npad;
   const long W = (long)p.nens * nw;
   Smem sm;
+  __shared__ double etab_s[64];
+  if (tid < 64) etab_s[tid] = exp2((double)tid * (1.0 / 64.0));
+  sm.etab = etab_s;
   double* f = reinterpret_cast<double*>(raw);
   sm.xs = nullptr;
   if (xs_in_smem) { sm.xs = f; f += (size_t)(d + 1) * Npad; }

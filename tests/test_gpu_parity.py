@@ -135,6 +135,22 @@ def test_loglik_batch_and_grad(fit_amp):
     np.testing.assert_allclose(g, g_o, rtol=1e-8, atol=1e-8 * np.max(np.abs(g_o)))
 
 
+def test_loglik_batch_fused_and_tiled_paths_agree(monkeypatch):
+    """N small enough for the one-restart-per-CTA shared-memory kernel: it must agree with the tiled
+    multi-launch path (forced with APGP_LOGLIK_TILED) and with the oracle."""
+    theta, y = rosenbrock_training(150)
+    gp, orc = make_pair(theta, y, np.zeros(2), amp=float(np.var(y)))
+    rng = np.random.default_rng(5)
+    P = np.column_stack([np.full(20, np.median(y)), rng.standard_normal((20, 3))])
+    ll_small = gp.log_likelihood_batch(P, y)
+    monkeypatch.setenv("APGP_LOGLIK_TILED", "1")
+    ll_tiled = gp.log_likelihood_batch(P, y)
+    np.testing.assert_allclose(ll_small, ll_tiled, rtol=1e-10)
+    for r in range(0, 20, 5):
+        orc.set_parameter_vector(P[r])
+        assert abs(ll_small[r] - orc.log_likelihood(y, quiet=True)) <= 1e-9 * abs(ll_small[r])
+
+
 def test_not_positive_definite_is_reported():
     from approxposterior_b200 import GP, kernels
     X = np.array([[0.0, 0.0], [0.0, 0.0], [1.0, 1.0]])      # duplicate point, no noise to speak of
@@ -198,7 +214,7 @@ def test_kernel_exp_matches_libm():
     from approxposterior_b200 import GP, kernels, _lib
     gp = GP(kernel=kernels.ExpSquaredKernel([1.0], ndim=1))
     rng = np.random.default_rng(0)
-    s = np.concatenate([rng.uniform(0, 700, 200000), rng.uniform(0, 3, 200000), [0.0, 1e-300, 1e-12, 699.999, 700.0, 750.0, 1e6]])
+    s = np.concatenate([rng.uniform(0, 700, 200000), rng.uniform(0, 3, 200000), [0.0, 1e-300, 1e-12, 699.999, 700.0, 750.0, 1e6, np.inf]])
     out = np.empty_like(s)
     _lib.check(gp._lib.apgp_debug_exp_neg(gp._h, _lib.ptr(s), s.size, _lib.ptr(out)), "apgp_debug_exp_neg")
     ref = np.exp(-s)
@@ -206,3 +222,6 @@ def test_kernel_exp_matches_libm():
     rel = np.abs(out[live] - ref[live]) / ref[live]
     assert rel.max() < 4.5e-16, rel.max()
     assert np.all(out[~live] == 0.0)
+    nan_out = np.empty(1)
+    _lib.check(gp._lib.apgp_debug_exp_neg(gp._h, _lib.ptr(np.array([np.nan])), 1, _lib.ptr(nan_out)), "apgp_debug_exp_neg")
+    assert np.isnan(nan_out[0])            # NaN queries must stay NaN (approx.py:185 maps them to -inf)
