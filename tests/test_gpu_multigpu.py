@@ -1,0 +1,86 @@
+"""N>1 GPU path: candidates / ensembles / restarts sharded over ranks with ONE all-gather (NCCL).
+The single-GPU result is the oracle: shards are independent, so gathered outputs must be bit-identical
+to running the same shards one after another on one device.  Skipped on single-GPU boxes."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _problem():
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-5, 5, size=(200, 3))
+    y = -0.5 * np.sum(X * X, axis=1) / 4.0
+    return X, y
+
+
+def _make_gp(device):
+    from approxposterior_b200 import GP, kernels
+    X, y = _problem()
+    gp = GP(kernel=kernels.ExpSquaredKernel([3.0, 3.0, 3.0], ndim=3), fit_mean=True, mean=float(np.median(y)),
+            white_noise=-12.0, device=device)
+    gp.compute(X, y=y)
+    return gp, y
+
+
+def _worker(rank, ws, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    try:
+        from approxposterior_b200 import dist as apd
+        gp, y = _make_gp(rank)
+        bounds = [(-5.0, 5.0)] * 3
+        theta, u = apd.scan_utility_sharded(gp, y, "bape", bounds, nCandidates=40000, seed=5)
+        rng = np.random.default_rng(11)
+        nens, nw = 4, 12
+        p0 = rng.uniform(-3, 3, size=(nens * nw, 3))
+        out = apd.run_ensembles_sharded(gp, y, p0, 60, bounds, nens, seed=21)
+        pb, mb = apd.best_restart_sharded(np.array([[rank, 1.0]]), np.array([-5.0 - rank]))
+        q.put((rank, theta, u, out["chain"], out["naccepted"], pb, mb))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_equals_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(30)
+    # every rank sees the same gathered results
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    # single-GPU oracle: run the two shards one after the other on device 0
+    from approxposterior_b200 import utility as ut
+    gp, y = _make_gp(0)
+    bounds = [(-5.0, 5.0)] * 3
+    bests = [ut.scanUtility(gp, y, "bape", bounds, nCandidates=20000, seed=5 * 1000003 + r, device_out=True)[:2]
+             for r in range(2)]
+    ib = int(np.argmin([b[1] for b in bests]))
+    assert np.array_equal(res[0][1], bests[ib][0]) and res[0][2] == bests[ib][1]
+    rng = np.random.default_rng(11)
+    p0 = rng.uniform(-3, 3, size=(4 * 12, 3))
+    halves = [gp.run_ensembles(y, p0[r * 24:(r + 1) * 24], 60, bounds, nens=2, seed=21 + 7919 * r) for r in range(2)]
+    assert np.array_equal(res[0][3], np.concatenate([h["chain"] for h in halves], axis=1))
+    assert np.array_equal(res[0][4], np.concatenate([h["naccepted"] for h in halves]))
+    assert res[0][6] == -5.0 and res[0][5][0] == 0
