@@ -38,7 +38,9 @@ struct DevBuf {
 struct apgp_handle {
   int device = 0, num_sms = 0;
   cudaStream_t stream = nullptr; bool own_stream = false;
-  int N = 0, d = 0, Np = 0, Npad = 0, variant = 1;   // 128x128 tiling measured faster (profiles/)
+  int N = 0, d = 0, Np = 0, Npad = 0;
+  int variant = 2;       // requested tiling: 2 = 256x64 (fastest measured, profiles/), 1 = 128x128, 0 = 64x256
+  int variant_eff = 2;   // tiling the current factorisation was packed for
   bool has_training = false, has_hyper = false, factored = false;
   double mean = 0, amp = 1, white_noise = -12;
   double log_metric[APGP_MAX_DIM];
@@ -90,7 +92,7 @@ int apgp_create(apgp_handle** out, int device) {
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   const char* v = getenv("APGP_PREDICT_VARIANT");
-  if (v) { int vv = atoi(v); h->variant = (vv == 0) ? 0 : 1; }
+  if (v) { int vv = atoi(v); h->variant = (vv >= 0 && vv <= 2) ? vv : 2; }
   *out = h;
   return APGP_OK;
 }
@@ -131,7 +133,7 @@ int apgp_synchronize(apgp_handle* h) {
 long long apgp_launch_count(const apgp_handle* h) { return h ? h->launches : 0; }
 
 int apgp_set_variant(apgp_handle* h, int variant) {
-  if (!h || variant < 0 || variant > 1) return fail(APGP_ERR_ARG, "apgp_set_variant");
+  if (!h || variant < 0 || variant > 2) return fail(APGP_ERR_ARG, "apgp_set_variant");
   h->variant = variant; h->factored = false;
   return APGP_OK;
 }
@@ -166,7 +168,9 @@ int apgp_factorize(apgp_handle* h, double* logdet, double* loglik, int* info) {
   if (!h->has_training || !h->has_hyper) return fail(APGP_ERR_ARG, "apgp_factorize: training set and hyper-parameters required");
   Guard g(h->device);
   const int N = h->N, d = h->d, Np = h->Np;
-  const int BN = predict_variant_bn(h->variant);
+  // the 256x64 tiling stages d x 256 scaled queries in shared memory: beyond d = 31 fall back to 128x128
+  h->variant_eff = (h->variant == 2 && d > 31) ? 1 : h->variant;
+  const int BN = predict_variant_bn(h->variant_eff);
   h->Npad = (N + BN - 1) / BN * BN;
   h->factored = false;
   if (info) *info = 0;
@@ -268,10 +272,10 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
   }
   int nl = 0;
   if (o->want_var) {
-    const size_t sb = predict_scratch_bytes(h->Npad, h->num_sms, h->variant);
+    const size_t sb = predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff);
     CUI(h->scratch.reserve(sb));
     p.scratch = h->scratch.as<double>();
-    CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant, &nl));
+    CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant_eff, &nl));
   } else {
     CUI(launch_predict_mean(p, h->num_sms, h->stream, &nl));
   }

@@ -385,10 +385,11 @@ int launch_var_t(const PredictParams& p, int num_sms, cudaStream_t st) {
 
 }  // namespace
 
-// variants: 0 = 64x256, 1 = 128x128 (default).  Two other schedules (warp-specialised builders, inline
+// variants (BM x BN): 0 = 64x256, 1 = 128x128, 2 = 256x64 (default: B fragments amortised over 8 m8 blocks,
+// smallest diagonal-block waste, no register spills).  Two other schedules (warp-specialised builders, inline
 // builder) were measured slower and are archived with their profiles under profiles/r01_schedules_tried/.
-static inline int variant_bm(int v) { return v == 0 ? 64 : 128; }
-static inline int variant_bn(int v) { return v == 0 ? 256 : 128; }
+static inline int variant_bm(int v) { return v == 0 ? 64 : (v == 2 ? 256 : 128); }
+static inline int variant_bn(int v) { return v == 0 ? 256 : (v == 2 ? 64 : 128); }
 int predict_variant_bn(int variant) { return variant_bn(variant); }
 
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant) {
@@ -398,6 +399,7 @@ size_t predict_scratch_bytes(int Npad, int num_sms, int variant) {
 int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches) {
   if (p.Q <= 0) return 0;
   if (launches) ++*launches;
+  if (variant == 2) return launch_var_t<256, 64, 4>(p, num_sms, st);
   if (variant == 1) return launch_var_t<128, 128, 5>(p, num_sms, st);
   return launch_var_t<64, 256, 4>(p, num_sms, st);
 }

@@ -125,7 +125,8 @@ int apgp_get_linv(apgp_handle* h, double* linv);
 int apgp_get_chol(apgp_handle* h, double* L);
 /* exp(-s), s >= 0, as evaluated inside the fused predict kernel (table + degree-5 polynomial); host buffers */
 int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out);
-/* select the variance-kernel tiling: 0 = 64x256, 1 = 128x128 (default).  Call before factorize. */
+/* select the variance-kernel tiling (queries x L^-1 rows per CTA tile): 0 = 64x256, 1 = 128x128,
+ * 2 = 256x64 (default).  Call before factorize. */
 int apgp_set_variant(apgp_handle* h, int variant);
 
 #ifdef __cplusplus
