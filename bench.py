@@ -32,6 +32,7 @@ N_TRAIN, DIM, Q_PER_GPU = 2048, 5, 1 << 20
 METRIC = "GP-surrogate lnprob evals/s (fp64 mean+var, N=2048, d=5)"
 UNIT = "evals/s"
 BOUNDS = [(-5.0, 5.0)] * DIM
+NCU_TRAFFIC_BYTES = 294.4e9      # dram__bytes_read.sum + dram__bytes_write.sum of one predict_var launch (profiles/)
 
 
 def flops_per_eval(N, d):
@@ -318,8 +319,13 @@ def run_gpu(args):
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": None,
-                             "kernel": "predict_var_kernel (fused K* panel + DMMA triangular GEMM + utility)",
+                             "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
+                             "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture "
+                                             "profiles/r01_predict_var_256x64_ncu_summary.txt): the K* slab is written "
+                                             "once (17 GB) and streamed back N/(2*64) times through a 13%-hit L2; "
+                                             "algorithmic I/O is 67 MB -- the kernel is FP64-pipe bound (DMMA pipe 94% "
+                                             "active), DRAM at 28% of peak",
+                             "kernel": "predict_var_kernel<256,64,4> (fused K* panel + DMMA triangular GEMM + utility)",
                              "kernel_ms": kernel_ms,
                              "flops_per_eval": flops_per_eval(N_TRAIN, DIM),
                              "peak_source": "cuBLAS DGEMM 8192^3 best-of-6 measured in this run "
