@@ -185,14 +185,24 @@ class ApproxPosterior(object):
                         break
 
     # ------------------------------------------------------------------ design-point selection
-    def _selectPoint(self, theta0, nMinObjRestarts, minObjMethod, minObjOptions, scanCandidates):
+    def _selectPoint(self, theta0, nMinObjRestarts, minObjMethod, minObjOptions, scanCandidates, scanPolish="device"):
+        """Next design point.  Default: the reference's multistart local minimisation (lock-step batched).
+        ``scanCandidates=n``: score n uniform candidates from ``bounds`` on the device in one launch, then
+        polish the winner either with a device-side shrinking-box search (``scanPolish="device"``) or with
+        the reference's local optimiser (``scanPolish="nelder-mead"`` etc.)."""
         if scanCandidates:
             kind = {ut.AGPUtility: "agp", ut.BAPEUtility: "bape", ut.JonesUtility: "jones"}[self.utility]
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            if scanPolish == "device":
+                best, ubest, _, _ = ut.scanUtility(self.gp, self.y, kind, self.bounds, nCandidates=int(scanCandidates),
+                                                   seed=seed, device_out=True, refineRounds=12)
+                if np.isfinite(self._lnprior(best)):
+                    return best, ubest
+                scanPolish = minObjMethod      # the Python prior is stricter than the box: fall through
             best, ubest, _, _ = ut.scanUtility(self.gp, self.y, kind, self.bounds, nCandidates=int(scanCandidates),
-                                               seed=int(np.random.randint(0, 2 ** 31 - 1)), device_out=True)
-            # polish the best candidate with the reference's local optimiser
+                                               seed=seed, device_out=True)
             thetaT, uT = ut.minimizeObjective(self.utility, self.y, self.gp, sampleFn=self.priorSample,
-                                              priorFn=self._lnprior, nRestarts=1, method=minObjMethod,
+                                              priorFn=self._lnprior, nRestarts=1, method=scanPolish,
                                               options=minObjOptions, bounds=self.bounds, theta0=None,
                                               args=(self.y, self.gp, self._lnprior), _start=best)
             if not (uT <= ubest):
@@ -207,7 +217,7 @@ class ApproxPosterior(object):
                       verbose=True, nGPRestarts=1, nMinObjRestarts=5, gpMethod="powell",
                       minObjMethod="nelder-mead", minObjOptions=None, runName="apRun", numNewPoints=1,
                       optGPEveryN=1, gpHyperPrior=gpUtils.defaultHyperPrior, args=None, scanCandidates=None,
-                      **kwargs):
+                      scanPolish="device", **kwargs):
         """Pick numNewPoints design points by minimising the (negative) utility, optionally evaluate the
         forward model there, grow the training set and refactor / re-optimise the GP
         (reference approx.py:527-754)."""
@@ -222,7 +232,8 @@ class ApproxPosterior(object):
         for ii in (_progress(range(numNewPoints)) if verbose else range(numNewPoints)):
             if self.algorithm == "alternate":
                 self.utility = ut.AGPUtility if ii % 2 == 0 else ut.BAPEUtility
-            thetaT, uT = self._selectPoint(theta0, nMinObjRestarts, minObjMethod, minObjOptions, scanCandidates)
+            thetaT, uT = self._selectPoint(theta0, nMinObjRestarts, minObjMethod, minObjOptions, scanCandidates,
+                                           scanPolish)
             newTheta.append(thetaT)
             if not computeLnLike:
                 continue

@@ -139,3 +139,17 @@ def test_run_posterior(engine, tmp_path):
     assert (tmp_path / "apRunAPFModelCache.npz").exists() and (tmp_path / "apRunAPGP.npz").exists()
     blobs = ap.sampler.get_blobs()
     assert blobs.dtype.names == ("lnprior",)
+
+
+def test_scan_refine_never_worse_than_scan():
+    from approxposterior_b200 import utility as ut
+    theta, y, gp = _rosen_setup(50, False)
+    bounds = [(-5, 5), (-5, 5)]
+    b0, u0, _, _ = ut.scanUtility(gp, y, "bape", bounds, nCandidates=20000, seed=3)
+    b1, u1, _, _ = ut.scanUtility(gp, y, "bape", bounds, nCandidates=20000, seed=3, refineRounds=10)
+    assert u1 <= u0 and np.all(np.abs(b1) <= 5.0)
+    # the refined point is a local minimum to optimiser precision: Nelder-Mead from it barely improves
+    from approxposterior_b200 import likelihood as lh
+    res = minimize(lambda x: ut.BAPEUtility(x, y, gp, lh.rosenbrockLnprior), b1, method="nelder-mead",
+                   options={"adaptive": True})
+    assert res.fun >= u1 - 1e-3 * max(1.0, abs(u1))

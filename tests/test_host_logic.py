@@ -211,3 +211,88 @@ def test_shard_bounds_cover_exactly():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _OracleGP(object):
+    """Factory for an oracle GP carrying the batched entry points + rebuild hook, so the whole
+    ApproxPosterior driver (lock-step restarts, design-point loop, host-rng MCMC) runs on CPU."""
+
+    @staticmethod
+    def make(ndim, metric, mean, white_noise=-12.0):
+        from oracle import GPOracle, UTILITY_BY_NAME
+
+        class G(GPOracle):
+            def rebuild(self, hype, theta, y):
+                g = G(self.ndim, np.exp(self.log_M), mean=self.mean, white_noise=self.white_noise)
+                g.set_parameter_vector(hype)
+                g.compute(theta)
+                return g
+
+            def predict_utility(self, y, t, kind, bounds=None, zeta=0.01):
+                mu, var = self.predict(y, t, return_var=True)
+                fn = UTILITY_BY_NAME[kind]
+                return mu, var, (fn(mu, var, np.max(y), zeta, True) if kind == "jones" else fn(mu, var, True))
+
+            def log_likelihood_batch(self, P, y):
+                p0 = self.get_parameter_vector()
+                out = []
+                for p in np.atleast_2d(P):
+                    self.set_parameter_vector(p)
+                    out.append(self.log_likelihood(y, quiet=True))
+                self.set_parameter_vector(p0)
+                self.recompute(quiet=True)
+                return np.array(out)
+
+        return G(ndim, metric, mean=mean, white_noise=white_noise)
+
+
+def test_approx_posterior_driver_on_oracle_gp(tmp_path):
+    """Host logic of ApproxPosterior.run (reference approx.py:229-524) end to end on the CPU oracle."""
+    from approxposterior_b200 import approx, likelihood as lh
+    np.random.seed(57)
+    bounds = [(-5, 5), (-5, 5)]
+    theta = lh.rosenbrockSample(30)
+    y = np.array([lh.rosenbrockLnlike(t) + lh.rosenbrockLnprior(t) for t in theta])
+    gp = _OracleGP.make(2, np.fabs(np.random.randn(2)), float(np.median(y)))
+    gp.compute(theta)
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lh.rosenbrockLnprior, lnlike=lh.rosenbrockLnlike,
+                                priorSample=lh.rosenbrockSample, bounds=bounds, algorithm="alternate")
+    ap.run(m=3, nmax=2, estBurnin=True, nGPRestarts=2, mcmcKwargs={"iterations": 300},
+           samplerKwargs={"nwalkers": 10, "engine": "host-rng"}, cache=True, runName=str(tmp_path / "ap"),
+           verbose=False, thinChains=True, timing=True, seed=3, convergenceCheck=True, nMinObjRestarts=3)
+    assert ap.theta.shape == (36, 2) and ap.y.shape == (36,)
+    assert len(ap.trainingTime) == 2 and len(ap.mcmcTime) == 2 and len(ap.iburns) == 2
+    assert len(ap.marginalMeans) == 2
+    chain = ap.sampler.get_chain()
+    assert chain.shape == (300, 10, 2) and np.all(np.abs(chain) <= 5)
+    for f in ("apAPFModelCache.npz", "apAPGP.npz", "apAPTiming.npz", "apConvergenceCache.npz", "ap1.npz"):
+        assert (tmp_path / f).exists(), f
+    cache = np.load(tmp_path / "apAPFModelCache.npz")
+    assert np.array_equal(cache["theta"], ap.theta) and np.array_equal(cache["y"], ap.y)
+    # _gpll conventions (approx.py:167-188)
+    assert ap._gpll(np.array([np.nan, np.nan])) == (-np.inf, np.nan) or np.isnan(ap._gpll(np.array([np.nan, np.nan]))[1])
+    assert ap._gpll(np.array([6.0, 0.0]))[0] == -np.inf
+    mu, lp = ap._gpll(np.array([0.5, 0.5]))
+    assert np.isfinite(mu) and lp == 0.0
+    lpb, blob = ap._gpll_batch(np.array([[0.5, 0.5], [6.0, 0.0], [np.nan, 1.0]]))
+    assert np.isclose(lpb[0], float(np.ravel(mu)[0])) and lpb[1] == -np.inf and lpb[2] == -np.inf and np.isnan(blob[1])
+    # MAP and a short Bayesian-optimisation loop run through the same drivers
+    m, v = ap.findMAP(nRestarts=3)
+    assert np.all(np.isfinite(m)) and np.isfinite(v)
+    soln = ap.bayesOpt(nmax=2, verbose=False, cache=False, nGPRestarts=1, nMinObjRestarts=2, findMAP=False, seed=5)
+    assert soln["nev"] == 2 and len(ap.y) == 38
+
+
+def test_approx_posterior_argument_validation():
+    from approxposterior_b200 import approx, likelihood as lh
+    theta = np.zeros((4, 2)); y = np.zeros(4)
+    with pytest.raises(ValueError):
+        approx.ApproxPosterior(None, y, lh.rosenbrockLnprior, lh.rosenbrockLnlike, lh.rosenbrockSample, [(-5, 5)] * 2, gp=1)
+    with pytest.raises(ValueError):
+        approx.ApproxPosterior(theta, y, lh.rosenbrockLnprior, lh.rosenbrockLnlike, lh.rosenbrockSample, [(-5, 5)], gp=1)
+    with pytest.raises(ValueError):
+        approx.ApproxPosterior(theta, y, lh.rosenbrockLnprior, lh.rosenbrockLnlike, lh.rosenbrockSample, [(-5, 5)] * 2,
+                               gp=1, algorithm="naive")
+    bad = theta.copy(); bad[0, 0] = np.inf
+    with pytest.raises(ValueError):
+        approx.ApproxPosterior(bad, y, lh.rosenbrockLnprior, lh.rosenbrockLnlike, lh.rosenbrockSample, [(-5, 5)] * 2, gp=1)

@@ -147,11 +147,37 @@ if "cfg4" in which:
 
 if "cfg1" in which:
     # README configuration: m0=50, m=20, nmax=2, 20 walkers x 2e4 steps, nGPRestarts=3
-    for engine in ("device", "host-rng"):
+    from oracle import UTILITY_BY_NAME, default_gp_oracle
+
+    class OracleGP(GPOracle):
+        """CPU oracle behind the same drivers (lock-step entry points + rebuild hook)."""
+        def rebuild(self, hype, theta, y):
+            g = OracleGP(self.ndim, np.exp(self.log_M), mean=self.mean, white_noise=self.white_noise)
+            g.set_parameter_vector(hype); g.compute(theta)
+            return g
+
+        def predict_utility(self, y, t, kind, bounds=None, zeta=0.01):
+            mu, var = self.predict(y, t, return_var=True)
+            fn = UTILITY_BY_NAME[kind]
+            return mu, var, (fn(mu, var, y.max(), zeta, True) if kind == "jones" else fn(mu, var, True))
+
+        def log_likelihood_batch(self, P, y):
+            p0 = self.get_parameter_vector(); out = []
+            for p in np.atleast_2d(P):
+                self.set_parameter_vector(p); out.append(self.log_likelihood(y, quiet=True))
+            self.set_parameter_vector(p0); self.recompute(quiet=True)
+            return np.array(out)
+
+    def readme_problem():
         np.random.seed(57)
-        bounds = [(-5, 5), (-5, 5)]
         theta = lh.rosenbrockSample(50)
         y = np.array([lh.rosenbrockLnlike(t) + lh.rosenbrockLnprior(t) for t in theta])
+        return theta, y
+
+    bounds = [(-5, 5), (-5, 5)]
+    for label, engine, scan in (("lock-step restarts", "device", None), ("lock-step restarts", "host-rng", None),
+                                ("device scan 65536 + device polish", "device", 65536)):
+        theta, y = readme_problem()
         gp = gpUtils.defaultGP(theta, y, white_noise=-12)
         prior = lh.BoxPrior(bounds) if engine == "device" else lh.rosenbrockLnprior
         ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=prior, lnlike=lh.rosenbrockLnlike,
@@ -159,9 +185,27 @@ if "cfg1" in which:
         t0 = time.perf_counter()
         ap.run(m=20, nmax=2, estBurnin=True, nGPRestarts=3, mcmcKwargs={"iterations": int(2.0e4)},
                samplerKwargs={"nwalkers": 20}, cache=False, verbose=False, thinChains=False, onlyLastMCMC=True,
-               timing=True, seed=57)
+               timing=True, seed=57, scanCandidates=scan)
         tot = time.perf_counter() - t0
         s = ap.sampler.get_chain(discard=ap.iburns[-1], flat=True, thin=ap.ithins[-1])
-        emit(config="cfg1", engine=engine, total_s=tot, trainingTime=ap.trainingTime, mcmcTime=ap.mcmcTime,
-             bape_iteration_s=float(np.mean(ap.trainingTime)), posterior_mean=s.mean(axis=0).tolist(),
-             posterior_std=s.std(axis=0).tolist(), iburn=int(ap.iburns[-1]), note="README.md:84-121 configuration")
+        emit(config="cfg1", acquisition=label, engine=engine, total_s=tot, trainingTime=ap.trainingTime,
+             mcmcTime=ap.mcmcTime, bape_iteration_s=float(np.mean(ap.trainingTime)),
+             posterior_mean=s.mean(axis=0).tolist(), posterior_std=s.std(axis=0).tolist(), iburn=int(ap.iburns[-1]),
+             note="README.md:84-121 configuration")
+    # the same drivers on the CPU oracle (one BAPE iteration + a 2000-step per-half-step-batched MCMC)
+    theta, y = readme_problem()
+    g0 = default_gp_oracle(theta, y)
+    gp = OracleGP(2, np.exp(g0.log_M), mean=g0.mean, white_noise=-12); gp.compute(theta)
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lh.rosenbrockLnprior, lnlike=lh.rosenbrockLnlike,
+                                priorSample=lh.rosenbrockSample, bounds=bounds, algorithm="bape")
+    ap.run(m=20, nmax=1, estBurnin=True, nGPRestarts=3, mcmcKwargs={"iterations": 2000},
+           samplerKwargs={"nwalkers": 20, "engine": "host-rng"}, cache=False, verbose=False, thinChains=False,
+           onlyLastMCMC=True, timing=True, seed=57)
+    # reference-shaped MCMC cost: one predict per walker per step (approx.py:178), extrapolated to 4e5 calls
+    t0 = time.perf_counter()
+    for i in range(2000):
+        ap.gp.predict(ap.y, ap.theta[i % 50:i % 50 + 1], return_var=False)
+    per_call = (time.perf_counter() - t0) / 2000
+    emit(config="cfg1-cpu-oracle", bape_iteration_s=ap.trainingTime[0], mcmc_2000_steps_batched_s=ap.mcmcTime[0],
+         mcmc_per_call_us=per_call * 1e6, mcmc_4e5_calls_extrapolated_s=per_call * 4e5, cores=os.cpu_count(),
+         note="restated george/emcee oracle through the same host drivers; george itself is not installable")
