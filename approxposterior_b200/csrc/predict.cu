@@ -408,13 +408,15 @@ int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, in
   if (p.Q <= 0) return 0;
   constexpr int QB = MEAN_THREADS * MEAN_QPT;
   const size_t qs_bytes = (size_t)p.d * QB * 8;
-  int JCH = (int)(((96 * 1024 - qs_bytes) / 8) / (p.d + 1)) & ~3;
+  // smem budget: 96 KB keeps 2 CTAs/SM for small d; large d needs more room for the staged queries
+  const size_t budget = (qs_bytes + 16 * 1024 <= 96 * 1024) ? 96 * 1024 : 200 * 1024;
+  int JCH = (int)(((budget - qs_bytes) / 8) / (p.d + 1)) & ~3;
   if (JCH > p.Npad) JCH = p.Npad;
   if (JCH < 4) return (int)cudaErrorInvalidValue;
   const size_t smem = (size_t)(p.d + 1) * JCH * 8 + qs_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(predict_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(predict_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }

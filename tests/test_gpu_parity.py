@@ -225,3 +225,29 @@ def test_kernel_exp_matches_libm():
     nan_out = np.empty(1)
     _lib.check(gp._lib.apgp_debug_exp_neg(gp._h, _lib.ptr(np.array([np.nan])), 1, _lib.ptr(nan_out)), "apgp_debug_exp_neg")
     assert np.isnan(nan_out[0])            # NaN queries must stay NaN (approx.py:185 maps them to -inf)
+
+
+@pytest.mark.parametrize("N,d", [(1, 1), (2, 2), (65, 31), (130, 32), (96, 20)])
+def test_edge_shapes(N, d):
+    """Smallest training sets and the largest supported dimensionalities (d = 32 switches the variance
+    kernel to its 128x128 tiling because the 256x64 one cannot stage 32 x 256 scaled queries)."""
+    rng = np.random.default_rng(N * 100 + d)
+    X = rng.uniform(-2, 2, size=(N, d))
+    y = rng.standard_normal(N)
+    logM = np.full(d, np.log(4.0 * d))
+    gp, orc = make_pair(X, y, logM, amp=1.7)
+    Xq = rng.uniform(-2, 2, size=(300, d))
+    check_predict(gp, orc, y, Xq, 1.7)
+    assert abs(gp.log_likelihood(y) - orc.log_likelihood(y)) <= 1e-9 * max(1.0, abs(orc.log_likelihood(y)))
+    P = np.vstack([gp.get_parameter_vector(), gp.get_parameter_vector() - 0.2])
+    ll = gp.log_likelihood_batch(P, y)
+    for p, v in zip(P, ll):
+        orc.set_parameter_vector(p)
+        assert abs(v - orc.log_likelihood(y, quiet=True)) <= 1e-9 * max(1.0, abs(v))
+
+
+def test_dimension_limits_are_reported():
+    from approxposterior_b200 import GP, kernels, _lib
+    gp = GP(kernel=kernels.ExpSquaredKernel(np.ones(33), ndim=33))
+    with pytest.raises(_lib.ApgpError):
+        gp.compute(np.zeros((4, 33)), y=np.zeros(4))
