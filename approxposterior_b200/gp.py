@@ -176,7 +176,7 @@ class GP(object):
             self._dirty = True
 
     # ------------------------------------------------------------------ predict
-    def _predict_raw(self, t, want_var, utility=None, bounds=None, ybest=0.0, zeta=0.01, want_mu=True):
+    def _predict_raw(self, t, want_var, utility=None, bounds=None, ybest=0.0, zeta=0.01, want_mu=True, out=None):
         opts = _lib.PredictOpts()
         opts.want_var = 1 if want_var else 0
         opts.utility = _lib.UTIL_KINDS[utility]
@@ -203,9 +203,15 @@ class GP(object):
             Q = t.shape[0]
             mk = lambda: np.empty(Q, dtype=np.float64)
             on_host = 1
-        mu = mk() if want_mu else None
-        var = mk() if want_var else None
-        util = mk() if utility not in (None, "none") else None
+        if out is not None:                      # caller-provided (e.g. pinned) result buffers, NumPy-style
+            mu, var, util = out
+            for o in (mu, var, util):
+                if o is not None and (o.shape != (Q,) or (on_host and (o.dtype != np.float64 or not o.flags.c_contiguous))):
+                    raise ValueError("out buffers must be contiguous float64 of shape (Q,)")
+        else:
+            mu = mk() if want_mu else None
+            var = mk() if want_var else None
+            util = mk() if utility not in (None, "none") else None
         _lib.check(self._lib.apgp_predict(self._h, _lib.ptr(t), Q, _lib.ptr(mu), _lib.ptr(var), _lib.ptr(util),
                                           C.byref(opts), on_host), "apgp_predict")
         return mu, var, util
@@ -222,13 +228,15 @@ class GP(object):
             return mu, var
         return mu
 
-    def predict_utility(self, y, t, utility, bounds=None, zeta=0.01):
+    def predict_utility(self, y, t, utility, bounds=None, zeta=0.01, out=None):
         """(mu, var, util) for every row of ``t`` with the reference's utility epilogue fused in
-        (utility.py:136,183,229-244) and ``+inf`` outside ``bounds`` (the priorFn gate)."""
+        (utility.py:136,183,229-244) and ``+inf`` outside ``bounds`` (the priorFn gate).
+        ``out=(mu, var, util)`` reuses caller-owned result buffers (pinned host memory makes the D2H
+        copies asynchronous-capable and skips three allocations per call)."""
         self._sync_y(y)
         self.recompute()
         return self._predict_raw(t, True, utility=str(utility).lower(), bounds=bounds,
-                                 ybest=float(np.max(self._y)), zeta=zeta)
+                                 ybest=float(np.max(self._y)), zeta=zeta, out=out)
 
     # ------------------------------------------------------------------ likelihood
     def log_likelihood(self, y, quiet=False):

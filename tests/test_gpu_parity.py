@@ -251,3 +251,22 @@ def test_dimension_limits_are_reported():
     gp = GP(kernel=kernels.ExpSquaredKernel(np.ones(33), ndim=33))
     with pytest.raises(_lib.ApgpError):
         gp.compute(np.zeros((4, 33)), y=np.zeros(4))
+
+
+def test_sampler_replay_large_training_set_global_path():
+    """(d+1) x N too large for shared memory: the sampler reads the training set through L2 instead."""
+    from oracle import stretch_move_oracle
+    from oracle.sampler_oracle import gpll_batch
+    N, d = 1300, 20
+    X, y, logM, _ = synthetic_gp_problem(N, d, seed=9)
+    gp, orc = make_pair(X, y, logM)
+    lo, hi = np.full(d, -5.0), np.full(d, 5.0)
+    nw, nsteps = 44, 15
+    rng = np.random.RandomState(4)
+    p0 = rng.uniform(-1, 1, size=(nw, d))
+    ref = stretch_move_oracle(lambda q: gpll_batch(orc, y, q, lo, hi), p0, nsteps, rng=rng, record=True)
+    out = gp.run_ensembles(y, p0, nsteps, bounds=list(zip(lo, hi)), nens=1,
+                           replay={k: ref[k][None] for k in ("inds", "zz", "rint", "logu")})
+    np.testing.assert_allclose(out["chain"], ref["chain"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out["log_prob"], ref["log_prob"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(out["naccepted"], ref["naccepted"])
