@@ -46,7 +46,8 @@ _SIGNATURES = {
     "apgp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.POINTER(PredictOpts), C.c_int]),
     "apgp_grad_log_likelihood": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
-    "apgp_loglik_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    "apgp_loglik_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                    C.c_void_p]),
     "apgp_sampler_run": (C.c_int, [C.c_void_p, C.POINTER(SamplerOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int]),
     "apgp_get_alpha": (C.c_int, [C.c_void_p, C.c_void_p]),

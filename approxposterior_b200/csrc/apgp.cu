@@ -48,7 +48,7 @@ struct apgp_handle {
   long long launches = 0;
   DevBuf X, y, K, Dinv, r, Linv, work, scal, info, hyper, Xs, alphaA, alpha, LinvF, scratch, qscale;
   DevBuf stage_in, stage_out;          // device staging for on_host calls
-  DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll;   // batched log-likelihood workspace
+  DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
 };
 
@@ -103,7 +103,7 @@ int apgp_destroy(apgp_handle* h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
                     &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->bK,
-                    &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->s_p0, &h->s_chain, &h->s_logp,
+                    &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
                     &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl};
   for (DevBuf* b : bufs) b->release();
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -312,7 +312,7 @@ int apgp_grad_log_likelihood(apgp_handle* h, int fit_amp, double* grad) {
 }
 
 int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fit_amp, double white_noise,
-                      double* ll_host) {
+                      double* ll_host, double* grad_host) {
   if (!h || !P_host || !ll_host) return fail(APGP_ERR_ARG, "apgp_loglik_batch: null argument");
   if (!h->has_training) return fail(APGP_ERR_ARG, "apgp_loglik_batch: no training set");
   const int d = h->d, N = h->N, Np = h->Np;
@@ -320,6 +320,9 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
   if (R < 1) return APGP_OK;
   Guard g(h->device);
   const bool small = loglik_small_smem(N, d) <= 220 * 1024 && !getenv("APGP_LOGLIK_TILED");
+  if (grad_host && !small)
+    return fail(APGP_ERR_ARG, "apgp_loglik_batch: batched gradients need the shared-memory path (N <= ~224); "
+                              "use apgp_grad_log_likelihood per vector");
   // chunk the restart axis so the tiled path's workspace stays below ~4 GiB
   size_t per = (size_t)Np * Np * 8;
   int Rc = small ? R : (int)((4ull << 30) / per); if (Rc < 1) Rc = 1; if (Rc > R) Rc = R;
@@ -332,6 +335,8 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
   CUI(h->bscal.reserve((size_t)(Rc > 2 + APGP_MAXD ? Rc : 2 + APGP_MAXD) * 8));
   CUI(h->bhyper.reserve((size_t)Rc * (3 + d) * 8));
   CUI(h->bll.reserve((size_t)Rc * 8));
+  if (grad_host) CUI(h->bgrad.reserve((size_t)Rc * (2 + d) * 8));
+  std::vector<double> gtmp(grad_host ? (size_t)Rc * (2 + d) : 0);
   std::vector<double> rows((size_t)Rc * (3 + d));
   std::vector<char> bad(R, 0);
   for (int r0 = 0; r0 < R; r0 += Rc) {
@@ -352,7 +357,9 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
     if (small) {
       // one restart per CTA, everything in shared memory: a single launch per optimiser round
       CUI(launch_loglik_small(h->X.as<double>(), h->y.as<double>(), N, d, h->bhyper.as<double>(), rc,
-                              h->bll.as<double>(), h->stream)); ++nl;
+                              h->bll.as<double>(), grad_host ? h->bgrad.as<double>() : nullptr, h->stream)); ++nl;
+      if (grad_host)
+        CU(cudaMemcpyAsync(gtmp.data(), h->bgrad.p, (size_t)rc * (2 + d) * 8, cudaMemcpyDeviceToHost, h->stream));
     } else {
       FactorBatch fb{rc, N, Np, h->bK.as<double>(), h->bDinv.as<double>(), h->br.as<double>(), h->bscal.as<double>(),
                      h->binfo.as<int>()};
@@ -363,6 +370,17 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
     CU(cudaMemcpyAsync(ll_host + r0, h->bll.p, (size_t)rc * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->launches += nl;
+    if (grad_host) {                         // [sum alpha, d/dlog_c, d/dlogM..] -> george order, amplitude slot optional
+      for (int r = 0; r < rc; ++r) {
+        const double* g = gtmp.data() + (size_t)r * (2 + d);
+        double* o = grad_host + (size_t)(r0 + r) * P;
+        int k = 0;
+        o[k++] = g[0];
+        if (fit_amp) o[k++] = g[1];
+        for (int i = 0; i < d; ++i) o[k++] = g[2 + i];
+        if (bad[r0 + r] || !isfinite(ll_host[r0 + r])) for (int i = 0; i < P; ++i) o[i] = 0.0;
+      }
+    }
   }
   for (int r = 0; r < R; ++r) if (bad[r] || !isfinite(ll_host[r])) ll_host[r] = -INFINITY;
   return APGP_OK;

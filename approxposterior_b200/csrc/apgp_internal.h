@@ -62,7 +62,7 @@ int launch_loglik_finish(const FactorBatch& fb, double* ll, cudaStream_t st);
 // fused one-restart-per-CTA path (everything in shared memory); usable when loglik_small_smem(N,d) <= 220 KB
 size_t loglik_small_smem(int N, int d);
 int launch_loglik_small(const double* X, const double* y, int N, int d, const double* hyper, int R, double* ll,
-                        cudaStream_t st);
+                        double* grad /*[R][2+d] or null*/, cudaStream_t st);
 // gradient pieces: Kinv = Linv^T Linv (lower), then tr-products
 int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv, const double* alpha,
                        const double* hyper_dev, int fit_amp, double* work /*[Np*Np]*/, double* grad_dev, cudaStream_t st,

@@ -370,9 +370,12 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restri
 // ---- one restart per CTA: covariance build + Cholesky + forward solve + log-likelihood, all in shared
 //      memory (packed lower triangle).  Used when N(N+1)/2 + N(d+2) doubles fit in 220 KB (N <= ~224).
 //      Replaces one gpUtils._nll evaluation (gpUtils.py:46-80) per CTA.
+//      With grad_out != nullptr the CTA goes on to alpha = L^{-T} z, inverts L in place, forms K^{-1} pair by pair
+//      and reduces  dl/dp = 1/2 tr[(alpha alpha^T - K^{-1}) dK/dp]  (george.GP.grad_log_likelihood, gpUtils.py:110):
+//      grad_out[r] = [ sum(alpha), d/dlog_constant, d/dlog M_0 .. ]   (the host drops the amplitude slot if unused).
 __global__ void __launch_bounds__(256) loglik_small_kernel(const double* __restrict__ X, const double* __restrict__ y,
                                                            int N, int d, const double* __restrict__ hyper,
-                                                           double* __restrict__ ll_out) {
+                                                           double* __restrict__ ll_out, double* __restrict__ grad_out) {
   extern __shared__ __align__(16) double sm[];
   double* K = sm;                                   // packed lower: K[i(i+1)/2 + j], j <= i
   double* xs = K + (size_t)N * (N + 1) / 2;         // [N][d]
@@ -409,10 +412,11 @@ __global__ void __launch_bounds__(256) loglik_small_kernel(const double* __restr
     const double inv = 1.0 / s;
     const double zj = r[j] * inv;                    // forward substitution rides along
     __syncthreads();                                 // everyone has read K_jj and r_j
-    if (tid == 0) r[j] = zj;
+    if (tid == 0) { r[j] = zj; K[(size_t)j * (j + 1) / 2 + j] = s; }
     for (int i = j + 1 + tid; i < N; i += 256) {
       const double l = K[(size_t)i * (i + 1) / 2 + j] * inv;
       col[i] = l;
+      K[(size_t)i * (i + 1) / 2 + j] = l;           // keep L (the gradient stage inverts it in place)
       r[i] -= l * zj;
     }
     __syncthreads();
@@ -434,6 +438,75 @@ __global__ void __launch_bounds__(256) loglik_small_kernel(const double* __restr
     if (bad || !(v == v) || v == INFINITY || v == -INFINITY) v = -INFINITY;
     ll_out[blockIdx.x] = v;
   }
+  if (grad_out == nullptr) return;
+  double* g_out = grad_out + (size_t)blockIdx.x * (2 + d);
+  __syncthreads();
+  if (bad) {                                          // quiet=True convention: zeros when the factorisation failed
+    for (int c = tid; c < 2 + d; c += 256) g_out[c] = 0.0;
+    return;
+  }
+  // ---- alpha = L^{-T} z (in r): back substitution, row j of L is contiguous
+  for (int j = N - 1; j >= 0; --j) {
+    const double* Lj = K + (size_t)j * (j + 1) / 2;
+    const double aj = r[j] / Lj[j];
+    __syncthreads();
+    if (tid == 0) r[j] = aj;
+    for (int i = tid; i < j; i += 256) r[i] -= Lj[i] * aj;
+    __syncthreads();
+  }
+  // ---- L <- L^{-1} in place, column by column from the right:
+  //      inv[j][j] = 1/L_jj ; inv[i][j] = -inv_jj * sum_{k=j+1..i} inv[i][k] L[k][j]   (i > j)
+  for (int j = N - 1; j >= 0; --j) {
+    const double ljj = K[(size_t)j * (j + 1) / 2 + j];
+    for (int i = j + 1 + tid; i < N; i += 256) col[i] = K[(size_t)i * (i + 1) / 2 + j];
+    __syncthreads();
+    const double ijj = 1.0 / ljj;
+    for (int i = j + 1 + tid; i < N; i += 256) {
+      const double* Ii = K + (size_t)i * (i + 1) / 2;
+      double s = 0.0;
+      for (int k = j + 1; k <= i; ++k) s += Ii[k] * col[k];
+      K[(size_t)i * (i + 1) / 2 + j] = -s * ijj;
+    }
+    if (tid == 0) K[(size_t)j * (j + 1) / 2 + j] = ijj;
+    __syncthreads();
+  }
+  // ---- pairs (a >= b): K^{-1}_ab = sum_{c >= a} inv[c][a] inv[c][b], then the trace products
+  double accs[APGP_MAXD + 1];
+  for (int c = 0; c <= d; ++c) accs[c] = 0.0;
+  const int npairs = N * (N + 1) / 2;
+  for (int pidx = tid; pidx < npairs; pidx += 256) {
+    int a = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
+    while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
+    while (a * (a + 1) / 2 > pidx) --a;
+    const int b = pidx - a * (a + 1) / 2;
+    double kinv = 0.0;
+    for (int cc = a; cc < N; ++cc) {
+      const double* Ic = K + (size_t)cc * (cc + 1) / 2;
+      kinv = fma(Ic[a], Ic[b], kinv);
+    }
+    double s = 0.0, df2[APGP_MAXD];
+    for (int c = 0; c < d; ++c) {
+      const double df = xs[a * d + c] - xs[b * d + c];
+      df2[c] = 0.5 * df * df * h[3 + c];
+      s += df2[c];
+    }
+    const double gk = ((a == b) ? 0.5 : 1.0) * (r[a] * r[b] - kinv) * amp * exp(-s);
+    accs[0] += gk;
+    for (int c = 0; c < d; ++c) accs[1 + c] += gk * df2[c];
+  }
+  for (int c = 0; c <= d; ++c) {
+    red[tid] = accs[c];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    if (tid == 0) g_out[1 + c] = red[0];
+    __syncthreads();
+  }
+  double sa = 0.0;
+  for (int i = tid; i < N; i += 256) sa += r[i];
+  red[tid] = sa;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  if (tid == 0) g_out[0] = red[0];
 }
 
 bool g_attr_done = false;
@@ -506,9 +579,9 @@ int launch_tri_inverse(const double* L, const double* Dinv, int Np, double* Linv
 size_t loglik_small_smem(int N, int d) { return ((size_t)N * (N + 1) / 2 + (size_t)N * (d + 2)) * sizeof(double); }
 
 int launch_loglik_small(const double* X, const double* y, int N, int d, const double* hyper, int R, double* ll,
-                        cudaStream_t st) {
+                        double* grad, cudaStream_t st) {
   int e = ensure_attrs(); if (e) return e;
-  loglik_small_kernel<<<R, 256, loglik_small_smem(N, d), st>>>(X, y, N, d, hyper, ll);
+  loglik_small_kernel<<<R, 256, loglik_small_smem(N, d), st>>>(X, y, N, d, hyper, ll, grad);
   return (int)cudaGetLastError();
 }
 

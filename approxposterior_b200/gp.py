@@ -261,10 +261,12 @@ class GP(object):
         _lib.check(self._lib.apgp_grad_log_likelihood(self._h, fit_amp, _lib.ptr(g)), "apgp_grad_log_likelihood")
         return g if self.fit_mean else g[1:]
 
-    def log_likelihood_batch(self, P, y):
+    def log_likelihood_batch(self, P, y, return_grad=False):
         """log-likelihood of ``y`` for every row of ``P`` (george parameter-vector layout) in one
         batched device pass; ``-inf`` where the covariance is not positive definite
-        (the quiet=True convention of gpUtils._nll, gpUtils.py:78-79).  Leaves the GP untouched."""
+        (the quiet=True convention of gpUtils._nll, gpUtils.py:78-79).  ``return_grad`` adds the
+        gradients (rows of zeros where the likelihood is -inf, as grad_log_likelihood(quiet=True)).
+        Leaves the GP's own hyper-parameters untouched."""
         P = np.ascontiguousarray(np.atleast_2d(np.asarray(P, dtype=np.float64)))
         if P.shape[1] != len(self):
             raise ValueError("dimension mismatch")
@@ -272,12 +274,28 @@ class GP(object):
         if not self._training_uploaded:
             self._upload_training()
         fit_amp = 1 if self.kernel.fit_amp else 0
-        if not self.fit_mean:
-            P = np.ascontiguousarray(np.hstack([np.full((P.shape[0], 1), self.mean), P]))
-        ll = np.empty(P.shape[0])
-        _lib.check(self._lib.apgp_loglik_batch(self._h, _lib.ptr(P), P.shape[0], P.shape[1], fit_amp,
-                                               self.white_noise, _lib.ptr(ll)), "apgp_loglik_batch")
-        return ll
+        Pfull = P if self.fit_mean else np.ascontiguousarray(np.hstack([np.full((P.shape[0], 1), self.mean), P]))
+        ll = np.empty(Pfull.shape[0])
+        grad = np.empty_like(Pfull) if return_grad else None
+        N, d = self._x.shape
+        fused = (N * (N + 1) // 2 + N * (d + 2)) * 8 <= 220 * 1024
+        if return_grad and not fused:
+            # large N: one factorisation per vector on the single-GP path (explicit inverse + trace products)
+            keep = self.get_parameter_vector()
+            for r in range(P.shape[0]):
+                self.set_parameter_vector(P[r])
+                ll[r] = self.log_likelihood(self._y, quiet=True)
+                g = self.grad_log_likelihood(self._y, quiet=True)
+                grad[r] = g if self.fit_mean else np.concatenate([[0.0], g])
+            self.set_parameter_vector(keep)
+            self.recompute(quiet=True)
+        else:
+            _lib.check(self._lib.apgp_loglik_batch(self._h, _lib.ptr(Pfull), Pfull.shape[0], Pfull.shape[1], fit_amp,
+                                                   self.white_noise, _lib.ptr(ll), _lib.ptr(grad)),
+                       "apgp_loglik_batch")
+        if not return_grad:
+            return ll
+        return ll, (grad if self.fit_mean else grad[:, 1:])
 
     # ------------------------------------------------------------------ sampler
     def run_ensembles(self, y, p0, nsteps, bounds, nens=1, a=2.0, seed=0, thin=1, lnprior_const=0.0, replay=None):

@@ -46,14 +46,24 @@ def _grad_nll(p, gp, y, priorFn=None):
     return -gp.grad_log_likelihood(y, quiet=True)
 
 
-def _nll_batch(P, gp, y, priorFn=None):
-    """``_nll`` for a list of parameter vectors with one batched device evaluation."""
+def _nll_batch(P, gp, y, priorFn=None, with_grad=False):
+    """``_nll`` (and, with_grad, ``_grad_nll``) for a list of parameter vectors with one batched device
+    evaluation.  Returns a list of floats, or of (nll, grad_nll) pairs."""
     P = [np.asarray(p, dtype=np.float64) for p in P]
     ok = np.array([priorFn is None or np.isfinite(priorFn(p)) for p in P], dtype=bool)
     out = np.full(len(P), np.inf)
+    gout = [np.full_like(p, np.inf) for p in P]              # prior rejection: gpUtils.py:105-107
     if np.any(ok):
-        ll = gp.log_likelihood_batch(np.array([p for p, k in zip(P, ok) if k]), y)
+        Pok = np.array([p for p, k in zip(P, ok) if k])
+        if with_grad:
+            ll, g = gp.log_likelihood_batch(Pok, y, return_grad=True)
+            for i, gi in zip(np.nonzero(ok)[0], g):
+                gout[i] = -gi
+        else:
+            ll = gp.log_likelihood_batch(Pok, y)
         out[ok] = np.where(np.isfinite(ll), -ll, np.inf)
+    if with_grad:
+        return [(float(f), g) for f, g in zip(out, gout)]
     return out
 
 
@@ -83,9 +93,9 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
 
     Start points are drawn exactly as the reference draws them (one ``np.random.randn()`` per
     kernel parameter per restart, gpUtils.py:227; ``seed`` is accepted and unused, as there).
-    With ``batched`` (default) and a derivative-free method the restarts advance in lock step and
-    every round of objective calls is one ``log_likelihood_batch`` launch; gradient methods use
-    the single-GP ``grad_log_likelihood`` path sequentially.
+    With ``batched`` (default) the restarts advance in lock step and every round of objective calls
+    is one ``log_likelihood_batch`` launch -- for gradient methods the same launch also returns the
+    gradients (fused one-restart-per-CTA kernel while the training set fits in shared memory).
     """
     y = np.asarray(y, dtype=np.float64)
     npar = len(gp.get_parameter_vector())
@@ -98,13 +108,16 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
         x0s.append(np.asarray(x0, dtype=np.float64))
 
     derivative_free = method in ["nelder-mead", "powell", "cg"]
-    use_batch = batched and derivative_free and hasattr(gp, "log_likelihood_batch")
+    use_batch = batched and hasattr(gp, "log_likelihood_batch")
 
     if use_batch:
+        # derivative-free: f(x) -> nll; gradient methods: f(x) -> (nll, grad_nll) in the same batched launch
         def worker(wid, f):
-            return minimize(f, x0s[wid], method=method, jac=None, bounds=None, options=options)["x"]
+            return minimize(f, x0s[wid], method=method, jac=None if derivative_free else True, bounds=None,
+                            options=options)["x"]
 
-        res, ev = run_lockstep(nGPRestarts, lambda P: _nll_batch(P, gp, y, gpHyperPrior), worker)
+        res, ev = run_lockstep(nGPRestarts,
+                               lambda P: _nll_batch(P, gp, y, gpHyperPrior, with_grad=not derivative_free), worker)
         optimizeGP.last_stats = dict(batches=ev.nbatches, evals=ev.nevals)
         mll = list(gp.log_likelihood_batch(np.array(res), y))
     else:

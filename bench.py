@@ -330,6 +330,9 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
+    if world > 1:                     # all collectives are done: release the other ranks before rank 0's CPU legs
+        dist.barrier()
+        dist.destroy_process_group()
     bape = None
     if rank == 0 and not args.no_bape:
         bape = bape_iteration_time()
@@ -366,8 +369,6 @@ def run_gpu(args):
                 "cpu_baseline": cpu,
                 "bape_iteration": bape}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

@@ -91,9 +91,12 @@ int apgp_grad_log_likelihood(apgp_handle* h, int fit_amp, double* grad);
  * evaluates one at a time inside optimizeGP's restarts (gpUtils.py:223-247).
  * P_host [R][P], rows in george order [mean, (log_constant), log M_0 .. log M_{d-1}], P = 1+fit_amp+d.
  * ll_host [R]: log-likelihood, -inf when not positive definite / non-finite (quiet=True semantics).
+ * grad_host [R][P] or NULL: gradient of the log-likelihood in the same parameter order (what gpUtils._grad_nll,
+ * gpUtils.py:83-111, evaluates one vector at a time); zeros where ll is -inf.  Batched gradients use the
+ * one-restart-per-CTA shared-memory kernel and need N(N+1)/2 + N(d+2) doubles <= 220 KB (N <= ~224).
  * Does not disturb the handle's current factorisation. */
 int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fit_amp, double white_noise,
-                      double* ll_host);
+                      double* ll_host, double* grad_host);
 
 typedef struct apgp_sampler_opts {
   int nens;                      /* independent ensembles */

@@ -135,6 +135,29 @@ def test_loglik_batch_and_grad(fit_amp):
     np.testing.assert_allclose(g, g_o, rtol=1e-8, atol=1e-8 * np.max(np.abs(g_o)))
 
 
+@pytest.mark.parametrize("N,fit_amp", [(40, True), (150, False), (224, True), (300, True)])
+def test_loglik_batch_gradients(N, fit_amp):
+    """Batched gradients: fused shared-memory kernel up to N ~ 224, per-vector path beyond; both vs the oracle."""
+    theta, y = rosenbrock_training(N)
+    gp, orc = make_pair(theta, y, np.zeros(2), amp=float(np.var(y)) if fit_amp else None)
+    rng = np.random.default_rng(N)
+    R = 9
+    P = np.column_stack([np.full(R, np.median(y))] + [0.7 * rng.standard_normal(R) for _ in range(len(gp) - 1)])
+    P[4, -1] = np.nan
+    keep = gp.get_parameter_vector().copy()
+    ll, g = gp.log_likelihood_batch(P, y, return_grad=True)
+    assert np.array_equal(gp.get_parameter_vector(), keep)
+    for r in range(R):
+        if not np.all(np.isfinite(P[r])):
+            assert ll[r] == -np.inf and np.all(g[r] == 0)
+            continue
+        orc.set_parameter_vector(P[r])
+        ref_ll = orc.log_likelihood(y, quiet=True)
+        ref_g = orc.grad_log_likelihood(y, quiet=True)
+        assert abs(ll[r] - ref_ll) <= 1e-9 * abs(ref_ll)
+        np.testing.assert_allclose(g[r], ref_g, rtol=1e-7, atol=1e-8 * np.max(np.abs(ref_g)))
+
+
 def test_loglik_batch_fused_and_tiled_paths_agree(monkeypatch):
     """N small enough for the one-restart-per-CTA shared-memory kernel: it must agree with the tiled
     multi-launch path (forced with APGP_LOGLIK_TILED) and with the oracle."""
