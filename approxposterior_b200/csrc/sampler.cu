@@ -22,56 +22,67 @@ struct Smem {
   double* lp;      // [nw]
   double* blob;    // [nw]
   double* q;       // [nw][d]   proposals (initial pass evaluates all nw walkers)
+  double* sq;      // [nw][d]   the same rows scaled for the kernel distance
   double* nlp;     // [nw]
   double* fac;     // [nw]
   double* logu;    // [nw]
   const double* etab;  // [64] 2^(j/64) for exp_neg
+  unsigned long long* key;  // [nw] random keys for the colouring
   int* colour;     // [nw]
   int* sidx;       // [nw]
   int* cidx;       // [nw]
   int* ok;         // [nw]
 };
 
-// lnprob for the `np` rows of sm.q (warp per row, lanes over training points)
+// lnprob for the `np` rows of sm.q.  A warp takes two rows per pass (they share every training-set load),
+// lanes stride over the training points; sm.sq holds the rows pre-scaled by sqrt(1/(2 M_i)).
 __device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int d = p.d, Npad = p.Npad;
-  for (int i = warp; i < np; i += nwarps) {
-    double acc = 0.0;
-    const int oki = sm.ok[i];
+  for (int i0 = 2 * warp; i0 < np; i0 += 2 * nwarps) {
+    const int i1 = (i0 + 1 < np) ? i0 + 1 : i0;
+    const int ok0 = sm.ok[i0], ok1 = sm.ok[i1];
     __syncwarp();
-    if (oki) {
-      if (sm.xs) {
-        const double* al = sm.xs + (size_t)d * Npad;
-        for (int j = lane; j < p.N; j += 32) {
-          double s = 0.0;
-          for (int c = 0; c < d; ++c) { double df = sm.xs[c * Npad + j] - sm.q[i * d + c] * p.qscale[c]; s = fma(df, df, s); }
-          acc = fma(exp_neg(s, sm.etab), al[j], acc);
+    double acc0 = 0.0, acc1 = 0.0;
+    if (ok0 | ok1) {
+      const double* xs = sm.xs ? sm.xs : p.Xs;
+      const double* al = sm.xs ? sm.xs + (size_t)d * Npad : p.alphaA;
+      const double* q0 = sm.sq + i0 * d;
+      const double* q1 = sm.sq + i1 * d;
+      for (int j = lane; j < p.N; j += 32) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int c = 0; c < d; ++c) {
+          const double x = xs[(size_t)c * Npad + j];
+          const double d0 = x - q0[c], d1 = x - q1[c];
+          s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
         }
-      } else {
-        for (int j = lane; j < p.N; j += 32) {
-          double s = 0.0;
-          for (int c = 0; c < d; ++c) { double df = p.Xs[(size_t)c * Npad + j] - sm.q[i * d + c] * p.qscale[c]; s = fma(df, df, s); }
-          acc = fma(exp_neg(s, sm.etab), p.alphaA[j], acc);
-        }
+        const double a = al[j];
+        acc0 = fma(exp_neg(s0, sm.etab), a, acc0);
+        acc1 = fma(exp_neg(s1, sm.etab), a, acc1);
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+      }
     }
-    if (lane == 0) {
-      double mu = p.mean + acc;
-      bool fin = oki && (mu == mu) && (fabs(mu) < INFINITY);
-      sm.nlp[i] = fin ? mu : -INFINITY;
-      sm.ok[i] = fin ? 1 : 0;
+    if (lane < 2) {
+      const int i = lane ? i1 : i0;
+      const int oki = lane ? ok1 : ok0;
+      const double mu = p.mean + (lane ? acc1 : acc0);
+      const bool fin = oki && (mu == mu) && (fabs(mu) < INFINITY);
+      if (lane == 0 || i1 != i0) { sm.nlp[i] = fin ? mu : -INFINITY; sm.ok[i] = fin ? 1 : 0; }
     }
   }
 }
 
-__device__ __forceinline__ int prior_ok(const SamplerParams& p, const double* x) {
+// prior gate on the raw row + its scaled copy for eval_rows
+__device__ __forceinline__ int stage_row(const SamplerParams& p, const Smem& sm, int i) {
   int ok = 1;
   for (int c = 0; c < p.d; ++c) {
-    double v = x[c];
+    const double v = sm.q[i * p.d + c];
     ok = ok && (v == v) && (v >= p.lo[c]) && (v <= p.hi[c]);
+    sm.sq[i * p.d + c] = v * p.qscale[c];
   }
   return ok;
 }
@@ -92,9 +103,11 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
   sm.lp = f; f += nw;
   sm.blob = f; f += nw;
   sm.q = f; f += nw * d;
+  sm.sq = f; f += nw * d;
   sm.nlp = f; f += nw;
   sm.fac = f; f += nw;
   sm.logu = f; f += nw;
+  sm.key = reinterpret_cast<unsigned long long*>(f); f += nw;
   int* ip = reinterpret_cast<int*>(f);
   sm.colour = ip; ip += nw;
   sm.sidx = ip; ip += nw;
@@ -110,7 +123,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
     sm.coords[idx] = v; sm.q[idx] = v;
   }
   __syncthreads();
-  for (int w = tid; w < nw; w += blockDim.x) sm.ok[w] = prior_ok(p, sm.q + w * d);
+  for (int w = tid; w < nw; w += blockDim.x) sm.ok[w] = stage_row(p, sm, w);
   __syncthreads();
   eval_rows(p, sm, nw);
   __syncthreads();
@@ -124,19 +137,28 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
     // ---- colours
     if (replay) {
       for (int w = tid; w < nw; w += blockDim.x) sm.colour[w] = p.r_inds[((size_t)e * p.nsteps + step) * nw + w];
-    } else if (tid == 0) {
-      for (int w = 0; w < nw; ++w) sm.colour[w] = w & 1;
-      for (int i = nw - 1; i >= 1; --i) {          // Fisher-Yates
-        uint32_t o[4]; rng.gen((uint32_t)e, (uint32_t)step, 0x10000u, (uint32_t)i, o);
-        int j = (int)(((uint64_t)o[0] * (uint64_t)(i + 1)) >> 32);
-        int t = sm.colour[i]; sm.colour[i] = sm.colour[j]; sm.colour[j] = t;
+    } else {
+      // uniformly random half/half colouring (same law as emcee's shuffle of arange(nw) % 2): every walker
+      // draws a key, the nw/2 smallest keys are colour 0.  Fully parallel -- no serial Fisher-Yates.
+      for (int w = tid; w < nw; w += blockDim.x) {
+        uint32_t o[4]; rng.gen((uint32_t)e, (uint32_t)step, 0x10000u, (uint32_t)w, o);
+        sm.key[w] = ((uint64_t)o[0] << 32) | o[1];
+      }
+      __syncthreads();
+      for (int w = tid; w < nw; w += blockDim.x) {
+        const uint64_t kw = sm.key[w];
+        int rank = 0;
+        for (int v = 0; v < nw; ++v) { const uint64_t kv = sm.key[v]; rank += (kv < kw) || (kv == kw && v < w); }
+        sm.colour[w] = rank < Ns ? 0 : 1;
       }
     }
     __syncthreads();
     for (int split = 0; split < 2; ++split) {
-      if (tid == 0) {
-        int a = 0, b = 0;
-        for (int w = 0; w < nw; ++w) { if (sm.colour[w] == split) sm.sidx[a++] = w; else sm.cidx[b++] = w; }
+      for (int w = tid; w < nw; w += blockDim.x) {       // position of w among the walkers of its colour
+        const int cw = sm.colour[w];
+        int pos = 0;
+        for (int v = 0; v < w; ++v) pos += (sm.colour[v] == cw);
+        if (cw == split) sm.sidx[pos] = w; else sm.cidx[pos] = w;
       }
       __syncthreads();
       for (int i = tid; i < Ns; i += blockDim.x) {
@@ -159,7 +181,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
         for (int c = 0; c < d; ++c) sm.q[i * d + c] = cs[c] - (cs[c] - ss[c]) * zz;
         sm.fac[i] = (d - 1.0) * log(zz);
         sm.logu[i] = lu;
-        sm.ok[i] = prior_ok(p, sm.q + i * d);
+        sm.ok[i] = stage_row(p, sm, i);
       }
       __syncthreads();
       eval_rows(p, sm, Ns);
@@ -197,7 +219,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
 
 int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   if (p.nwalk < 2 || (p.nwalk & 1) || p.nwalk > 1024 || p.nens < 1) return (int)cudaErrorInvalidValue;
-  const size_t small = (size_t)p.nwalk * (2 * p.d + 5) * 8 + (size_t)p.nwalk * 4 * 4 + 64;
+  const size_t small = (size_t)p.nwalk * (3 * p.d + 6) * 8 + (size_t)p.nwalk * 4 * 4 + 64;
   const size_t xs_bytes = (size_t)(p.d + 1) * p.Npad * 8;
   int xs_in_smem = (small + xs_bytes <= 200 * 1024) ? 1 : 0;
   const size_t smem = small + (xs_in_smem ? xs_bytes : 0);
