@@ -30,9 +30,21 @@ def _next_pow_two(n):
 
 
 def _acf_1d_batch(x):
-    """Normalised autocorrelation of every column of x[n_t, n_w] via FFT."""
+    """Normalised autocorrelation of every column of x[n_t, n_w] via FFT.  Large chains (the device
+    sampler produces tens of thousands of walkers) are transformed with torch.fft on the GPU."""
     n_t = x.shape[0]
     n = _next_pow_two(n_t)
+    if x.size >= (1 << 22):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+                t = t - t.mean(dim=0, keepdim=True)
+                f = torch.fft.rfft(t, n=2 * n, dim=0)
+                acf = torch.fft.irfft(f * f.conj(), n=2 * n, dim=0)[:n_t]
+                return (acf / acf[0]).cpu().numpy()
+        except Exception:
+            pass
     f = np.fft.fft(x - np.mean(x, axis=0), n=2 * n, axis=0)
     acf = np.fft.ifft(f * np.conjugate(f), axis=0)[:n_t].real
     return acf / acf[0]
