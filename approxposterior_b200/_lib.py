@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libapgp.so")
 
-APGP_OK, APGP_NOT_POSDEF, APGP_NOT_COMPUTED = 0, 1, 2
+APGP_OK, APGP_NOT_POSDEF, APGP_NOT_COMPUTED, APGP_NEEDS_REFACTOR = 0, 1, 2, 3
 MAX_DIM = 32
 UTIL_KINDS = {None: 0, "none": 0, "agp": 1, "bape": 2, "jones": 3}
 
@@ -43,6 +43,7 @@ _SIGNATURES = {
     "apgp_set_training": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "apgp_set_hyper": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double]),
     "apgp_factorize": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "apgp_append_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "apgp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.POINTER(PredictOpts), C.c_int]),
     "apgp_grad_log_likelihood": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

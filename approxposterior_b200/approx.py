@@ -260,6 +260,13 @@ class ApproxPosterior(object):
                     self.gpPar.append(currentHype)
                 if hasattr(self.gp, "rebuild"):          # foreign george-like GP (tests inject the CPU oracle)
                     self.gp = self.gp.rebuild(currentHype, self.theta, self.y)
+                elif isinstance(self.gp, GP):
+                    # the reference builds a fresh george.GP around the same kernel (approx.py:712-717);
+                    # re-computing in place is equivalent and keeps the device handle and its buffers
+                    # ... and, with unchanged hyper-parameters, a bordered O(N^2) update replaces the refactor
+                    # (append_point falls back to a full compute when it cannot take the fast path)
+                    self.gp.set_parameter_vector(currentHype)
+                    self.gp.append_point(thetaT, yT)
                 else:
                     self.gp = GP(kernel=self.gp.kernel, fit_mean=True, mean=self.gp.mean,
                                  white_noise=self.gp.white_noise, fit_white_noise=False)

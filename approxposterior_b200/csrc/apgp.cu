@@ -23,6 +23,17 @@ static const double TINY2 = 1.25e-12 * 1.25e-12;   // george's default yerr^2, a
 
 struct DevBuf {
   void* p = nullptr; size_t cap = 0;
+  int reserve_keep(size_t bytes, size_t keep, cudaStream_t st) {     // grow, preserving the first `keep` bytes
+    if (bytes <= cap) return 0;
+    void* q = nullptr;
+    size_t want = bytes + bytes / 2;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) return (int)e;
+    if (p && keep) { e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return (int)e; cudaStreamSynchronize(st); }
+    if (p) cudaFree(p);
+    p = q; cap = want;
+    return 0;
+  }
   int reserve(size_t bytes) {
     if (bytes <= cap) return 0;
     if (p) cudaFree(p);
@@ -48,6 +59,7 @@ struct apgp_handle {
   long long launches = 0;
   DevBuf X, y, K, Dinv, r, Linv, work, scal, info, hyper, Xs, alphaA, alpha, LinvF, scratch, qscale;
   DevBuf stage_in, stage_out;          // device staging for on_host calls
+  DevBuf ap_k, ap_l, ap_u, ap_x;       // bordered-append work vectors
   DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
 };
@@ -102,7 +114,7 @@ int apgp_destroy(apgp_handle* h) {
   Guard g(h->device);
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
-                    &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->bK,
+                    &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->ap_k, &h->ap_l, &h->ap_u, &h->ap_x, &h->bK,
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
                     &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl};
   for (DevBuf* b : bufs) b->release();
@@ -163,6 +175,19 @@ int apgp_set_hyper(apgp_handle* h, double mean, double amp, const double* log_me
   return APGP_OK;
 }
 
+static int pack_predict_operands(apgp_handle* h, int* nl) {
+  const int N = h->N, d = h->d, Np = h->Np;
+  const int BN = predict_variant_bn(h->variant_eff);
+  scale_pad_kernel<<<(h->Npad + 255) / 256, 256, 0, h->stream>>>(h->alpha.as<double>(), N, h->Npad, h->amp,
+                                                                 h->alphaA.as<double>()); ++*nl;
+  double qs[APGP_MAX_DIM];
+  for (int i = 0; i < d; ++i) qs[i] = sqrt(0.5 * exp(-h->log_metric[i]));
+  CU(cudaMemcpyAsync(h->qscale.p, qs, d * 8, cudaMemcpyHostToDevice, h->stream));
+  CUI(launch_pack_xs(h->X.as<double>(), N, d, h->Npad, h->qscale.as<double>(), h->Xs.as<double>(), h->stream)); ++*nl;
+  CUI(launch_pack_linv(h->Linv.as<double>(), Np, N, h->Npad, BN, h->amp, h->LinvF.as<double>(), h->stream)); ++*nl;
+  return APGP_OK;
+}
+
 int apgp_factorize(apgp_handle* h, double* logdet, double* loglik, int* info) {
   if (!h) return fail(APGP_ERR_ARG, "null handle");
   if (!h->has_training || !h->has_hyper) return fail(APGP_ERR_ARG, "apgp_factorize: training set and hyper-parameters required");
@@ -220,16 +245,46 @@ int apgp_factorize(apgp_handle* h, double* logdet, double* loglik, int* info) {
   CUI(launch_tri_inverse(h->K.as<double>(), h->Dinv.as<double>(), Np, h->Linv.as<double>(), h->work.as<double>(),
                          h->stream, &nl));
   CUI(launch_linvT_matvec(h->Linv.as<double>(), Np, h->r.as<double>(), h->alpha.as<double>(), h->stream)); ++nl;
-  scale_pad_kernel<<<(h->Npad + 255) / 256, 256, 0, h->stream>>>(h->alpha.as<double>(), N, h->Npad, h->amp,
-                                                                 h->alphaA.as<double>()); ++nl;
-  double qs[APGP_MAX_DIM];
-  for (int i = 0; i < d; ++i) qs[i] = sqrt(0.5 * exp(-h->log_metric[i]));
-  CU(cudaMemcpyAsync(h->qscale.p, qs, d * 8, cudaMemcpyHostToDevice, h->stream));
-  CUI(launch_pack_xs(h->X.as<double>(), N, d, h->Npad, h->qscale.as<double>(), h->Xs.as<double>(), h->stream)); ++nl;
-  CUI(launch_pack_linv(h->Linv.as<double>(), Np, N, h->Npad, BN, h->amp, h->LinvF.as<double>(), h->stream)); ++nl;
+  { int st_ = pack_predict_operands(h, &nl); if (st_ != APGP_OK) return st_; }
   CU(cudaStreamSynchronize(h->stream));
   h->launches += nl;
   h->factored = true;
+  return APGP_OK;
+}
+
+int apgp_append_point(apgp_handle* h, const double* x_new, double y_new, double* logdet, double* loglik) {
+  if (!h || !x_new) return fail(APGP_ERR_ARG, "apgp_append_point: null argument");
+  if (!h->factored) return fail(APGP_NOT_COMPUTED, "apgp_append_point: GP not computed");
+  const int N = h->N, d = h->d, Np = h->Np;
+  const int BN = predict_variant_bn(h->variant_eff);
+  if (N + 1 > Np || (N + BN) / BN * BN != h->Npad) return APGP_NEEDS_REFACTOR;   // padded buffers are full
+  Guard g(h->device);
+  CUI(h->X.reserve_keep((size_t)(N + 1) * d * 8, (size_t)N * d * 8, h->stream));
+  CUI(h->y.reserve_keep((size_t)(N + 1) * 8, (size_t)N * 8, h->stream));
+  CUI(h->ap_k.reserve((size_t)Np * 8)); CUI(h->ap_l.reserve((size_t)Np * 8)); CUI(h->ap_u.reserve((size_t)Np * 8));
+  CUI(h->ap_x.reserve(APGP_MAX_DIM * 8));
+  CU(cudaMemcpyAsync(h->ap_x.p, x_new, d * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->X.as<double>() + (size_t)N * d, x_new, d * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->y.as<double>() + N, &y_new, 8, cudaMemcpyHostToDevice, h->stream));
+  const double kappa = h->amp + exp(h->white_noise) + TINY2;
+  int nl = 0;
+  CUI(launch_append_point(h->X.as<double>(), N, d, Np, h->ap_x.as<double>(), h->hyper.as<double>(), kappa,
+                          y_new - h->mean, h->K.as<double>(), h->Linv.as<double>(), h->r.as<double>(),
+                          h->alpha.as<double>(), h->ap_k.as<double>(), h->ap_l.as<double>(), h->ap_u.as<double>(),
+                          h->scal.as<double>(), h->info.as<int>(), h->stream, &nl));
+  double sc[2]; int status = 0;
+  CU(cudaMemcpyAsync(sc, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&status, h->info.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->launches += nl; nl = 0;
+  if (status != 0) return APGP_NOT_POSDEF;      // nothing was written: the N-point factorisation is still valid
+  h->N = N + 1;
+  h->logdet = sc[0]; h->loglik = sc[1];
+  if (logdet) *logdet = sc[0];
+  if (loglik) *loglik = sc[1];
+  { int st_ = pack_predict_operands(h, &nl); if (st_ != APGP_OK) return st_; }
+  CU(cudaStreamSynchronize(h->stream));
+  h->launches += nl;
   return APGP_OK;
 }
 

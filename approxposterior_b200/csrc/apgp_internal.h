@@ -59,6 +59,10 @@ int launch_tri_inverse(const double* L, const double* Dinv, int Np, double* Linv
 // alpha = L^{-T} z  using the explicit inverse
 int launch_linvT_matvec(const double* Linv, int Np, const double* z, double* alpha, cudaStream_t st);
 int launch_loglik_finish(const FactorBatch& fb, double* ll, cudaStream_t st);
+// bordered append of one training point to an existing factorisation (needs N + 1 <= Np)
+int launch_append_point(const double* X, int N, int d, int Np, const double* xnew_dev, const double* hyper_dev, double kappa,
+                        double rnew, double* L, double* Linv, double* z, double* alpha, double* kvec, double* lvec,
+                        double* uvec, double* scal, int* status, cudaStream_t st, int* launches);
 // fused one-restart-per-CTA path (everything in shared memory); usable when loglik_small_smem(N,d) <= 220 KB
 size_t loglik_small_smem(int N, int d);
 int launch_loglik_small(const double* X, const double* y, int N, int d, const double* hyper, int R, double* ll,

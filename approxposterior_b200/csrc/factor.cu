@@ -509,6 +509,72 @@ __global__ void __launch_bounds__(256) loglik_small_kernel(const double* __restr
   if (tid == 0) g_out[0] = red[0];
 }
 
+
+// ---- bordered (rank-1) append of one design point: O(N^2) instead of the O(N^3) refactor the reference
+//      performs for every new point (approx.py:693-717).  With l = L^{-1} k(X, x_new):
+//        L'    = [L 0; l^T lam]            lam^2 = kappa - l^T l
+//        L'^-1 = [L^-1 0; -(l^T L^-1)/lam  1/lam]
+//        z'    = [z; (r_new - l^T z)/lam]  alpha' = [alpha + w z_N; z_N/lam],  w = -(l^T L^-1)/lam
+__global__ void append_kvec_kernel(const double* __restrict__ X, int N, int d, const double* __restrict__ xnew,
+                                   const double* __restrict__ hyper, double* __restrict__ kvec) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  double s = 0.0;
+  for (int c = 0; c < d; ++c) { const double df = X[(size_t)j * d + c] - xnew[c]; s += df * df * hyper[3 + c]; }
+  kvec[j] = hyper[1] * exp(-0.5 * s);
+}
+// l_i = sum_{j<=i} Linv[i][j] k_j : one warp per row
+__global__ void __launch_bounds__(256) append_linv_rows_kernel(const double* __restrict__ Linv, int Np, int N,
+                                                               const double* __restrict__ kvec, double* __restrict__ l) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= N) return;
+  double s = 0.0;
+  for (int j = lane; j <= i; j += 32) s += Linv[(size_t)i * Np + j] * kvec[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) l[i] = s;
+}
+// single CTA: everything that is O(N).  u = l^T L^-1 (computed by linvT_matvec into `u`).
+// scal: [0] logdet, [1] loglik (in/out).  status: 0 ok, 1 not positive definite.
+__global__ void __launch_bounds__(256) append_finish_kernel(double* __restrict__ L, double* __restrict__ Linv, int Np, int N,
+                                                            const double* __restrict__ l, const double* __restrict__ u,
+                                                            double* __restrict__ z, double* __restrict__ alpha,
+                                                            double kappa, double rnew, double* __restrict__ scal,
+                                                            int* __restrict__ status) {
+  __shared__ double red[256];
+  __shared__ double sh[3];
+  const int tid = threadIdx.x;
+  double a = 0.0, b = 0.0, zz = 0.0;
+  for (int i = tid; i < N; i += 256) { a += l[i] * l[i]; b += l[i] * z[i]; zz += z[i] * z[i]; }
+  for (int k = 0; k < 3; ++k) {
+    red[tid] = (k == 0) ? a : (k == 1 ? b : zz);
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    if (tid == 0) sh[k] = red[0];
+    __syncthreads();
+  }
+  const double lam2 = kappa - sh[0];
+  if (!(lam2 > 0.0) || !(lam2 < INFINITY)) { if (tid == 0) *status = 1; return; }
+  const double lam = sqrt(lam2), ilam = 1.0 / lam;
+  const double zN = (rnew - sh[1]) * ilam;
+  for (int j = tid; j < N; j += 256) {
+    const double w = -u[j] * ilam;
+    L[(size_t)N * Np + j] = l[j];
+    Linv[(size_t)N * Np + j] = w;
+    alpha[j] += w * zN;
+  }
+  if (tid == 0) {
+    L[(size_t)N * Np + N] = lam;
+    Linv[(size_t)N * Np + N] = ilam;
+    z[N] = zN;
+    alpha[N] = zN * ilam;
+    const double logdet = scal[0] + 2.0 * log(lam);
+    scal[0] = logdet;
+    scal[1] = -0.5 * (sh[2] + zN * zN) - 0.5 * logdet - 0.5 * (N + 1) * 1.8378770664093454836;
+    *status = 0;
+  }
+}
+
 bool g_attr_done = false;
 int ensure_attrs() {
   if (g_attr_done) return 0;
@@ -582,6 +648,18 @@ int launch_loglik_small(const double* X, const double* y, int N, int d, const do
                         double* grad, cudaStream_t st) {
   int e = ensure_attrs(); if (e) return e;
   loglik_small_kernel<<<R, 256, loglik_small_smem(N, d), st>>>(X, y, N, d, hyper, ll, grad);
+  return (int)cudaGetLastError();
+}
+
+int launch_append_point(const double* X, int N, int d, int Np, const double* xnew_dev, const double* hyper_dev, double kappa,
+                        double rnew, double* L, double* Linv, double* z, double* alpha, double* kvec, double* lvec,
+                        double* uvec, double* scal, int* status, cudaStream_t st, int* launches) {
+  append_kvec_kernel<<<(N + 255) / 256, 256, 0, st>>>(X, N, d, xnew_dev, hyper_dev, kvec);
+  cudaMemsetAsync(lvec, 0, sizeof(double) * Np, st);
+  append_linv_rows_kernel<<<(N + 7) / 8, 256, 0, st>>>(Linv, Np, N, kvec, lvec);
+  linvT_matvec_kernel<<<Np / T, 256, 0, st>>>(Linv, Np, lvec, uvec);      // u_j = sum_{i>=j} Linv[i][j] l_i
+  append_finish_kernel<<<1, 256, 0, st>>>(L, Linv, Np, N, lvec, uvec, z, alpha, kappa, rnew, scal, status);
+  if (launches) *launches += 4;
   return (int)cudaGetLastError();
 }
 

@@ -91,6 +91,8 @@ class GP(object):
         p = np.asarray(p, dtype=np.float64).ravel()
         if p.size != len(self):
             raise ValueError("dimension mismatch: expected %d parameters, got %d" % (len(self), p.size))
+        if np.array_equal(p, self.get_parameter_vector()):
+            return                                  # unchanged: keep the factorisation
         k = 0
         if self.fit_mean:
             self.mean = float(p[0])
@@ -162,6 +164,29 @@ class GP(object):
         self.computed = True
         self._dirty = False
         return True
+
+    def append_point(self, x_new, y_new):
+        """Grow the training set by one point with a bordered O(N^2) update of the factorisation (L, L^-1,
+        alpha, log-determinant, log-likelihood) -- what the reference obtains by rebuilding and re-computing
+        the GP from scratch for every new design point (approx.py:693-717).  Hyper-parameters are unchanged.
+        Falls back to a full ``compute`` when the padded device buffers are full or the update is not
+        positive definite.  Returns True if the fast path was taken."""
+        x_new = np.ascontiguousarray(np.asarray(x_new, dtype=np.float64).ravel())
+        y_new = float(np.asarray(y_new, dtype=np.float64).ravel()[0])
+        if x_new.size != self.ndim:
+            raise ValueError("dimension mismatch")
+        X = np.vstack([self._x, x_new[None, :]])
+        Y = np.concatenate([self._y if self._y is not None else np.zeros(self._x.shape[0]), [y_new]])
+        if self.computed and not self._dirty and self._y is not None and self._training_uploaded:
+            logdet, ll = C.c_double(), C.c_double()
+            st = _lib.check(self._lib.apgp_append_point(self._h, _lib.ptr(x_new), y_new, C.byref(logdet), C.byref(ll)),
+                            "apgp_append_point")
+            if st == _lib.APGP_OK:
+                self._x, self._y = np.ascontiguousarray(X), Y
+                self._logdet, self._loglik = logdet.value, ll.value
+                return True
+        self.compute(X, y=Y)
+        return False
 
     def _sync_y(self, y):
         """Make the device-side y (hence alpha and the stored log-likelihood) match ``y``."""

@@ -27,6 +27,7 @@ extern "C" {
 #define APGP_OK 0
 #define APGP_NOT_POSDEF 1        /* covariance not positive definite (george: LinAlgError) */
 #define APGP_NOT_COMPUTED 2      /* predict/log-likelihood before a successful factorisation */
+#define APGP_NEEDS_REFACTOR 3    /* apgp_append_point: padded buffers are full, call set_training + factorize */
 #define APGP_ERR_ARG (-1)
 #define APGP_ERR_CUDA (-2)
 #define APGP_ERR_NOMEM (-3)
@@ -67,6 +68,13 @@ int apgp_set_hyper(apgp_handle* h, double mean, double amp, const double* log_me
  * *logdet = log|K|, *loglik = log-likelihood of the stored y (george.GP.log_likelihood,
  * gpUtils.py:78,247); either may be NULL. */
 int apgp_factorize(apgp_handle* h, double* logdet, double* loglik, int* info);
+
+/* Append ONE training point (x_new [d], y_new; host) to the current factorisation with a bordered O(N^2)
+ * update of L, L^-1, alpha, log|K| and the log-likelihood -- instead of the from-scratch refactorisation the
+ * reference performs for every new design point (approx.py:693-717).  Hyper-parameters are unchanged.
+ * Returns APGP_NEEDS_REFACTOR when the 64-padded buffers are full (caller re-uploads and factorises),
+ * APGP_NOT_POSDEF when the bordered pivot is not positive. */
+int apgp_append_point(apgp_handle* h, const double* x_new, double y_new, double* logdet, double* loglik);
 
 typedef struct apgp_predict_opts {
   int want_var;                  /* 0: mean only (approx.py:178-180); 1: mean+variance (utility.py:131,178,224) */

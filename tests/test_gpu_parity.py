@@ -293,3 +293,29 @@ def test_sampler_replay_large_training_set_global_path():
     np.testing.assert_allclose(out["chain"], ref["chain"], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(out["log_prob"], ref["log_prob"], rtol=1e-9, atol=1e-9)
     assert np.array_equal(out["naccepted"], ref["naccepted"])
+
+
+@pytest.mark.parametrize("N0,nadd", [(50, 30), (120, 10), (255, 3)])
+def test_append_point_matches_full_compute(N0, nadd):
+    """Bordered O(N^2) append (reference approx.py:693-717 refactors from scratch) vs a fresh factorisation:
+    alpha, L^-1, log-likelihood and predictions must agree; crossing a 64-row padding boundary falls back."""
+    rng = np.random.default_rng(N0)
+    d = 3
+    X = rng.uniform(-5, 5, size=(N0 + nadd, d))
+    y = np.sin(X).sum(axis=1)
+    logM = np.log(np.full(d, 3.0))
+    gp, _ = make_pair(X[:N0], y[:N0], logM, amp=2.0, mean=0.1)
+    fast = 0
+    for k in range(N0, N0 + nadd):
+        fast += bool(gp.append_point(X[k], y[k]))
+    ref, orc = make_pair(X, y, logM, amp=2.0, mean=0.1)
+    assert fast >= nadd - 1 - nadd // 64        # only padding-boundary crossings refactor
+    assert gp._x.shape == (N0 + nadd, d) and np.array_equal(gp._y, y)
+    np.testing.assert_allclose(gp._alpha(), ref._alpha(), rtol=1e-8, atol=1e-10 * np.max(np.abs(ref._alpha())))
+    assert np.max(np.abs(gp._linv() @ orc._L - np.eye(N0 + nadd))) < 1e-9
+    assert abs(gp.log_likelihood(y) - orc.log_likelihood(y)) <= 1e-9 * abs(orc.log_likelihood(y))
+    assert abs(gp.log_determinant - orc.log_determinant) <= 1e-9 * max(1.0, abs(orc.log_determinant))
+    Xq = rng.uniform(-5, 5, size=(400, d))
+    check_predict(gp, orc, y, Xq, 2.0)
+    # a duplicated point makes the bordered pivot vanish only up to the white noise: still positive definite
+    assert gp.append_point(X[0], y[0]) in (True, False) and gp.computed
