@@ -45,7 +45,7 @@ struct VarCfg {
   static constexpr int RING = NSTAGE * STAGE;            // doubles, reused as the phase-1 staging area
   static size_t smem_bytes(int d) {
     return (size_t)RING * 8 + (size_t)d * BM * 8 /*qs*/ + (size_t)BM * 8 /*mu_s*/ +
-           (size_t)WARPS_N * BM * 8 /*ss_s*/ + 64 * 8 /*exp table*/ + 2 * NSTAGE * 8 /*barriers*/ + 128;
+           (size_t)WARPS_N * BM * 8 /*ss_s*/ + 64 * 8 /*exp table*/ + (2 * NSTAGE + 1) * 8 /*barriers*/ + 128;
   }
 };
 
@@ -61,6 +61,7 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
   double* etab = ss_s + C::WARPS_N * BM;                // [64] 2^(j/64) for exp_neg
   uint64_t* full = reinterpret_cast<uint64_t*>(etab + 64);
   uint64_t* empty = full + NSTAGE;
+  uint64_t* stagebar = empty + NSTAGE;                  // training-set staging (phase 1) completion
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -72,11 +73,13 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS_WARPS); }
+    mbar_init(stagebar, 1);
     mbar_fence_init();
   }
   __syncthreads();
 
   uint32_t it = 0;   // ring position, identical sequence in producer and consumers
+  uint32_t nstaged = 0;   // completed training-set staging copies (parity of stagebar)
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long q0 = tile * BM;
@@ -96,11 +99,14 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
       for (int j0 = 0; j0 < Npad; j0 += JCH) {
         const int jn = min(JCH, Npad - j0);
         named_bar_sync(1, NCONS);                      // previous chunk fully consumed / qs visible
-        for (int e = tid; e < (d + 1) * jn; e += NCONS) {
-          int i = e / jn, j = e - i * jn;
-          ring[i * JCH + j] = (i < d) ? p.Xs[(size_t)i * Npad + j0 + j] : p.alphaA[j0 + j];
+        // TMA-staged training set: d rows of the scaled SoA inputs + the alpha row, one bulk copy each
+        if (tid == 0) {
+          mbar_arrive_expect_tx(stagebar, (uint32_t)((d + 1) * jn * 8));
+          for (int i = 0; i < d; ++i) bulk_g2s(ring + i * JCH, p.Xs + (size_t)i * Npad + j0, jn * 8, stagebar);
+          bulk_g2s(ring + d * JCH, p.alphaA + j0, jn * 8, stagebar);
         }
-        named_bar_sync(1, NCONS);
+        mbar_wait(stagebar, nstaged & 1u);
+        ++nstaged;
         const double* al = ring + d * JCH;
         double macc[R] = {};
         for (int jb = 0; jb < jn; jb += 16) {           // 4 k4-blocks per trip

@@ -41,7 +41,7 @@ def check_predict(gp, orc, y, Xq, amp_scale):
     return mu, var
 
 
-@pytest.mark.parametrize("N,d", [(20, 2), (64, 1), (100, 3), (256, 2), (300, 5), (700, 5)])
+@pytest.mark.parametrize("N,d", [(20, 2), (64, 1), (100, 3), (256, 2), (300, 5), (700, 5), (2100, 20)])
 def test_factor_and_predict_vs_oracle(N, d):
     X, y, logM, _ = synthetic_gp_problem(N, d, seed=N + d)
     gp, orc = make_pair(X, y, logM)
