@@ -30,15 +30,19 @@ namespace apgp {
 namespace {
 
 constexpr int BK = 16;
-constexpr int NCONS_WARPS = 8;
-constexpr int NCONS = NCONS_WARPS * 32;
-constexpr int NTHREADS = NCONS + 32;
 
-template <int BM, int BN, int NSTAGE>
+// NCW consumer warps (warp tile 32x64) + 1 TMA producer warp.  NCW = 8: one CTA per SM (all shipped tilings).
+// NCW = 4 (two co-resident 128x64 CTAs per SM, so one CTA's panel phase overlaps the other's DMMA phase) was
+// measured: identical results, 0-2 % slower at every N (profiles/r01_schedules_tried/README.md).
+template <int BM, int BN, int NSTAGE, int NCW = 8>
 struct VarCfg {
+  static constexpr int NCONS_WARPS = NCW;
+  static constexpr int NCONS = NCW * 32;
+  static constexpr int NTHREADS = NCONS + 32;
+  static constexpr int CTAS_PER_SM = (NCW == 4) ? 2 : 1;
   static constexpr int WARPS_M = BM / 32;
   static constexpr int WARPS_N = BN / 64;
-  static_assert(WARPS_M * WARPS_N == NCONS_WARPS, "8 consumer warps, warp tile 32x64");
+  static_assert(WARPS_M * WARPS_N == NCW, "consumer warps x warp tile 32x64 must cover the CTA tile");
   static constexpr int A_TILE = BM * BK;                 // doubles
   static constexpr int B_TILE = BN * BK;
   static constexpr int STAGE = A_TILE + B_TILE;
@@ -49,10 +53,11 @@ struct VarCfg {
   }
 };
 
-template <int BM, int BN, int NSTAGE>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int BM, int BN, int NSTAGE, int NCW>
+__global__ void __launch_bounds__(NCW * 32 + 32, (NCW == 4) ? 2 : 1)
 predict_var_kernel(const __grid_constant__ PredictParams p) {
-  using C = VarCfg<BM, BN, NSTAGE>;
+  using C = VarCfg<BM, BN, NSTAGE, NCW>;
+  constexpr int NCONS_WARPS = C::NCONS_WARPS, NCONS = C::NCONS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
   double* qs = ring + C::RING;                          // [d][BM] scaled queries
@@ -94,7 +99,7 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
       // chunk of training columns staged in the (idle) ring: xs[d][JCH] + alpha[JCH]
       int JCH = (C::RING / (d + 1)) & ~15;
       if (JCH > Npad) JCH = Npad;
-      constexpr int R = BM / 64;                       // m8 blocks per warp: their exp chains interleave (4R-way ILP)
+      constexpr int R = BM / (8 * NCW);                // m8 blocks per warp: their exp chains interleave (4R-way ILP)
       double mu_part[R] = {};
       for (int j0 = 0; j0 < Npad; j0 += JCH) {
         const int jn = min(JCH, Npad - j0);
@@ -371,21 +376,22 @@ __global__ void exp_neg_test_kernel(const double* __restrict__ s, int n, double*
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = exp_neg(s[i], tab);
 }
 
-template <int BM, int BN, int NSTAGE>
+template <int BM, int BN, int NSTAGE, int NCW = 8>
 int launch_var_t(const PredictParams& p, int num_sms, cudaStream_t st) {
-  using C = VarCfg<BM, BN, NSTAGE>;
+  using C = VarCfg<BM, BN, NSTAGE, NCW>;
   const size_t smem = C::smem_bytes(p.d);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(predict_var_kernel<BM, BN, NSTAGE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(predict_var_kernel<BM, BN, NSTAGE, NCW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / C::CTAS_PER_SM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   long long ntiles = (p.Q + BM - 1) / BM;
-  int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  const long long cap = (long long)num_sms * C::CTAS_PER_SM;
+  int grid = (int)(ntiles < cap ? ntiles : cap);
   if (grid < 1) return 0;
-  predict_var_kernel<BM, BN, NSTAGE><<<grid, NTHREADS, smem, st>>>(p);
+  predict_var_kernel<BM, BN, NSTAGE, NCW><<<grid, C::NTHREADS, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -399,7 +405,7 @@ static inline int variant_bn(int v) { return v == 0 ? 256 : (v == 2 ? 64 : 128);
 int predict_variant_bn(int variant) { return variant_bn(variant); }
 
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant) {
-  return (size_t)num_sms * variant_bm(variant) * Npad * 8 ;
+  return (size_t)num_sms * variant_bm(variant) * Npad * 8;
 }
 
 int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches) {
