@@ -319,3 +319,42 @@ def test_append_point_matches_full_compute(N0, nadd):
     check_predict(gp, orc, y, Xq, 2.0)
     # a duplicated point makes the bordered pivot vanish only up to the white noise: still positive definite
     assert gp.append_point(X[0], y[0]) in (True, False) and gp.computed
+
+
+def test_ill_conditioned_against_multiprecision_truth():
+    """cond(K) ~ 1e10 (huge amplitude, very long length scale -- the regime optimizeGP's amplitude fits end in,
+    reference tests/test_OptimizeGP.py:50).  Neither fp64 implementation can agree with the other to 1e-9
+    there; what must hold is that the CUDA path is as close to the 60-digit truth as the oracle is."""
+    import mpmath as mp
+    mp.mp.dps = 60
+    N, amp, logM, wn = 40, 5.7e4, np.array([4.2, 10.8]), -12.0
+    theta, y = rosenbrock_training(N)
+    mean = float(np.median(y))
+    gp, orc = make_pair(theta, y, logM, amp=amp, mean=mean, wn=wn)
+    Xq = np.random.default_rng(2).uniform(-5, 5, size=(12, 2))
+    mu_g, var_g = gp.predict(y, Xq, return_cov=False, return_var=True)
+    mu_o, var_o = orc.predict(y, Xq, return_var=True)
+    # multiprecision reference
+    w = [mp.e ** (-mp.mpf(float(v))) for v in logM]
+    A = mp.mpf(orc.amplitude)
+    def k(a, b):
+        return A * mp.e ** (-mp.mpf("0.5") * sum(w[i] * (mp.mpf(float(a[i])) - mp.mpf(float(b[i]))) ** 2 for i in range(2)))
+    K = mp.matrix(N, N)
+    for i in range(N):
+        for j in range(N):
+            K[i, j] = k(theta[i], theta[j])
+        K[i, i] += mp.e ** mp.mpf(wn) + mp.mpf("1.25e-12") ** 2
+    r = mp.matrix([mp.mpf(float(v)) - mp.mpf(mean) for v in y])
+    alpha = mp.lu_solve(K, r)
+    err_g = err_o = verr_g = verr_o = 0.0
+    for qi, q in enumerate(Xq):
+        ks = mp.matrix([k(q, theta[j]) for j in range(N)])
+        mu_t = mp.mpf(mean) + sum(ks[j] * alpha[j] for j in range(N))
+        v_t = A - sum(ks[j] * s for j, s in enumerate(mp.lu_solve(K, ks)))
+        err_g = max(err_g, abs(float(mp.mpf(float(mu_g[qi])) - mu_t)))
+        err_o = max(err_o, abs(float(mp.mpf(float(mu_o[qi])) - mu_t)))
+        verr_g = max(verr_g, abs(float(mp.mpf(float(var_g[qi])) - v_t)))
+        verr_o = max(verr_o, abs(float(mp.mpf(float(var_o[qi])) - v_t)))
+    scale = float(np.max(np.abs(y)))
+    assert err_g <= 20 * max(err_o, 1e-12 * scale), (err_g, err_o)
+    assert verr_g <= 20 * max(verr_o, 1e-12 * amp), (verr_g, verr_o)
