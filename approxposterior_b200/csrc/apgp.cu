@@ -60,6 +60,8 @@ struct apgp_handle {
   DevBuf X, y, K, Dinv, r, Linv, work, scal, info, hyper, Xs, alphaA, alpha, LinvF, scratch, qscale;
   DevBuf stage_in, stage_out;          // device staging for on_host calls
   DevBuf ap_k, ap_l, ap_u, ap_x;       // bordered-append work vectors
+  double* pin = nullptr;               // pinned host staging for small calls (latency path)
+  static constexpr size_t PIN_DOUBLES = 32768;   // 256 KB: [0, PIN/2) inputs, [PIN/2, PIN) outputs
   DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
 };
@@ -103,6 +105,7 @@ int apgp_create(apgp_handle** out, int device) {
   h->num_sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  CU(cudaHostAlloc((void**)&h->pin, apgp_handle::PIN_DOUBLES * 8, cudaHostAllocDefault));
   const char* v = getenv("APGP_PREDICT_VARIANT");
   if (v) { int vv = atoi(v); h->variant = (vv >= 0 && vv <= 2) ? vv : 2; }
   *out = h;
@@ -118,6 +121,7 @@ int apgp_destroy(apgp_handle* h) {
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
                     &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl};
   for (DevBuf* b : bufs) b->release();
+  if (h->pin) cudaFreeHost(h->pin);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return APGP_OK;
@@ -313,10 +317,16 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
   p.has_box = o->has_box; p.utility_kind = o->utility; p.ybest = o->ybest; p.zeta = o->zeta;
   for (int i = 0; i < d; ++i) { p.lo[i] = o->lo[i]; p.hi[i] = o->hi[i]; }
   const int nout = (mu ? 1 : 0) + (var ? 1 : 0) + (util ? 1 : 0);
+  // small host calls (optimiser rounds: a handful of queries) go through pinned staging: one async H2D,
+  // one async D2H, no pageable-memory bounce -- this path is pure latency
+  const size_t half = apgp_handle::PIN_DOUBLES / 2;
+  const bool small_call = on_host && (size_t)Q * d <= half && (size_t)Q * (nout ? nout : 1) <= half;
   if (on_host) {
     CUI(h->stage_in.reserve((size_t)Q * d * 8));
     CUI(h->stage_out.reserve((size_t)Q * 8 * (nout ? nout : 1)));
-    CU(cudaMemcpyAsync(h->stage_in.p, Xq, (size_t)Q * d * 8, cudaMemcpyHostToDevice, h->stream));
+    const double* src = Xq;
+    if (small_call) { memcpy(h->pin, Xq, (size_t)Q * d * 8); src = h->pin; }
+    CU(cudaMemcpyAsync(h->stage_in.p, src, (size_t)Q * d * 8, cudaMemcpyHostToDevice, h->stream));
     p.Xq = h->stage_in.as<double>();
     double* o0 = h->stage_out.as<double>();
     if (mu) { p.mu = o0; o0 += Q; }
@@ -335,7 +345,14 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
     CUI(launch_predict_mean(p, h->num_sms, h->stream, &nl));
   }
   h->launches += nl;
-  if (on_host) {
+  if (on_host && small_call) {
+    double* hp = h->pin + half;
+    CU(cudaMemcpyAsync(hp, h->stage_out.p, (size_t)Q * 8 * nout, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (mu) { memcpy(mu, hp, (size_t)Q * 8); hp += Q; }
+    if (var) { memcpy(var, hp, (size_t)Q * 8); hp += Q; }
+    if (util) { memcpy(util, hp, (size_t)Q * 8); hp += Q; }
+  } else if (on_host) {
     if (mu) CU(cudaMemcpyAsync(mu, p.mu, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
     if (var) CU(cudaMemcpyAsync(var, p.var, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
     if (util) CU(cudaMemcpyAsync(util, p.util, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -407,7 +424,10 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
       if (fin) fill_hyper_row(row, p[0], amp, white_noise, lm, d);
       else { row[0] = 0; row[1] = 1; row[2] = 1; for (int i = 0; i < d; ++i) row[3 + i] = 1; }
     }
-    CU(cudaMemcpyAsync(h->bhyper.p, rows.data(), (size_t)rc * (3 + d) * 8, cudaMemcpyHostToDevice, h->stream));
+    const bool pin_ok = (size_t)rc * (3 + d) <= apgp_handle::PIN_DOUBLES / 2 && (size_t)rc <= apgp_handle::PIN_DOUBLES / 2;
+    const double* rsrc = rows.data();
+    if (pin_ok) { memcpy(h->pin, rows.data(), (size_t)rc * (3 + d) * 8); rsrc = h->pin; }
+    CU(cudaMemcpyAsync(h->bhyper.p, rsrc, (size_t)rc * (3 + d) * 8, cudaMemcpyHostToDevice, h->stream));
     int nl = 0;
     if (small) {
       // one restart per CTA, everything in shared memory: a single launch per optimiser round
@@ -422,8 +442,10 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
       CUI(launch_cholesky(fb, h->num_sms, h->stream, &nl));
       CUI(launch_loglik_finish(fb, h->bll.as<double>(), h->stream)); ++nl;
     }
-    CU(cudaMemcpyAsync(ll_host + r0, h->bll.p, (size_t)rc * 8, cudaMemcpyDeviceToHost, h->stream));
+    double* lldst = pin_ok ? h->pin + apgp_handle::PIN_DOUBLES / 2 : ll_host + r0;
+    CU(cudaMemcpyAsync(lldst, h->bll.p, (size_t)rc * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (pin_ok) memcpy(ll_host + r0, lldst, (size_t)rc * 8);
     h->launches += nl;
     if (grad_host) {                         // [sum alpha, d/dlog_c, d/dlogM..] -> george order, amplitude slot optional
       for (int r = 0; r < rc; ++r) {
