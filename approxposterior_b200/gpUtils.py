@@ -8,6 +8,7 @@ import numpy as np
 from scipy.optimize import minimize
 
 from . import kernels
+from . import _optimizers as _opt
 from ._lockstep import run_lockstep
 from .gp import GP
 
@@ -110,7 +111,15 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
     derivative_free = method in ["nelder-mead", "powell", "cg"]
     use_batch = batched and hasattr(gp, "log_likelihood_batch")
 
-    if use_batch:
+    if use_batch and _opt.supported(method, options):
+        # thread-free lock step: SciPy's Powell / Nelder-Mead restated as coroutines (same iterates)
+        make = _opt.powell_gen if str(method).lower() == "powell" else _opt.nelder_mead_gen
+        out, rounds, evals = _opt.run_generators([make(x0, **(options or {})) for x0 in x0s],
+                                                 lambda P: _nll_batch(P, gp, y, gpHyperPrior))
+        res = [o[0] for o in out]
+        optimizeGP.last_stats = dict(batches=rounds, evals=evals, scheduler="generators")
+        mll = list(gp.log_likelihood_batch(np.array(res), y))
+    elif use_batch:
         # derivative-free: f(x) -> nll; gradient methods: f(x) -> (nll, grad_nll) in the same batched launch
         def worker(wid, f):
             return minimize(f, x0s[wid], method=method, jac=None if derivative_free else True, bounds=None,
@@ -118,7 +127,7 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
 
         res, ev = run_lockstep(nGPRestarts,
                                lambda P: _nll_batch(P, gp, y, gpHyperPrior, with_grad=not derivative_free), worker)
-        optimizeGP.last_stats = dict(batches=ev.nbatches, evals=ev.nevals)
+        optimizeGP.last_stats = dict(batches=ev.nbatches, evals=ev.nevals, scheduler="threads")
         mll = list(gp.log_likelihood_batch(np.array(res), y))
     else:
         res, mll = [], []

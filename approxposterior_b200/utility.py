@@ -10,6 +10,7 @@ import numpy as np
 from scipy.optimize import minimize
 from scipy.special import ndtr
 
+from . import _optimizers as _opt
 from ._lockstep import run_lockstep
 
 __all__ = ["logsubexp", "AGPUtility", "BAPEUtility", "JonesUtility", "minimizeObjective", "klNumerical",
@@ -208,8 +209,6 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
             ii += 1
 
     if use_batch:
-        import threading
-        rng_lock = threading.Lock()
         zeta = 0.01
 
         def batch_fn(thetas):
@@ -217,12 +216,35 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
                 return fn_batch(np.array(thetas))
             return utilityBatch(np.array(thetas), y, gp, priorFn, kind, zeta=zeta)
 
-        def redraw():
-            with rng_lock:
-                return draw()
+        if _opt.supported(method, options, bounds):
+            # thread-free lock step: SciPy's algorithm restated as a coroutine per restart
+            make = _opt.nelder_mead_gen if str(method).lower() == "nelder-mead" else _opt.powell_gen
 
-        out, ev = run_lockstep(nRestarts, batch_fn, lambda wid, f: solve(f, starts[wid], redraw))
-        minimizeObjective.last_stats = dict(batches=ev.nbatches, evals=ev.nevals)
+            def restart(t0):
+                ii = 0
+                while True:
+                    if ii >= maxIters:
+                        raise RuntimeError("ERROR: Cannot find a valid solution. Current iterations: %d\n"
+                                           "Maximum iterations: %d\n" % (ii, maxIters))
+                    tmp, _ = yield from make(t0, **(options or {}))
+                    if np.all(np.isfinite(tmp)) and np.isfinite(priorFn(tmp)):
+                        ftmp = yield np.copy(tmp)            # the reference re-evaluates fn at the optimum
+                        return tmp, ftmp
+                    t0 = draw()
+                    ii += 1
+
+            out, rounds, evals = _opt.run_generators([restart(t0) for t0 in starts], batch_fn)
+            minimizeObjective.last_stats = dict(batches=rounds, evals=evals, scheduler="generators")
+        else:
+            import threading
+            rng_lock = threading.Lock()
+
+            def redraw():
+                with rng_lock:
+                    return draw()
+
+            out, ev = run_lockstep(nRestarts, batch_fn, lambda wid, f: solve(f, starts[wid], redraw))
+            minimizeObjective.last_stats = dict(batches=ev.nbatches, evals=ev.nevals, scheduler="threads")
     else:
         out = [solve(lambda x: fn(x, *args), t0, draw) for t0 in starts]
 

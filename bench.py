@@ -304,7 +304,8 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = gp.launch_count - l0
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kernel_each = [float(a.elapsed_time(b)) for a, b in kev]
+    kernel_ms = float(np.mean(kernel_each))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -361,7 +362,7 @@ def run_gpu(args):
                                              "algorithmic I/O is 67 MB -- the kernel is FP64-pipe bound (DMMA pipe 94% "
                                              "active), DRAM at 28% of peak",
                              "kernel": "predict_var_kernel<256,64,4> (fused K* panel + DMMA triangular GEMM + utility)",
-                             "kernel_ms": kernel_ms,
+                             "kernel_ms": kernel_ms, "kernel_ms_each": [round(v, 3) for v in kernel_each],
                              "flops_per_eval": flops_per_eval(N_TRAIN, DIM),
                              "peak_source": "cuBLAS DGEMM 8192^3 best-of-6 measured in this run "
                                             "(MEASURED_PEAKS.json carries no fp64 entry); DMMA issue peak "

@@ -296,3 +296,51 @@ def test_approx_posterior_argument_validation():
     bad = theta.copy(); bad[0, 0] = np.inf
     with pytest.raises(ValueError):
         approx.ApproxPosterior(bad, y, lh.rosenbrockLnprior, lh.rosenbrockLnlike, lh.rosenbrockSample, [(-5, 5)] * 2, gp=1)
+
+
+def test_generator_optimisers_match_scipy():
+    """The coroutine restatements of SciPy's Nelder-Mead / Powell must evaluate exactly the points SciPy
+    evaluates (same order, bit-identical) and return the same optimum -- including through inf regions."""
+    import warnings
+    from scipy.optimize import minimize, rosen
+    from approxposterior_b200._optimizers import nelder_mead_gen, powell_gen, run_generators, supported
+    funcs = {
+        "rosen3": (rosen, 3),
+        "quad+sin": (lambda x: float(np.sum((x - 1.5) ** 2) + np.sin(3 * x[0])), 2),
+        "walled": (lambda x: float(np.sum(np.abs(x)) + (np.inf if x[0] > 3 else 0)), 3),
+        "log": (lambda x: float(np.log(x[0]) + x[0] ** 2 + x[1] ** 2) if x[0] > 0 else np.inf, 2),
+        "flat": (lambda x: 1.0, 2),
+    }
+    rng = np.random.default_rng(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, (f, n) in funcs.items():
+            for trial in range(3):
+                x0 = np.abs(rng.standard_normal(n)) * 2 + 0.1
+                for method, gen, opts in (("nelder-mead", nelder_mead_gen, {"adaptive": True}),
+                                          ("nelder-mead", nelder_mead_gen, {"maxfev": 37}),
+                                          ("powell", powell_gen, {}), ("powell", powell_gen, {"maxfev": 29})):
+                    assert supported(method, opts)
+                    rec, rec2 = [], []
+                    res = minimize(lambda x: (rec.append(np.array(x, copy=True)), f(np.asarray(x)))[1], x0,
+                                   method=method, options=opts or None)
+                    (out,), rounds, evals = run_generators(
+                        [gen(x0, **opts)], lambda xs: (rec2.extend(np.array(x, copy=True) for x in xs),
+                                                       [f(x) for x in xs])[1])
+                    assert len(rec) == len(rec2) == evals, (name, method, opts, len(rec), len(rec2))
+                    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(rec, rec2)), (name, method)
+                    assert np.array_equal(res.x, out[0], equal_nan=True)
+    assert not supported("powell", {"direc": np.eye(2)}) and not supported("l-bfgs-b", None)
+    assert not supported("nelder-mead", {"adaptive": True}, bounds=[(0, 1)])
+
+
+def test_generator_lockstep_batches_restarts():
+    from approxposterior_b200._optimizers import nelder_mead_gen, run_generators
+    f = lambda x: float(np.sum((np.asarray(x) - 1.5) ** 2))
+    x0s = [np.array([0.1 * i, -0.3 * i, 0.2]) for i in range(1, 8)]
+    sizes = []
+    out, rounds, evals = run_generators([nelder_mead_gen(x0, adaptive=True) for x0 in x0s],
+                                        lambda xs: (sizes.append(len(xs)), [f(x) for x in xs])[1])
+    assert max(sizes) == len(x0s) and rounds == len(sizes) and evals == sum(sizes) and rounds < evals
+    for (x, fx) in out:
+        assert np.allclose(x, 1.5, atol=1e-3) and fx < 1e-6
