@@ -148,7 +148,10 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        self.first = len(self.rows)         # timed region starts here
 
     def start(self):
         try:
@@ -174,7 +177,7 @@ class ClockSampler(object):
             pass
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
             except Exception:
@@ -276,13 +279,15 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-
+    # the sampler is started before the warm-up (process start-up perturbs the first launches) and only
+    # the samples taken inside the timed region are kept
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks.mark()
     l0 = gp.launch_count
     kev = []
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
