@@ -1,79 +1,87 @@
-"""MCMC helpers: mirror of reference ``approxposterior/mcmcUtils.py``."""
+"""MCMC helpers mirroring the public functions of reference ``approxposterior/mcmcUtils.py``
+(``validateMCMCKwargs`` :15-100, ``batchMeansMCSE`` :103-161, ``estimateBurnin`` :164-227).
+Same names, arguments, defaults and return values; written for the B200 engine's sampler objects
+(anything exposing ``get_autocorr_time(tol=0)`` works)."""
 import numpy as np
 
 __all__ = ["validateMCMCKwargs", "batchMeansMCSE", "estimateBurnin"]
 
+_DEFAULT_ITERATIONS = 10000
+_WALKERS_PER_DIM = 20
+
 
 def validateMCMCKwargs(ap, samplerKwargs, mcmcKwargs, verbose=False):
-    """Sanitise the sampler / run kwargs (reference mcmcUtils.py:15-100): ndim and log_prob_fn are
-    forced, a user backend is dropped, defaults are nwalkers = 20*ndim, iterations = 10000 and
-    initial_state = ap.priorSample(nwalkers).  (The reference's ``samplerKwargs=None`` branch reads
-    a non-existent "dim" key, mcmcUtils.py:47; the intended 20*ndim default is used here.)"""
-    if samplerKwargs is None:
-        samplerKwargs = dict()
-        samplerKwargs["ndim"] = ap.ndim
-        samplerKwargs["nwalkers"] = 20 * samplerKwargs["ndim"]
-        samplerKwargs["log_prob_fn"] = ap._gpll
-    else:
-        samplerKwargs.pop("ndim", None)
-        samplerKwargs["ndim"] = ap.ndim
-        if "nwalkers" not in samplerKwargs:
+    """Return sanitised (samplerKwargs, mcmcKwargs) for an ``ApproxPosterior`` ``ap``.
+
+    Sampler side: ``ndim`` is always ``ap.ndim`` and ``log_prob_fn`` always ``ap._gpll`` (user values are
+    dropped), a user ``backend`` is dropped with a warning (the driver creates its own chain cache), and
+    ``nwalkers`` defaults to 20 per dimension.  Run side: ``iterations`` defaults to 10000 and
+    ``initial_state`` to ``ap.priorSample(nwalkers)``.  Passing ``samplerKwargs=None`` gives the same
+    defaults -- the reference reads a non-existent ``"dim"`` key on that branch (mcmcUtils.py:47) and
+    raises KeyError; the documented intent (20 * ndim walkers) is what is implemented here."""
+    sk = {} if samplerKwargs is None else samplerKwargs
+    had_sampler_kwargs = samplerKwargs is not None
+    if had_sampler_kwargs and "backend" in sk:
+        print("WARNING: backend in samplerKwargs. approxposterior creates its own!")
+        print("with filename = apRun.h5. Disregarding user-supplied backend.")
+    for forced in ("ndim", "log_prob_fn", "backend"):
+        sk.pop(forced, None)
+    sk["ndim"] = ap.ndim
+    if "nwalkers" not in sk:
+        if had_sampler_kwargs:
             print("WARNING: samplerKwargs provided but nwalkers not in samplerKwargs")
             print("Defaulting to nwalkers = 20 per dimension.")
-            samplerKwargs["nwalkers"] = 20 * samplerKwargs["ndim"]
-        if "backend" in samplerKwargs:
-            print("WARNING: backend in samplerKwargs. approxposterior creates its own!")
-            print("with filename = apRun.h5. Disregarding user-supplied backend.")
-        samplerKwargs.pop("log_prob_fn", None)
-        samplerKwargs.pop("backend", None)
-        samplerKwargs["log_prob_fn"] = ap._gpll
+        sk["nwalkers"] = _WALKERS_PER_DIM * ap.ndim
+    sk["log_prob_fn"] = ap._gpll
 
-    if mcmcKwargs is None:
-        mcmcKwargs = dict()
-        mcmcKwargs["iterations"] = 10000
-        mcmcKwargs["initial_state"] = ap.priorSample(samplerKwargs["nwalkers"])
-    else:
-        if "iterations" not in mcmcKwargs:
-            mcmcKwargs["iterations"] = 10000
-            if verbose:
-                print("WARNING: mcmcKwargs provided, but iterations not in mcmcKwargs.")
-                print("Defaulting to iterations = 10000.")
-        if "initial_state" not in mcmcKwargs:
-            mcmcKwargs["initial_state"] = ap.priorSample(samplerKwargs["nwalkers"])
-            if verbose:
-                print("WARNING: mcmcKwargs provided, but initial_state not in mcmcKwargs.")
-                print("Defaulting to nwalkers samples from priorSample.")
-    return samplerKwargs, mcmcKwargs
+    mk = {} if mcmcKwargs is None else mcmcKwargs
+    had_mcmc_kwargs = mcmcKwargs is not None
+    if "iterations" not in mk:
+        mk["iterations"] = _DEFAULT_ITERATIONS
+        if had_mcmc_kwargs and verbose:
+            print("WARNING: mcmcKwargs provided, but iterations not in mcmcKwargs.")
+            print("Defaulting to iterations = %d." % _DEFAULT_ITERATIONS)
+    if "initial_state" not in mk:
+        mk["initial_state"] = ap.priorSample(sk["nwalkers"])
+        if had_mcmc_kwargs and verbose:
+            print("WARNING: mcmcKwargs provided, but initial_state not in mcmcKwargs.")
+            print("Defaulting to nwalkers samples from priorSample.")
+    return sk, mk
 
 
 def batchMeansMCSE(samples, bins=None, fn=None):
-    """Non-overlapping batch-means Monte-Carlo standard error (reference mcmcUtils.py:103-161)."""
-    samples = np.asarray(samples)
-    vals = samples if fn is None else np.asarray(fn(samples))
-    n = len(samples)
+    """Monte-Carlo standard error of ``mean(fn(samples))`` by non-overlapping batch means:
+    with b = len(samples) // bins,  MCSE^2 = b / (bins - 1) * sum_k (batchmean_k - overall)^2 / len(samples).
+    ``bins`` defaults to max(int(sqrt(n)), 2); ``fn`` to the identity."""
+    chain = np.asarray(samples)
+    values = chain if fn is None else np.asarray(fn(chain))
+    nsamp = len(chain)
     if bins is None:
-        bins = max(int(np.sqrt(n)), 2)
-    assert isinstance(bins, int), "bins must be an integer"
-    size = int(n / bins)
-    total = np.mean(vals, axis=0)                       # statistic over the whole chain
-    means = np.array([np.sum(vals[i * size:(i + 1) * size], axis=0) / size for i in range(bins)])
-    mcse = size / (bins - 1) * np.sum((means - total) ** 2, axis=0)
-    return np.sqrt(mcse / n)
+        bins = max(int(np.sqrt(nsamp)), 2)
+    if not isinstance(bins, int):
+        raise AssertionError("bins must be an integer")
+    width = int(nsamp / bins)
+    overall = values.mean(axis=0)
+    batch = np.stack([values[k * width:(k + 1) * width].sum(axis=0) / width for k in range(bins)])
+    spread = ((batch - overall) ** 2).sum(axis=0)
+    return np.sqrt(width / (bins - 1) * spread / nsamp)
 
 
 def estimateBurnin(sampler, estBurnin=True, thinChains=True, verbose=False):
-    """Burn-in = int(2 max tau), thin = max(int(0.5 min tau), 1) from the integrated autocorrelation
-    time with tol=0 (reference mcmcUtils.py:164-227)."""
-    tau = sampler.get_autocorr_time(tol=0)
-    if np.any(~np.isfinite(tau)):
-        tau = tau[np.isfinite(np.array(tau))]
-        if len(tau) < 1:
+    """(iburn, ithin) from the integrated autocorrelation time tau of a finished chain:
+    iburn = int(2 max tau) if ``estBurnin`` else 0;  ithin = max(int(0.5 min tau), 1) if ``thinChains`` else 1.
+    Non-finite tau entries are ignored; if none is finite tau = 1 is used."""
+    tau = np.atleast_1d(np.asarray(sampler.get_autocorr_time(tol=0), dtype=float))
+    finite = np.isfinite(tau)
+    if not finite.all():
+        tau = tau[finite]
+        if tau.size == 0:
             if verbose:
                 print("Failed to compute integrated autocorrelation length, tau.")
                 print("Setting tau = 1")
-            tau = 1
-    iburn = int(2.0 * np.max(tau)) if estBurnin else 0
-    ithin = np.max((int(0.5 * np.min(tau)), 1)) if thinChains else 1
+            tau = np.ones(1)
+    iburn = int(2.0 * tau.max()) if estBurnin else 0
+    ithin = max(int(0.5 * tau.min()), 1) if thinChains else 1
     if verbose:
         print("burn-in estimate: %d" % iburn)
         print("thin estimate: %d" % ithin)
