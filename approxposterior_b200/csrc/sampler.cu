@@ -36,6 +36,44 @@ struct Smem {
 
 // lnprob for the `np` rows of sm.q.  A warp takes two rows per pass (they share every training-set load),
 // lanes stride over the training points; sm.sq holds the rows pre-scaled by sqrt(1/(2 M_i)).
+// inner product loop of eval_rows over the training points; XS is the [d+1][Npad] SoA block (row d = alphaA).
+// Two query rows x two training points per trip: every operand load is shared by at least two evaluations,
+// and all addressing is 32-bit offset arithmetic (the kernel is issue-bound, not FP64-bound).
+__device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const double* __restrict__ al,
+                                          const double* __restrict__ q0, const double* __restrict__ q1,
+                                          const double* __restrict__ etab, int N, int Npad, int d, int lane,
+                                          double& acc0, double& acc1) {
+  int j = lane;
+  for (; j + 32 < N; j += 64) {
+    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;      // s[row][point]
+    int off = j;
+    for (int c = 0; c < d; ++c, off += Npad) {
+      const double xa = xs[off], xb = xs[off + 32];
+      const double qa = q0[c], qb = q1[c];
+      double t;
+      t = xa - qa; s00 = fma(t, t, s00);
+      t = xb - qa; s01 = fma(t, t, s01);
+      t = xa - qb; s10 = fma(t, t, s10);
+      t = xb - qb; s11 = fma(t, t, s11);
+    }
+    const double a0 = al[j], a1 = al[j + 32];
+    acc0 = fma(exp_neg(s00, etab), a0, acc0); acc0 = fma(exp_neg(s01, etab), a1, acc0);
+    acc1 = fma(exp_neg(s10, etab), a0, acc1); acc1 = fma(exp_neg(s11, etab), a1, acc1);
+  }
+  for (; j < N; j += 32) {
+    double s0 = 0.0, s1 = 0.0;
+    int off = j;
+    for (int c = 0; c < d; ++c, off += Npad) {
+      const double x = xs[off];
+      const double d0 = x - q0[c], d1 = x - q1[c];
+      s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
+    }
+    const double a = al[j];
+    acc0 = fma(exp_neg(s0, etab), a, acc0);
+    acc1 = fma(exp_neg(s1, etab), a, acc1);
+  }
+}
+
 __device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int d = p.d, Npad = p.Npad;
@@ -45,21 +83,10 @@ __device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np) {
     __syncwarp();
     double acc0 = 0.0, acc1 = 0.0;
     if (ok0 | ok1) {
-      const double* xs = sm.xs ? sm.xs : p.Xs;
-      const double* al = sm.xs ? sm.xs + (size_t)d * Npad : p.alphaA;
       const double* q0 = sm.sq + i0 * d;
       const double* q1 = sm.sq + i1 * d;
-      for (int j = lane; j < p.N; j += 32) {
-        double s0 = 0.0, s1 = 0.0;
-        for (int c = 0; c < d; ++c) {
-          const double x = xs[(size_t)c * Npad + j];
-          const double d0 = x - q0[c], d1 = x - q1[c];
-          s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
-        }
-        const double a = al[j];
-        acc0 = fma(exp_neg(s0, sm.etab), a, acc0);
-        acc1 = fma(exp_neg(s1, sm.etab), a, acc1);
-      }
+      if (sm.xs) eval_pair(sm.xs, sm.xs + d * Npad, q0, q1, sm.etab, p.N, Npad, d, lane, acc0, acc1);
+      else eval_pair(p.Xs, p.alphaA, q0, q1, sm.etab, p.N, Npad, d, lane, acc0, acc1);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
