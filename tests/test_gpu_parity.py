@@ -358,3 +358,16 @@ def test_ill_conditioned_against_multiprecision_truth():
     scale = float(np.max(np.abs(y)))
     assert err_g <= 20 * max(err_o, 1e-12 * scale), (err_g, err_o)
     assert verr_g <= 20 * max(verr_o, 1e-12 * amp), (verr_g, verr_o)
+
+
+def test_sampler_argument_errors_are_reported():
+    from approxposterior_b200 import _lib
+    theta, y = rosenbrock_training(30)
+    gp, _ = make_pair(theta, y, np.zeros(2))
+    b = [(-5, 5), (-5, 5)]
+    with pytest.raises(_lib.ApgpError):
+        gp.run_ensembles(y, np.zeros((7, 2)), 10, b)            # odd number of walkers
+    with pytest.raises(_lib.ApgpError):
+        gp.run_ensembles(y, np.zeros((4, 2)), 0, b)             # no steps
+    with pytest.raises(ValueError):
+        gp.run_ensembles(y, np.zeros((10, 2)), 10, b, nens=3)   # rows not a multiple of nens
