@@ -150,13 +150,20 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index, self.rows, self.proc, self.first = index, [], None, 0
 
+    def wait_first_sample(self, timeout=8.0):
+        """nvidia-smi's start-up holds a driver lock for a moment (a ~100 ms launch stall was measured when it
+        overlapped a timed step): wait until it is up and sampling before any GPU work is timed."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
     def mark(self):
         self.first = len(self.rows)         # timed region starts here
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -284,6 +291,7 @@ def run_gpu(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        clocks.wait_first_sample()
     for i in range(args.warmup):
         step(i)
     barrier()
