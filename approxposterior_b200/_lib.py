@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(_HERE, "libapgp.so")
 
 APGP_OK, APGP_NOT_POSDEF, APGP_NOT_COMPUTED, APGP_NEEDS_REFACTOR = 0, 1, 2, 3
 MAX_DIM = 32
-UTIL_KINDS = {None: 0, "none": 0, "agp": 1, "bape": 2, "jones": 3}
+UTIL_KINDS = {None: 0, "none": 0, "agp": 1, "bape": 2, "jones": 3, "negmean": 4}
+OPT_METHODS = {"nelder-mead": 0, "powell": 1}
+OPT_INF = 1 << 62
 
 
 class PredictOpts(C.Structure):
@@ -30,6 +32,11 @@ class SamplerOpts(C.Structure):
                 ("lnprior_const", C.c_double),
                 ("replay_inds", C.c_void_p), ("replay_zz", C.c_void_p),
                 ("replay_rint", C.c_void_p), ("replay_logu", C.c_void_p)]
+
+
+class OptOpts(C.Structure):
+    _fields_ = [("method", C.c_int), ("adaptive", C.c_int), ("xtol", C.c_double), ("ftol", C.c_double),
+                ("maxiter", C.c_longlong), ("maxfev", C.c_longlong)]
 
 
 _SIGNATURES = {
@@ -51,6 +58,11 @@ _SIGNATURES = {
                                     C.c_void_p]),
     "apgp_sampler_run": (C.c_int, [C.c_void_p, C.POINTER(SamplerOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int]),
+    "apgp_minimize_utility": (C.c_int, [C.c_void_p, C.POINTER(PredictOpts), C.POINTER(OptOpts), C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "apgp_minimize_nll": (C.c_int, [C.c_void_p, C.POINTER(OptOpts), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "apgp_minimize_nll_fits": (C.c_int, [C.c_void_p, C.c_int]),
     "apgp_get_alpha": (C.c_int, [C.c_void_p, C.c_void_p]),
     "apgp_get_linv": (C.c_int, [C.c_void_p, C.c_void_p]),
     "apgp_get_chol": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -39,7 +39,10 @@ def supported(method, options, bounds=None, jac=None):
 # ----------------------------------------------------------------------------------------------
 # Nelder-Mead (scipy.optimize._optimize._minimize_neldermead)
 # ----------------------------------------------------------------------------------------------
-def nelder_mead_gen(x0, adaptive=False, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None):
+def nelder_mead_gen(x0, adaptive=False, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None, _stable=False):
+    """``_stable`` orders tied simplex values with a stable sort, as the device restatement (csrc/optimize.cu)
+    does; SciPy's plain ``np.argsort`` leaves the order of ties to NumPy's introsort / SIMD dispatch."""
+    argsort = (lambda a: np.argsort(a, kind="stable")) if _stable else np.argsort
     x0 = np.atleast_1d(np.asarray(x0, dtype=np.float64)).flatten()
     N = len(x0)
     if adaptive:
@@ -82,7 +85,7 @@ def nelder_mead_gen(x0, adaptive=False, xatol=1e-4, fatol=1e-4, maxiter=None, ma
             fsim[k] = yield from ev(sim[k])
     except _MaxFun:
         pass
-    ind = np.argsort(fsim)
+    ind = argsort(fsim)
     sim = np.take(sim, ind, 0)
     fsim = np.take(fsim, ind, 0)
     iterations = 1
@@ -133,7 +136,7 @@ def nelder_mead_gen(x0, adaptive=False, xatol=1e-4, fatol=1e-4, maxiter=None, ma
         except _MaxFun:
             pass
         finally:
-            ind = np.argsort(fsim)
+            ind = argsort(fsim)
             sim = np.take(sim, ind, 0)
             fsim = np.take(fsim, ind, 0)
     return sim[0], fsim[0]

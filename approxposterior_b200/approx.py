@@ -339,6 +339,7 @@ class ApproxPosterior(object):
             return -(self._gpll(x)[0])
 
         fn.batch = lambda T: -self._gpll_batch(T)[0]      # all restarts' calls in one mean-only predict
+        fn.device_kind = "negmean"                        # ... or the whole multistart on the device (box priors)
 
         MAP, MAPVal = ut.minimizeObjective(fn, self.y, self.gp, self.priorSample, self._lnprior,
                                            nRestarts=nRestarts, args=None, method=method, options=options,

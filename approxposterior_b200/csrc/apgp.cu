@@ -64,6 +64,7 @@ struct apgp_handle {
   static constexpr size_t PIN_DOUBLES = 32768;   // 256 KB: [0, PIN/2) inputs, [PIN/2, PIN) outputs
   DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
+  DevBuf o_in, o_x, o_f, o_stats;      // device optimiser staging
 };
 
 namespace {
@@ -119,7 +120,7 @@ int apgp_destroy(apgp_handle* h) {
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
                     &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->ap_k, &h->ap_l, &h->ap_u, &h->ap_x, &h->bK,
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
-                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl};
+                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats};
   for (DevBuf* b : bufs) b->release();
   if (h->pin) cudaFreeHost(h->pin);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -517,6 +518,89 @@ int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* o, const double* p
     CU(cudaStreamSynchronize(h->stream));
   }
   return APGP_OK;
+}
+
+// ---- device-resident optimisers ---------------------------------------------------------------------
+static int resolve_opt(const apgp_opt_opts* o, int n, OptimizeParams& q) {
+  if (o->method != APGP_OPT_NELDER_MEAD && o->method != APGP_OPT_POWELL) return -1;
+  const long long INF = 1LL << 62;
+  long long mi = o->maxiter, mf = o->maxfev;
+  const long long def = (long long)n * (o->method == APGP_OPT_NELDER_MEAD ? 200 : 1000);   // SciPy's defaults
+  if (mi < 0 && mf < 0) { mi = def; mf = def; }
+  else if (mi < 0) mi = (mf >= INF) ? def : INF;
+  else if (mf < 0) mf = (mi >= INF) ? def : INF;
+  q.method = o->method; q.adaptive = o->adaptive; q.xtol = o->xtol; q.ftol = o->ftol; q.maxiter = mi; q.maxfun = mf;
+  return 0;
+}
+
+static int opt_stage(apgp_handle* h, const double* in, size_t nin, size_t nx, int R) {
+  CUI(h->o_in.reserve(nin * 8)); CUI(h->o_x.reserve(nx * 8)); CUI(h->o_f.reserve((size_t)R * 8));
+  CUI(h->o_stats.reserve((size_t)R * 16));
+  const double* src = in;
+  if (nin <= apgp_handle::PIN_DOUBLES / 2) { memcpy(h->pin, in, nin * 8); src = h->pin; }
+  CU(cudaMemcpyAsync(h->o_in.p, src, nin * 8, cudaMemcpyHostToDevice, h->stream));
+  return APGP_OK;
+}
+
+static int opt_fetch(apgp_handle* h, size_t nx, int R, double* x_out, double* f_out, long long* nfev) {
+  std::vector<long long> st((size_t)2 * R);
+  CU(cudaMemcpyAsync(x_out, h->o_x.p, nx * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(f_out, h->o_f.p, (size_t)R * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(st.data(), h->o_stats.p, (size_t)R * 16, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (nfev) for (int r = 0; r < R; ++r) nfev[r] = st[2 * r];
+  return APGP_OK;
+}
+
+int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const apgp_opt_opts* opt, const double* x0,
+                          int R, double* x_out, double* f_out, long long* nfev, int evaluate_only) {
+  if (!h || !obj || !opt || !x0 || !x_out || !f_out) return fail(APGP_ERR_ARG, "apgp_minimize_utility: null argument");
+  if (!h->factored) return fail(APGP_NOT_COMPUTED, "apgp_minimize_utility: GP not computed");
+  if (obj->utility < APGP_UTIL_AGP || obj->utility > APGP_UTIL_NEGMEAN)
+    return fail(APGP_ERR_ARG, "apgp_minimize_utility: objective must be AGP, BAPE, Jones or NEGMEAN");
+  if (R < 1) return APGP_OK;
+  Guard g(h->device);
+  const int d = h->d;
+  OptimizeParams q;
+  if (resolve_opt(opt, d, q)) return fail(APGP_ERR_ARG, "apgp_minimize_utility: bad method");
+  UtilityPointParams u;
+  memset(&u, 0, sizeof(u));
+  u.N = h->N; u.d = d; u.Npad = h->Npad; u.ldL = h->Np;
+  u.Xs = h->Xs.as<double>(); u.alphaA = h->alphaA.as<double>(); u.Linv = h->Linv.as<double>();
+  u.amp = h->amp; u.mean = h->mean; u.ybest = obj->ybest; u.zeta = obj->zeta; u.kind = obj->utility; u.has_box = obj->has_box;
+  for (int i = 0; i < d; ++i) { u.lo[i] = obj->lo[i]; u.hi[i] = obj->hi[i]; u.qscale[i] = sqrt(0.5 * exp(-h->log_metric[i])); }
+  { int st_ = opt_stage(h, x0, (size_t)R * d, (size_t)R * d, R); if (st_ != APGP_OK) return st_; }
+  CUI(launch_minimize_utility(u, q, R, h->o_in.as<double>(), h->o_x.as<double>(), h->o_f.as<double>(),
+                              h->o_stats.as<long long>(), evaluate_only ? 0 : 1, h->stream));
+  h->launches += 1;
+  return opt_fetch(h, (size_t)R * d, R, x_out, f_out, nfev);
+}
+
+int apgp_minimize_nll_fits(const apgp_handle* h, int P) {
+  if (!h || !h->has_training) return 0;
+  return minimize_nll_fits(h->N, h->d, P) ? 1 : 0;
+}
+
+int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0, int R, int P, int fit_amp,
+                      double white_noise, int default_prior, double* p_out, double* f_out, long long* nfev,
+                      int evaluate_only) {
+  if (!h || !opt || !p0 || !p_out || !f_out) return fail(APGP_ERR_ARG, "apgp_minimize_nll: null argument");
+  if (!h->has_training) return fail(APGP_ERR_ARG, "apgp_minimize_nll: no training set");
+  const int d = h->d, N = h->N;
+  if (P != 1 + (fit_amp ? 1 : 0) + d) return fail(APGP_ERR_ARG, "apgp_minimize_nll: P != 1 + fit_amp + d");
+  if (!minimize_nll_fits(N, d, P))
+    return fail(APGP_ERR_ARG, "apgp_minimize_nll: training set too large for the one-restart-per-CTA shared-memory "
+                              "path (N <= ~220); drive apgp_loglik_batch from the host optimiser instead");
+  if (R < 1) return APGP_OK;
+  Guard g(h->device);
+  OptimizeParams q;
+  if (resolve_opt(opt, P, q)) return fail(APGP_ERR_ARG, "apgp_minimize_nll: bad method");
+  { int st_ = opt_stage(h, p0, (size_t)R * P, (size_t)R * P, R); if (st_ != APGP_OK) return st_; }
+  CUI(launch_minimize_nll(h->X.as<double>(), h->y.as<double>(), N, d, P, fit_amp ? 1 : 0, default_prior ? 1 : 0,
+                          exp(white_noise) + TINY2, q, R, h->o_in.as<double>(), h->o_x.as<double>(), h->o_f.as<double>(),
+                          h->o_stats.as<long long>(), evaluate_only ? 0 : 1, h->stream));
+  h->launches += 1;
+  return opt_fetch(h, (size_t)R * P, R, p_out, f_out, nfev);
 }
 
 int apgp_get_alpha(apgp_handle* h, double* alpha) {

@@ -72,6 +72,33 @@ int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv
                        const double* hyper_dev, int fit_amp, double* work /*[Np*Np]*/, double* grad_dev, cudaStream_t st,
                        int* launches);
 
+
+// ---- device-resident optimisers (optimize.cu) ------------------------------------
+struct OptimizeParams {
+  int method;              // 0 Nelder-Mead, 1 Powell
+  int adaptive;            // Nelder-Mead {"adaptive": True}
+  double xtol, ftol;       // Nelder-Mead xatol/fatol, Powell xtol/ftol
+  long long maxiter, maxfun;   // resolved by the caller with SciPy's default rules
+};
+struct UtilityPointParams {  // single-query predict + utility, read straight from the handle's factorisation
+  int N, d, Npad, ldL;
+  const double* Xs;        // [d][Npad] scaled SoA
+  const double* alphaA;    // [Npad]
+  const double* Linv;      // [ldL][ldL] row-major explicit L^{-1}
+  double amp, mean, ybest, zeta;
+  int kind;                // 1 AGP, 2 BAPE, 3 Jones, 4 -(mean)
+  int has_box;
+  double lo[APGP_MAXD], hi[APGP_MAXD], qscale[APGP_MAXD];
+};
+// mode 0: evaluate the objective at the R points; mode 1: minimise from the R starts (one CTA each).
+// stats_dev [R][2] = (function evaluations, iterations) or null.
+int launch_minimize_utility(const UtilityPointParams& u, const OptimizeParams& q, int R, const double* x0_dev,
+                            double* x_out_dev, double* f_out_dev, long long* stats_dev, int mode, cudaStream_t st);
+bool minimize_nll_fits(int N, int d, int P);
+int launch_minimize_nll(const double* X_dev, const double* y_dev, int N, int d, int P, int fit_amp, int default_prior,
+                        double noise, const OptimizeParams& q, int R, const double* p0_dev, double* p_out_dev,
+                        double* f_out_dev, long long* stats_dev, int mode, cudaStream_t st);
+
 // ---- sampler ---------------------------------------------------------------------
 struct SamplerParams {
   int nens, nwalk, d, nsteps, N, Npad;

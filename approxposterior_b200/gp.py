@@ -322,6 +322,82 @@ class GP(object):
             return ll
         return ll, (grad if self.fit_mean else grad[:, 1:])
 
+    # ------------------------------------------------------------------ device-resident optimisers
+    @staticmethod
+    def _opt_opts(method, options):
+        """(method, options) of scipy.optimize.minimize -> apgp_opt_opts (same defaults as SciPy)."""
+        m = str(method).lower()
+        opts = dict(options or {})
+        o = _lib.OptOpts()
+        o.method = _lib.OPT_METHODS[m]
+        o.adaptive = 1 if opts.get("adaptive", False) else 0
+        if m == "nelder-mead":
+            o.xtol, o.ftol = float(opts.get("xatol", 1e-4)), float(opts.get("fatol", 1e-4))
+        else:
+            o.xtol, o.ftol = float(opts.get("xtol", 1e-4)), float(opts.get("ftol", 1e-4))
+
+        def lim(v):
+            if v is None:
+                return -1
+            return _lib.OPT_INF if v == np.inf else int(v)
+        o.maxiter, o.maxfev = lim(opts.get("maxiter")), lim(opts.get("maxfev"))
+        return o
+
+    def minimize_utility(self, y, x0, utility, bounds=None, method="nelder-mead", options=None, zeta=0.01,
+                         evaluate_only=False):
+        """``scipy.optimize.minimize(fn, x0[r], method=method, options=options)`` for every row of ``x0`` in ONE
+        launch (one CTA per start; reference utility.py:332-371).  ``fn`` is the AGP/BAPE/Jones utility exactly
+        as utility.py:99-250 evaluates it at a single point (``+inf`` outside ``bounds``), or ``"negmean"``
+        (findMAP's objective, approx.py:909-914).  Returns (x [R,d], f [R], nfev [R]).  ``evaluate_only``
+        returns fn(x0) -- the very function the device optimiser minimises."""
+        self._sync_y(y)
+        self.recompute()
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(-1, self.ndim))
+        R = x0.shape[0]
+        obj = _lib.PredictOpts()
+        obj.want_var = 1
+        obj.utility = _lib.UTIL_KINDS[str(utility).lower()]
+        obj.ybest, obj.zeta = float(np.max(self._y)), float(zeta)
+        if bounds is not None:
+            obj.has_box = 1
+            _lib.fill_bounds(obj.lo, obj.hi, bounds, self.ndim)
+        o = self._opt_opts(method, options)
+        x, f, nfev = np.empty_like(x0), np.empty(R), np.zeros(R, dtype=np.int64)
+        _lib.check(self._lib.apgp_minimize_utility(self._h, C.byref(obj), C.byref(o), _lib.ptr(x0), R, _lib.ptr(x),
+                                                   _lib.ptr(f), _lib.ptr(nfev), 1 if evaluate_only else 0),
+                   "apgp_minimize_utility")
+        return x, f, nfev
+
+    def can_minimize_nll(self):
+        """True when the training set fits the one-restart-per-CTA shared-memory optimiser (N <= ~220)."""
+        if self._x is None:
+            return False
+        if not self._training_uploaded:
+            self._upload_training()
+        return bool(self._lib.apgp_minimize_nll_fits(self._h, len(self) if self.fit_mean else len(self) + 1))
+
+    def minimize_nll(self, P0, y, method="powell", options=None, default_prior=True, evaluate_only=False):
+        """``scipy.optimize.minimize(_nll, P0[r], method=method, options=options)`` for every row of ``P0`` in ONE
+        launch (one CTA per restart; reference gpUtils.py:223-247 with _nll of gpUtils.py:46-80).
+        ``default_prior`` applies gpUtils.defaultHyperPrior inside the objective.  Returns (p [R,P], nll [R], nfev [R]).
+        Leaves the GP's own hyper-parameters untouched."""
+        if not self.fit_mean:
+            raise NotImplementedError("minimize_nll needs fit_mean=True (the gpUtils.defaultGP layout)")
+        P0 = np.ascontiguousarray(np.atleast_2d(np.asarray(P0, dtype=np.float64)))
+        if P0.shape[1] != len(self):
+            raise ValueError("dimension mismatch")
+        self._sync_y(y)
+        if not self._training_uploaded:
+            self._upload_training()
+        R = P0.shape[0]
+        o = self._opt_opts(method, options)
+        p, f, nfev = np.empty_like(P0), np.empty(R), np.zeros(R, dtype=np.int64)
+        _lib.check(self._lib.apgp_minimize_nll(self._h, C.byref(o), _lib.ptr(P0), R, P0.shape[1],
+                                               1 if self.kernel.fit_amp else 0, self.white_noise,
+                                               1 if default_prior else 0, _lib.ptr(p), _lib.ptr(f), _lib.ptr(nfev),
+                                               1 if evaluate_only else 0), "apgp_minimize_nll")
+        return p, f, nfev
+
     # ------------------------------------------------------------------ sampler
     def run_ensembles(self, y, p0, nsteps, bounds, nens=1, a=2.0, seed=0, thin=1, lnprior_const=0.0, replay=None):
         """Device-resident stretch-move sampling of the surrogate posterior mean (emcee as driven

@@ -88,15 +88,22 @@ def defaultGP(theta, y, order=None, white_noise=-12, fitAmp=False):
     return gp
 
 
+DEVICE_OPTIMIZER = True      # module default for optimizeGP(engine=None)
+
+
 def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=None, p0=None,
-               gpHyperPrior=defaultHyperPrior, batched=True):
+               gpHyperPrior=defaultHyperPrior, batched=True, engine=None):
     """Maximise the marginal likelihood over nGPRestarts starts (reference gpUtils.py:184-257).
 
     Start points are drawn exactly as the reference draws them (one ``np.random.randn()`` per
     kernel parameter per restart, gpUtils.py:227; ``seed`` is accepted and unused, as there).
-    With ``batched`` (default) the restarts advance in lock step and every round of objective calls
-    is one ``log_likelihood_batch`` launch -- for gradient methods the same launch also returns the
-    gradients (fused one-restart-per-CTA kernel while the training set fits in shared memory).
+    ``engine="device"`` (default for Powell / Nelder-Mead with the default hyper-prior while the training
+    set fits one CTA's shared memory, N <= ~220): every restart is minimised by ONE CTA of
+    ``apgp_minimize_nll`` -- SciPy's algorithm restated on the device with the covariance build and the
+    Cholesky inside the objective -- so the whole multistart fit is a single launch.
+    ``engine="lockstep"`` / larger N: the restarts advance in lock step on the host and every round of
+    objective calls is one ``log_likelihood_batch`` launch -- for gradient methods the same launch also
+    returns the gradients (fused one-restart-per-CTA kernel while the training set fits in shared memory).
     """
     y = np.asarray(y, dtype=np.float64)
     npar = len(gp.get_parameter_vector())
@@ -111,7 +118,19 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
     derivative_free = method in ["nelder-mead", "powell", "cg"]
     use_batch = batched and hasattr(gp, "log_likelihood_batch")
 
-    if use_batch and _opt.supported(method, options):
+    if engine is None:
+        engine = "device" if DEVICE_OPTIMIZER else "lockstep"
+    on_device = (engine == "device" and use_batch and _opt.supported(method, options)
+                 and (gpHyperPrior is defaultHyperPrior or gpHyperPrior is None)
+                 and hasattr(gp, "minimize_nll") and gp.can_minimize_nll())
+
+    if on_device:
+        res, _, nfev = gp.minimize_nll(np.array(x0s), y, method=method, options=options,
+                                       default_prior=gpHyperPrior is not None)
+        res = list(res)
+        optimizeGP.last_stats = dict(batches=1, evals=int(np.sum(nfev)), scheduler="device")
+        mll = list(gp.log_likelihood_batch(np.array(res), y))
+    elif use_batch and _opt.supported(method, options):
         # thread-free lock step: SciPy's Powell / Nelder-Mead restated as coroutines (same iterates)
         make = _opt.powell_gen if str(method).lower() == "powell" else _opt.nelder_mead_gen
         out, rounds, evals = _opt.run_generators([make(x0, **(options or {})) for x0 in x0s],

@@ -150,16 +150,25 @@ def scanUtility(gp, y, kind, bounds, nCandidates=1 << 20, seed=None, zeta=0.01, 
     return best_np, ubest, cand.cpu().numpy(), u.cpu().numpy()
 
 
+DEVICE_OPTIMIZER = True      # module default for minimizeObjective(engine=None)
+
+
 def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-mead", options=None, bounds=None,
-                      theta0=None, args=None, maxIters=100, batched=True, _start=None):
+                      theta0=None, args=None, maxIters=100, batched=True, _start=None, engine=None):
     """Multistart local minimisation of ``fn`` (reference utility.py:253-372).
 
     Protocol kept from the reference: Nelder-Mead ``{"adaptive": True}`` by default; bounds are only
     forwarded for methods " l-bfgs-b" (sic) and "tnc"; each restart starts from ``sampleFn(1)`` (or
     a perturbed ``theta0``), and is retried from a fresh prior sample, up to ``maxIters`` times,
     until its optimum is finite and allowed by ``priorFn``; the best of the restarts is returned.
-    When ``fn`` is one of the three utilities and ``gp`` is the B200 GP, the restarts run in lock
-    step and each round of objective calls is one fused predict+utility launch.
+    When ``fn`` is one of the three utilities and ``gp`` is the B200 GP, the restarts do not go through
+    SciPy one objective call at a time:
+
+    * ``engine="device"`` (default when ``priorFn`` is a box prior exposing ``.bounds`` and the method/options
+      are covered): every restart is minimised by ONE CTA of ``apgp_minimize_utility`` -- SciPy's
+      Nelder-Mead / Powell restated on the device, the whole multistart in a single launch;
+    * ``engine="lockstep"``: the restarts advance in lock step on the host (coroutine restatements of the
+      same SciPy algorithms) and each round of objective calls is one fused predict+utility launch.
     """
     if str(method).lower() == "nelder-mead" and options is None:
         options = {"adaptive": True}
@@ -189,8 +198,38 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
     if _start is not None:          # engine extension: polish a known-good candidate (scanUtility)
         starts[0] = np.asarray(_start, dtype=np.float64).ravel()
 
-    kind = _KIND.get(fn)
+    kind = _KIND.get(fn) or getattr(fn, "device_kind", None)
     fn_batch = getattr(fn, "batch", None)      # any objective may bring its own batched form
+    box = getattr(priorFn, "bounds", None)
+    if engine is None:
+        engine = "device" if DEVICE_OPTIMIZER else "lockstep"
+    if (engine == "device" and batched and kind is not None and box is not None and hasattr(gp, "minimize_utility")
+            and _opt.supported(method, options, bounds)):
+        # one CTA per restart, the whole multistart in one launch; restarts whose optimum is not finite or is
+        # rejected by the prior are redrawn from the prior and re-run (utility.py:342-366), together
+        res, objective = [None] * nRestarts, [None] * nRestarts
+        todo, t0s, nlaunch, nev = list(range(nRestarts)), list(starts), 0, 0
+        for ii in range(maxIters + 1):
+            if ii >= maxIters:
+                raise RuntimeError("ERROR: Cannot find a valid solution. Current iterations: %d\n"
+                                   "Maximum iterations: %d\n" % (ii, maxIters))
+            xs, fs, nfev = gp.minimize_utility(y, np.array(t0s), kind, bounds=box, method=method, options=options)
+            nlaunch += 1
+            nev += int(np.sum(nfev))
+            again, t0n = [], []
+            for r, x, f in zip(todo, xs, fs):
+                if np.all(np.isfinite(x)) and np.isfinite(priorFn(x)):
+                    res[r], objective[r] = x, f
+                else:
+                    again.append(r)
+                    t0n.append(draw())
+            todo, t0s = again, t0n
+            if not todo:
+                break
+        minimizeObjective.last_stats = dict(batches=nlaunch, evals=nev, scheduler="device")
+        bestInd = np.argmin(objective)
+        return np.array(res)[bestInd], objective[bestInd]
+
     use_batch = batched and nRestarts > 1 and (fn_batch is not None or
                                                (kind is not None and hasattr(gp, "predict_utility")))
 

@@ -38,6 +38,7 @@ extern "C" {
 #define APGP_UTIL_AGP 1          /* utility.py:99-142  */
 #define APGP_UTIL_BAPE 2         /* utility.py:145-189 */
 #define APGP_UTIL_JONES 3        /* utility.py:192-250 */
+#define APGP_UTIL_NEGMEAN 4      /* -(GP mean): findMAP's objective, approx.py:909-914 (apgp_minimize_utility only) */
 
 typedef struct apgp_handle apgp_handle;
 
@@ -129,6 +130,36 @@ typedef struct apgp_sampler_opts {
  * chain [nsteps/thin][nens*nwalkers][d], logp/blob [nsteps/thin][nens*nwalkers], naccept [nens*nwalkers] int32. */
 int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double* p0, double* chain, double* logp,
                      double* blob, int* naccept, int on_host);
+
+/* ---- device-resident local optimisers: one CTA per start, the whole multistart in ONE launch ----------------- */
+#define APGP_OPT_NELDER_MEAD 0
+#define APGP_OPT_POWELL 1
+typedef struct apgp_opt_opts {
+  int method;                    /* APGP_OPT_* : scipy.optimize.minimize(method="nelder-mead" | "powell") */
+  int adaptive;                  /* Nelder-Mead options={"adaptive": True} (utility.py:307-308) */
+  double xtol, ftol;             /* Nelder-Mead xatol/fatol, Powell xtol/ftol (SciPy default 1e-4 each) */
+  long long maxiter, maxfev;     /* < 0: None (SciPy's default rule: N*200 / N*1000); >= 2^62: inf */
+} apgp_opt_opts;
+
+/* utility.minimizeObjective's inner loop (utility.py:332-371): scipy.optimize.minimize(fn, x0[r], method=...)["x"]
+ * for R starts at once on the current factorisation.  fn = obj->utility in {AGP, BAPE, JONES} evaluated as
+ * utility.py:99-250 does (single-query predict with variance + epilogue; +inf outside obj's box when has_box,
+ * the priorFn gate), or NEGMEAN = -(GP mean) with the same gate (findMAP, approx.py:909-914).
+ * x0, x_out [R][d], f_out [R] = fn(x_out[r]), nfev [R] or NULL; all host buffers.  evaluate_only=1 returns
+ * fn(x0[r]) without optimising (x_out = x0): the exact function the optimiser minimises, for tests. */
+int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const apgp_opt_opts* opt, const double* x0,
+                          int R, double* x_out, double* f_out, long long* nfev, int evaluate_only);
+
+/* gpUtils.optimizeGP's inner loop (gpUtils.py:223-247): scipy.optimize.minimize(_nll, p0[r], method=...)["x"] for
+ * R restarts at once; _nll as gpUtils.py:46-80 (+inf when default_prior and any |p[1:]| > 20 -- gpUtils.py:22-43 --,
+ * when the covariance is not positive definite or the likelihood is not finite).  Rows in george order
+ * [mean, (log_constant), log M_0..], P = 1 + fit_amp + d.  Needs the one-restart-per-CTA shared-memory path
+ * (apgp_minimize_nll_fits() == 1, N <= ~220); otherwise drive apgp_loglik_batch from a host optimiser.
+ * Does not disturb the handle's current factorisation. */
+int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0, int R, int P, int fit_amp,
+                      double white_noise, int default_prior, double* p_out, double* f_out, long long* nfev,
+                      int evaluate_only);
+int apgp_minimize_nll_fits(const apgp_handle* h, int P);
 
 /* test/diagnostic accessors (host outputs): alpha [N], Linv [N][N] row-major (lower), L likewise */
 int apgp_get_alpha(apgp_handle* h, double* alpha);
