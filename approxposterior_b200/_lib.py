@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libapgp.so")
+LIB_PATH = os.environ.get("APGP_LIB") or os.path.join(_HERE, "libapgp.so")     # APGP_LIB: debug/profiling builds
 
 APGP_OK, APGP_NOT_POSDEF, APGP_NOT_COMPUTED, APGP_NEEDS_REFACTOR = 0, 1, 2, 3
 MAX_DIM = 32
@@ -68,6 +68,7 @@ _SIGNATURES = {
     "apgp_get_chol": (C.c_int, [C.c_void_p, C.c_void_p]),
     "apgp_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "apgp_debug_exp_neg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "apgp_debug_read_prof": (C.c_int, [C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -535,25 +535,23 @@ static int resolve_opt(const apgp_opt_opts* o, int n, OptimizeParams& q) {
 
 static int opt_stage(apgp_handle* h, const double* in, size_t nin, size_t nx, int R) {
   CUI(h->o_in.reserve(nin * 8)); CUI(h->o_x.reserve(nx * 8)); CUI(h->o_f.reserve((size_t)R * 8));
-  CUI(h->o_stats.reserve((size_t)R * 16));
+  CUI(h->o_stats.reserve((size_t)R * 24));
   const double* src = in;
   if (nin <= apgp_handle::PIN_DOUBLES / 2) { memcpy(h->pin, in, nin * 8); src = h->pin; }
   CU(cudaMemcpyAsync(h->o_in.p, src, nin * 8, cudaMemcpyHostToDevice, h->stream));
   return APGP_OK;
 }
 
-static int opt_fetch(apgp_handle* h, size_t nx, int R, double* x_out, double* f_out, long long* nfev) {
-  std::vector<long long> st((size_t)2 * R);
+static int opt_fetch(apgp_handle* h, size_t nx, int R, double* x_out, double* f_out, long long* stats) {
   CU(cudaMemcpyAsync(x_out, h->o_x.p, nx * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(f_out, h->o_f.p, (size_t)R * 8, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaMemcpyAsync(st.data(), h->o_stats.p, (size_t)R * 16, cudaMemcpyDeviceToHost, h->stream));
+  if (stats) CU(cudaMemcpyAsync(stats, h->o_stats.p, (size_t)R * 24, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  if (nfev) for (int r = 0; r < R; ++r) nfev[r] = st[2 * r];
   return APGP_OK;
 }
 
 int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const apgp_opt_opts* opt, const double* x0,
-                          int R, double* x_out, double* f_out, long long* nfev, int evaluate_only) {
+                          int R, double* x_out, double* f_out, long long* stats, int evaluate_only) {
   if (!h || !obj || !opt || !x0 || !x_out || !f_out) return fail(APGP_ERR_ARG, "apgp_minimize_utility: null argument");
   if (!h->factored) return fail(APGP_NOT_COMPUTED, "apgp_minimize_utility: GP not computed");
   if (obj->utility < APGP_UTIL_AGP || obj->utility > APGP_UTIL_NEGMEAN)
@@ -573,7 +571,7 @@ int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const ap
   CUI(launch_minimize_utility(u, q, R, h->o_in.as<double>(), h->o_x.as<double>(), h->o_f.as<double>(),
                               h->o_stats.as<long long>(), evaluate_only ? 0 : 1, h->stream));
   h->launches += 1;
-  return opt_fetch(h, (size_t)R * d, R, x_out, f_out, nfev);
+  return opt_fetch(h, (size_t)R * d, R, x_out, f_out, stats);
 }
 
 int apgp_minimize_nll_fits(const apgp_handle* h, int P) {
@@ -582,7 +580,7 @@ int apgp_minimize_nll_fits(const apgp_handle* h, int P) {
 }
 
 int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0, int R, int P, int fit_amp,
-                      double white_noise, int default_prior, double* p_out, double* f_out, long long* nfev,
+                      double white_noise, int default_prior, double* p_out, double* f_out, long long* stats,
                       int evaluate_only) {
   if (!h || !opt || !p0 || !p_out || !f_out) return fail(APGP_ERR_ARG, "apgp_minimize_nll: null argument");
   if (!h->has_training) return fail(APGP_ERR_ARG, "apgp_minimize_nll: no training set");
@@ -600,7 +598,7 @@ int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0
                           exp(white_noise) + TINY2, q, R, h->o_in.as<double>(), h->o_x.as<double>(), h->o_f.as<double>(),
                           h->o_stats.as<long long>(), evaluate_only ? 0 : 1, h->stream));
   h->launches += 1;
-  return opt_fetch(h, (size_t)R * P, R, p_out, f_out, nfev);
+  return opt_fetch(h, (size_t)R * P, R, p_out, f_out, stats);
 }
 
 int apgp_get_alpha(apgp_handle* h, double* alpha) {
@@ -633,6 +631,7 @@ int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out) {
   CU(cudaStreamSynchronize(h->stream));
   return APGP_OK;
 }
+int apgp_debug_read_prof(long long* out16) { return out16 ? read_prof(out16) : APGP_ERR_ARG; }
 int apgp_get_linv(apgp_handle* h, double* linv) { return get_square(h, h->Linv, linv); }
 int apgp_get_chol(apgp_handle* h, double* L) { return get_square(h, h->K, L); }
 

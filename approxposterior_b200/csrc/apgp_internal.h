@@ -91,10 +91,11 @@ struct UtilityPointParams {  // single-query predict + utility, read straight fr
   double lo[APGP_MAXD], hi[APGP_MAXD], qscale[APGP_MAXD];
 };
 // mode 0: evaluate the objective at the R points; mode 1: minimise from the R starts (one CTA each).
-// stats_dev [R][2] = (function evaluations, iterations) or null.
+// stats_dev [R][3] = (function evaluations, iterations, SM clock cycles) or null.
 int launch_minimize_utility(const UtilityPointParams& u, const OptimizeParams& q, int R, const double* x0_dev,
                             double* x_out_dev, double* f_out_dev, long long* stats_dev, int mode, cudaStream_t st);
 bool minimize_nll_fits(int N, int d, int P);
+int read_prof(long long* out16);   // -DAPGP_PROF builds: per-phase cycle counters of the nll objective (zeros otherwise)
 int launch_minimize_nll(const double* X_dev, const double* y_dev, int N, int d, int P, int fit_amp, int default_prior,
                         double noise, const OptimizeParams& q, int R, const double* p0_dev, double* p_out_dev,
                         double* f_out_dev, long long* stats_dev, int mode, cudaStream_t st);

@@ -13,6 +13,7 @@
 // Padding: N is padded to Np (multiple of 64) with an identity block, so L and L^{-1} pad with
 // the identity and the rhs with zeros; nothing downstream needs edge handling.
 #include "apgp_internal.h"
+#include "chol_small.cuh"
 #include <math.h>
 
 namespace apgp {
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restri
 
 
 // ---- one restart per CTA: covariance build + Cholesky + forward solve + log-likelihood, all in shared
-//      memory (packed lower triangle).  Used when N(N+1)/2 + N(d+2) doubles fit in 220 KB (N <= ~224).
+//      memory (packed lower triangle).  Used when N(N+1)/2 + N(d+2) doubles fit in 220 KB (N <= ~224 < 256 threads).
 //      Replaces one gpUtils._nll evaluation (gpUtils.py:46-80) per CTA.
 //      With grad_out != nullptr the CTA goes on to alpha = L^{-T} z, inverts L in place, forms K^{-1} pair by pair
 //      and reduces  dl/dp = 1/2 tr[(alpha alpha^T - K^{-1}) dK/dp]  (george.GP.grad_log_likelihood, gpUtils.py:110):
@@ -402,34 +403,15 @@ __global__ void __launch_bounds__(256) loglik_small_kernel(const double* __restr
     }
   }
   __syncthreads();
-  double logdet = 0.0;                               // tracked by every thread identically
-  for (int j = 0; j < N; ++j) {
-    const double dj = K[(size_t)j * (j + 1) / 2 + j];
-    double s;
-    if (dj > 0.0 && dj < INFINITY) s = sqrt(dj);
-    else { s = 1.0; if (tid == 0) bad = 1; }
-    logdet += log(s);
-    const double inv = 1.0 / s;
-    const double zj = r[j] * inv;                    // forward substitution rides along
-    __syncthreads();                                 // everyone has read K_jj and r_j
-    if (tid == 0) { r[j] = zj; K[(size_t)j * (j + 1) / 2 + j] = s; }
-    for (int i = j + 1 + tid; i < N; i += 256) {
-      const double l = K[(size_t)i * (i + 1) / 2 + j] * inv;
-      col[i] = l;
-      K[(size_t)i * (i + 1) / 2 + j] = l;           // keep L (the gradient stage inverts it in place)
-      r[i] -= l * zj;
-    }
-    __syncthreads();
-    // trailing update K[i][c] -= L[i][j] L[c][j],  j < c <= i ; warp per row, lanes over c
-    for (int i = j + 1 + warp; i < N; i += 8) {
-      double* Ki = K + (size_t)i * (i + 1) / 2;
-      const double li = col[i];
-      for (int cc = j + 1 + lane; cc <= i; cc += 32) Ki[cc] -= li * col[cc];
-    }
-    __syncthreads();
-  }
-  double part = 0.0;
-  for (int i = tid; i < N; i += 256) part += r[i] * r[i];
+  // blocked Cholesky, forward substitution riding along (chol_small.cuh): r <- z, col <- diag(L)
+  chol_packed_blocked<256>(K, r, col, N, &bad, grad_out != nullptr);
+  double part = 0.0, lpart = 0.0;
+  for (int i = tid; i < N; i += 256) { part = fma(r[i], r[i], part); lpart += log(col[i]); }
+  red[tid] = lpart;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  const double logdet = red[0];
+  __syncthreads();
   red[tid] = part;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }

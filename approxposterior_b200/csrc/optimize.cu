@@ -19,6 +19,7 @@
 // element-wise by threads i < n; an objective evaluation is a CTA-cooperative function that returns the same
 // value to every thread.
 #include "apgp_internal.h"
+#include "chol_small.cuh"
 #include <math.h>
 
 namespace apgp {
@@ -41,27 +42,34 @@ __device__ __forceinline__ double cta_sum(double v, double* red /*[OW]*/) {
   return t;
 }
 
+// The objectives are __noinline__ on purpose: the optimisers call them from ~20 places, and inlining every copy
+// made 600 KB of SASS per kernel whose instruction fetches dominated the run time (profiles/r01_optimizers.md).
+// A non-inlined member cannot see that the struct's pointers are shared-memory addresses, so the structs carry
+// OFFSETS (in doubles) from the dynamic shared-memory base and eval() rebuilds typed shared pointers from them.
+
 // ------------------------------------------------------------------------------------------------------
 // Objective 1: acquisition utility at one point (single-query george.GP.predict(return_var=True) + epilogue)
 // ------------------------------------------------------------------------------------------------------
 struct UtilObj {
   int N, d, Npad, ldL;
-  const double* Xs;        // [d][Npad] scaled SoA (shared copy or global)
-  const double* alphaA;    // [Npad]
-  const double* L;         // L^{-1}: packed lower rows in shared memory (packed=1) or row-major global, ld = ldL
-  int packed;
+  int all_smem;            // scaled training set AND packed L^-1 are resident in shared memory
+  int oXs, oL;             // offsets of the shared copies: xs [d+1][Npad] (row d = alphaA), packed L^-1 rows
+  const double* gXs;       // global fallbacks: [d][Npad] scaled SoA, [Npad] alphaA, row-major L^-1 (ld = ldL)
+  const double* gAlpha;
+  const double* gL;
   double amp, mean, ybest, zeta;
   int kind, has_box;
-  const double* lo; const double* hi; const double* qscale;   // shared [d]
-  double* E;               // [N] shared
-  double* red;             // [OW] shared
+  int oLo, oHi, oQs, oE, oRed;   // shared: lo/hi/qscale [d], E [N], red [OW]
 
-  __device__ __forceinline__ const double* lrow(int i) const {
-    return packed ? (L + (size_t)i * (i + 1) / 2) : (L + (size_t)i * ldL);
-  }
-
-  __device__ double eval(const double* x) {
+  template <bool SM>
+  __device__ __forceinline__ double eval_t(int ox) const {
+    extern __shared__ __align__(16) double smem_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double* x = smem_dyn + ox;
+    const double* lo = smem_dyn + oLo; const double* hi = smem_dyn + oHi; const double* qscale = smem_dyn + oQs;
+    double* E = smem_dyn + oE; double* red = smem_dyn + oRed;
+    const double* Xs = SM ? smem_dyn + oXs : gXs;
+    const double* alphaA = SM ? smem_dyn + oXs + (size_t)d * Npad : gAlpha;
     __syncthreads();                                     // x visible; previous evaluation's reads of E done
     bool ok = true;
     for (int i = 0; i < d; ++i) {
@@ -82,7 +90,7 @@ struct UtilObj {
     if (kind == 4) return -mu;                           // findMAP objective: -(GP mean)
     double acc = 0.0;
     for (int i = warp; i < N; i += OW) {
-      const double* Li = lrow(i);
+      const double* Li = SM ? smem_dyn + oL + (size_t)i * (i + 1) / 2 : gL + (size_t)i * ldL;
       double s = 0.0;
       for (int j = lane; j <= i; j += 32) s = fma(Li[j], E[j], s);
 #pragma unroll
@@ -99,6 +107,8 @@ struct UtilObj {
     const double var = amp - tot;
     return utility_eval(kind, mu, var, ybest, zeta);
   }
+
+  __device__ __noinline__ double eval(int ox) const { return all_smem ? eval_t<true>(ox) : eval_t<false>(ox); }
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -108,16 +118,17 @@ struct UtilObj {
 struct NllObj {
   int N, d, P, fit_amp, default_prior;
   double noise;            // exp(white_noise) + TINY^2
-  const double* X;         // [N][d] shared
-  const double* y;         // [N] shared
-  double* K;               // packed lower, shared
-  double* r;               // [N] shared
-  double* col;             // [N] shared
-  double* invM;            // [d] shared
-  double* red;             // [OW] shared
+  int oX, oY, oK, oR, oCol, oInvM, oRed, oBad;   // shared: X [N][d], y [N], packed K, r [N], diag(L) [N], invM [d], red, flag
 
-  __device__ double eval(const double* p) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __device__ __noinline__ double eval(int ox) const {
+    extern __shared__ __align__(16) double smem_dyn[];
+    const int tid = threadIdx.x;
+    const double* p = smem_dyn + ox;
+    const double* X = smem_dyn + oX; const double* y = smem_dyn + oY;
+    double* K = smem_dyn + oK; double* r = smem_dyn + oR; double* col = smem_dyn + oCol;
+    double* invM = smem_dyn + oInvM; double* red = smem_dyn + oRed;
+    int* badflag = reinterpret_cast<int*>(smem_dyn + oBad);
+    PROF_T(t_e0);
     __syncthreads();
     bool fin = true;
     for (int k = 0; k < P; ++k) { const double v = p[k]; fin = fin && (v == v) && (fabs(v) < INFINITY); }
@@ -127,43 +138,53 @@ struct NllObj {
     const double mean = p[0];
     const double amp = fit_amp ? (double)d * exp(p[1]) : 1.0;
     if (tid < d) invM[tid] = exp(-p[1 + fit_amp + tid]);
+    if (tid == 0) *badflag = 0;
     for (int i = tid; i < N; i += OT) r[i] = y[i] - mean;
     __syncthreads();
-    for (int i = warp; i < N; i += OW) {
-      double* Ki = K + (size_t)i * (i + 1) / 2;
-      for (int j = lane; j <= i; j += 32) {
-        double s = 0.0;
-        for (int c = 0; c < d; ++c) { const double df = X[i * d + c] - X[j * d + c]; s = fma(df * df, invM[c], s); }
-        double v = amp * exp(-0.5 * s);
-        if (i == j) v += noise;
-        Ki[j] = v;
+    PROF_ADD(6, t_e0);
+    PROF_T(t_b0);
+    // covariance: the packed triangle is one linear array, so element e = i(i+1)/2 + j goes to thread e mod OT
+    // ((i, j) recovered with a float sqrt + integer fix-up); two elements are in flight per thread so their
+    // exp chains overlap
+    {
+      const int total = N * (N + 1) / 2;
+      for (int e0 = tid; e0 < total; e0 += 2 * OT) {
+        const int e1 = e0 + OT;
+        const bool two = e1 < total;
+        int i0 = (int)((sqrtf(8.0f * (float)e0 + 1.0f) - 1.0f) * 0.5f);
+        if ((i0 + 1) * (i0 + 2) / 2 <= e0) ++i0;
+        if (i0 * (i0 + 1) / 2 > e0) --i0;
+        const int j0 = e0 - i0 * (i0 + 1) / 2;
+        int i1 = (int)((sqrtf(8.0f * (float)e1 + 1.0f) - 1.0f) * 0.5f);
+        if ((i1 + 1) * (i1 + 2) / 2 <= e1) ++i1;
+        if (i1 * (i1 + 1) / 2 > e1) --i1;
+        if (!two) i1 = 0;
+        const int j1 = two ? e1 - i1 * (i1 + 1) / 2 : 0;
+        double s0 = 0.0, s1 = 0.0;
+        for (int c = 0; c < d; ++c) {
+          const double m = invM[c];
+          const double da = X[i0 * d + c] - X[j0 * d + c];
+          const double db = X[i1 * d + c] - X[j1 * d + c];
+          s0 = fma(da * da, m, s0); s1 = fma(db * db, m, s1);
+        }
+        double v0 = amp * exp(-0.5 * s0), v1 = amp * exp(-0.5 * s1);
+        if (i0 == j0) v0 += noise;
+        if (i1 == j1) v1 += noise;
+        K[e0] = v0;
+        if (two) K[e1] = v1;
       }
     }
+    PROF_ADD(7, t_b0);
     __syncthreads();
-    double logdet = 0.0, ssq = 0.0;                      // carried identically by every thread
-    bool bad = false;
-    for (int j = 0; j < N; ++j) {
-      const double dj = K[(size_t)j * (j + 1) / 2 + j];
-      double s;
-      if (dj > 0.0 && dj < INFINITY) s = sqrt(dj);
-      else { s = 1.0; bad = true; }
-      logdet += log(s);
-      const double inv = 1.0 / s;
-      const double zj = r[j] * inv;
-      ssq = fma(zj, zj, ssq);
-      for (int i = j + 1 + tid; i < N; i += OT) {
-        const double l = K[(size_t)i * (i + 1) / 2 + j] * inv;
-        col[i] = l;
-        r[i] = fma(-l, zj, r[i]);
-      }
-      __syncthreads();
-      for (int i = j + 1 + warp; i < N; i += OW) {
-        double* Ki = K + (size_t)i * (i + 1) / 2;
-        const double li = col[i];
-        for (int c = j + 1 + lane; c <= i; c += 32) Ki[c] = fma(-li, col[c], Ki[c]);
-      }
-      __syncthreads();
-    }
+    PROF_ADD(2, t_e0);                                            // prologue + covariance build
+    chol_packed_blocked<OT>(K, r, col, N, badflag, false);      // r <- z = L^{-1}(y - m), col <- diag(L)
+    PROF_T(t_e1);
+    double zpart = 0.0, lpart = 0.0;
+    for (int i = tid; i < N; i += OT) { zpart = fma(r[i], r[i], zpart); lpart += log(col[i]); }
+    const double ssq = cta_sum(zpart, red);
+    const double logdet = cta_sum(lpart, red);
+    const bool bad = (*badflag != 0);
+    PROF_ADD(3, t_e1);                                            // log-det + |z|^2 reductions
     const double ll = -0.5 * ssq - logdet - 0.5 * N * LOG_2PI;
     if (bad || !(ll == ll) || !(fabs(ll) < INFINITY)) return INFINITY;
     return -ll;
@@ -182,6 +203,8 @@ struct OptWork {
   double* v2;      // [n]  NM: trial 2   Powell: current direction
   double* v3;      // [n]  evaluation point
   int* perm;       // [n+1]
+  const double* base;  // dynamic shared-memory base: evaluation points travel as offsets from it
+  __device__ __forceinline__ int off(const double* q) const { return (int)(q - base); }
   static __host__ __device__ size_t doubles(int n) { return (size_t)2 * (n + 1) * n + (n + 1) + 4 * n + (n + 2) / 2 + 1; }
   __device__ void carve(double* base, int n) {
     sim = base; tmp = sim + (size_t)(n + 1) * n; fsim = tmp + (size_t)(n + 1) * n;
@@ -227,7 +250,7 @@ __device__ void nm_sort(OptWork& w, int n) {
   do {                                                    \
     if (ncalls >= o.maxfun) goto iter_end;                \
     ++ncalls;                                             \
-    dst = f.eval(xptr);                                   \
+    dst = f.eval(w.off(xptr));                                   \
   } while (0)
 
 // scipy.optimize._optimize._minimize_neldermead; x0 in w.sim[0..n); result: w.sim[0..n), return f
@@ -247,7 +270,7 @@ __device__ double nelder_mead_dev(Obj& f, int n, const OptOpts& o, OptWork& w, l
   for (int k = 0; k <= n; ++k) {
     if (ncalls >= o.maxfun) break;
     ++ncalls;
-    const double v = f.eval(w.sim + k * n);
+    const double v = f.eval(w.off(w.sim + k * n));
     if (tid == 0) w.fsim[k] = v;
   }
   nm_sort(w, n);
@@ -335,7 +358,7 @@ __device__ __forceinline__ bool line_ev(Obj& f, int n, OptWork& w, PCtx& c, doub
   ++c.ncalls;
   __syncthreads();
   if (threadIdx.x < n) w.v3[threadIdx.x] = w.v0[threadIdx.x] + alpha * w.v2[threadIdx.x];
-  out = f.eval(w.v3);
+  out = f.eval(w.off(w.v3));
   return true;
 }
 
@@ -483,7 +506,7 @@ __device__ double powell_dev(Obj& f, int n, const OptOpts& o, OptWork& w, long l
   long long it = 0;
   if (c.ncalls >= c.maxfun) { nfev = 0; nit = 0; return fval; }
   ++c.ncalls;
-  fval = f.eval(w.v0);
+  fval = f.eval(w.off(w.v0));
   while (true) {
     const double fx = fval;
     int bigind = 0;
@@ -513,7 +536,7 @@ __device__ double powell_dev(Obj& f, int n, const OptOpts& o, OptWork& w, long l
     }
     if (c.ncalls >= c.maxfun) break;
     ++c.ncalls;
-    const double fx2 = f.eval(w.v3);
+    const double fx2 = f.eval(w.off(w.v3));
     if (fx > fx2) {
       double t = 2.0 * (fx + fx2 - 2.0 * fval);
       double temp = (fx - fval - delta);
@@ -544,7 +567,7 @@ __device__ double powell_dev(Obj& f, int n, const OptOpts& o, OptWork& w, long l
 // host restatement of the optimisers can then be driven by exactly the function the device minimises).
 // ------------------------------------------------------------------------------------------------------
 struct UtilKernelParams {
-  int N, d, Npad, ldL, packed, xs_in_smem;
+  int N, d, Npad, ldL, all_smem;
   const double* Xs; const double* alphaA; const double* Linv;
   double amp, mean, ybest, zeta;
   int kind, has_box;
@@ -552,50 +575,55 @@ struct UtilKernelParams {
   const double* x0;        // [R][d]
   double* x_out;           // [R][d]
   double* f_out;           // [R]
-  long long* stats;        // [R][2] nfev, nit
+  long long* stats;        // [R][3] nfev, nit, SM cycles
   int mode;                // 0 evaluate, 1 minimise
   OptOpts opt;
 };
 
-__global__ void __launch_bounds__(OT) minimize_utility_kernel(const __grid_constant__ UtilKernelParams p) {
+__global__ void __launch_bounds__(OT, 1) minimize_utility_kernel(const __grid_constant__ UtilKernelParams p) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, n = p.d;
   double* cur = sm;
   double* lo = cur; cur += n; double* hi = cur; cur += n; double* qs = cur; cur += n;
   double* E = cur; cur += p.N;
   double* red = cur; cur += OW;
-  OptWork w; w.carve(cur, n); cur += OptWork::doubles(n);
-  const double* Xs = p.Xs; const double* al = p.alphaA; const double* L = p.Linv;
-  if (p.xs_in_smem) {
+  OptWork w; w.carve(cur, n); w.base = sm; cur += OptWork::doubles(n);
+  UtilObj f;
+  f.N = p.N; f.d = n; f.Npad = p.Npad; f.ldL = p.ldL; f.all_smem = p.all_smem;
+  f.gXs = p.Xs; f.gAlpha = p.alphaA; f.gL = p.Linv;
+  f.amp = p.amp; f.mean = p.mean; f.ybest = p.ybest; f.zeta = p.zeta; f.kind = p.kind; f.has_box = p.has_box;
+  f.oLo = (int)(lo - sm); f.oHi = (int)(hi - sm); f.oQs = (int)(qs - sm); f.oE = (int)(E - sm); f.oRed = (int)(red - sm);
+  f.oXs = 0; f.oL = 0;
+  if (p.all_smem) {                                      // resident copies: scaled training set (+ alpha row), packed L^-1
     double* xs = cur; cur += (size_t)(n + 1) * p.Npad;
     for (int e = tid; e < n * p.Npad; e += OT) xs[e] = p.Xs[e];
     for (int e = tid; e < p.Npad; e += OT) xs[(size_t)n * p.Npad + e] = p.alphaA[e];
-    Xs = xs; al = xs + (size_t)n * p.Npad;
-  }
-  if (p.packed) {
-    double* lp = cur;
-    for (int i = tid >> 5; i < p.N; i += OW) {
-      const double* src = p.Linv + (size_t)i * p.ldL;
-      double* dst = lp + (size_t)i * (i + 1) / 2;
-      for (int j = tid & 31; j <= i; j += 32) dst[j] = src[j];
+    f.oXs = (int)(xs - sm);
+    if (p.kind != 4) {
+      double* lp = cur;
+      for (int i = tid >> 5; i < p.N; i += OW) {
+        const double* src = p.Linv + (size_t)i * p.ldL;
+        double* dst = lp + (size_t)i * (i + 1) / 2;
+        for (int j = tid & 31; j <= i; j += 32) dst[j] = src[j];
+      }
+      f.oL = (int)(lp - sm);
     }
-    L = lp;
   }
   if (tid < n) { lo[tid] = p.lo[tid]; hi[tid] = p.hi[tid]; qs[tid] = p.qscale[tid]; }
-  UtilObj f{p.N, n, p.Npad, p.ldL, Xs, al, L, p.packed, p.amp, p.mean, p.ybest, p.zeta, p.kind, p.has_box, lo, hi, qs, E, red};
   const double* x0 = p.x0 + (size_t)blockIdx.x * n;
   double* start = (p.opt.method == 1 && p.mode == 1) ? w.v0 : w.sim;
   if (tid < n) start[tid] = x0[tid];
   __syncthreads();
   double fbest; long long nfev = 1, nit = 0;
-  if (p.mode == 0) fbest = f.eval(start);
+  const long long t_start = clock64();
+  if (p.mode == 0) fbest = f.eval(w.off(start));
   else if (p.opt.method == 0) fbest = nelder_mead_dev(f, n, p.opt, w, nfev, nit);
   else fbest = powell_dev(f, n, p.opt, w, nfev, nit);
   __syncthreads();
   if (tid < n) p.x_out[(size_t)blockIdx.x * n + tid] = start[tid];
   if (tid == 0) {
     p.f_out[blockIdx.x] = fbest;
-    if (p.stats) { p.stats[2 * blockIdx.x] = nfev; p.stats[2 * blockIdx.x + 1] = nit; }
+    if (p.stats) { p.stats[3 * blockIdx.x] = nfev; p.stats[3 * blockIdx.x + 1] = nit; p.stats[3 * blockIdx.x + 2] = clock64() - t_start; }
   }
 }
 
@@ -606,12 +634,12 @@ struct NllKernelParams {
   const double* p0;        // [R][P]
   double* p_out;           // [R][P]
   double* f_out;           // [R]
-  long long* stats;        // [R][2]
+  long long* stats;        // [R][3]
   int mode;
   OptOpts opt;
 };
 
-__global__ void __launch_bounds__(OT) minimize_nll_kernel(const __grid_constant__ NllKernelParams p) {
+__global__ void __launch_bounds__(OT, 1) minimize_nll_kernel(const __grid_constant__ NllKernelParams p) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, n = p.P;
   double* cur = sm;
@@ -622,23 +650,26 @@ __global__ void __launch_bounds__(OT) minimize_nll_kernel(const __grid_constant_
   double* col = cur; cur += p.N;
   double* invM = cur; cur += p.d;
   double* red = cur; cur += OW;
-  OptWork w; w.carve(cur, n);
+  int* badflag = reinterpret_cast<int*>(cur); cur += 1;
+  OptWork w; w.carve(cur, n); w.base = sm;
   for (int e = tid; e < p.N * p.d; e += OT) X[e] = p.X[e];
   for (int e = tid; e < p.N; e += OT) y[e] = p.y[e];
-  NllObj f{p.N, p.d, p.P, p.fit_amp, p.default_prior, p.noise, X, y, K, r, col, invM, red};
+  NllObj f{p.N, p.d, p.P, p.fit_amp, p.default_prior, p.noise, (int)(X - sm), (int)(y - sm), (int)(K - sm), (int)(r - sm),
+           (int)(col - sm), (int)(invM - sm), (int)(red - sm), (int)(reinterpret_cast<double*>(badflag) - sm)};
   const double* x0 = p.p0 + (size_t)blockIdx.x * n;
   double* start = (p.opt.method == 1 && p.mode == 1) ? w.v0 : w.sim;
   if (tid < n) start[tid] = x0[tid];
   __syncthreads();
   double fbest; long long nfev = 1, nit = 0;
-  if (p.mode == 0) fbest = f.eval(start);
+  const long long t_start = clock64();
+  if (p.mode == 0) fbest = f.eval(w.off(start));
   else if (p.opt.method == 0) fbest = nelder_mead_dev(f, n, p.opt, w, nfev, nit);
   else fbest = powell_dev(f, n, p.opt, w, nfev, nit);
   __syncthreads();
   if (tid < n) p.p_out[(size_t)blockIdx.x * n + tid] = start[tid];
   if (tid == 0) {
     p.f_out[blockIdx.x] = fbest;
-    if (p.stats) { p.stats[2 * blockIdx.x] = nfev; p.stats[2 * blockIdx.x + 1] = nit; }
+    if (p.stats) { p.stats[3 * blockIdx.x] = nfev; p.stats[3 * blockIdx.x + 1] = nit; p.stats[3 * blockIdx.x + 2] = clock64() - t_start; }
   }
 }
 
@@ -672,9 +703,20 @@ void fill_opt(OptOpts& o, const OptimizeParams& q, int n) {
 }  // namespace
 
 size_t minimize_nll_smem(int N, int d, int P) {
-  return ((size_t)N * (N + 1) / 2 + (size_t)N * (d + 3) + d + OW + OptWork::doubles(P)) * sizeof(double);
+  return ((size_t)N * (N + 1) / 2 + (size_t)N * (d + 3) + d + OW + 1 + OptWork::doubles(P)) * sizeof(double);
 }
-bool minimize_nll_fits(int N, int d, int P) { return minimize_nll_smem(N, d, P) <= SMEM_CAP && P + 1 <= OT; }
+bool minimize_nll_fits(int N, int d, int P) { return minimize_nll_smem(N, d, P) <= SMEM_CAP && P + 1 <= OT && N < OT; }
+
+#ifdef APGP_PROF
+int read_prof(long long* out16) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_prof, sizeof(long long) * 16);
+  long long z[16] = {};
+  cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+  return (int)e;
+}
+#else
+int read_prof(long long* out16) { for (int i = 0; i < 16; ++i) out16[i] = 0; return 0; }
+#endif
 
 int launch_minimize_utility(const UtilityPointParams& u, const OptimizeParams& q, int R, const double* x0_dev,
                             double* x_out_dev, double* f_out_dev, long long* stats_dev, int mode, cudaStream_t st) {
@@ -686,14 +728,13 @@ int launch_minimize_utility(const UtilityPointParams& u, const OptimizeParams& q
   for (int i = 0; i < u.d; ++i) { p.lo[i] = u.lo[i]; p.hi[i] = u.hi[i]; p.qscale[i] = u.qscale[i]; }
   p.x0 = x0_dev; p.x_out = x_out_dev; p.f_out = f_out_dev; p.stats = stats_dev; p.mode = mode;
   fill_opt(p.opt, q, u.d);
-  // shared-memory plan: fixed part, then the scaled training set, then the packed L^-1, as far as they fit
+  // shared-memory plan: fixed part, then -- if both fit -- the scaled training set and the packed L^-1
   size_t base = ((size_t)3 * u.d + u.N + OW + OptWork::doubles(u.d)) * 8;
   const size_t xs_b = (size_t)(u.d + 1) * u.Npad * 8;
   const size_t lp_b = (size_t)u.N * (u.N + 1) / 2 * 8;
-  p.xs_in_smem = (base + xs_b <= SMEM_CAP) ? 1 : 0;
-  if (p.xs_in_smem) base += xs_b;
-  p.packed = (u.kind != 4 && base + lp_b <= SMEM_CAP) ? 1 : 0;
-  if (p.packed) base += lp_b;
+  const size_t resident = xs_b + (u.kind != 4 ? lp_b : 0);
+  p.all_smem = (base + resident <= SMEM_CAP) ? 1 : 0;     // else the objective streams both from global (L2)
+  if (p.all_smem) base += resident;
   minimize_utility_kernel<<<R, OT, base, st>>>(p);
   return (int)cudaGetLastError();
 }

@@ -362,11 +362,12 @@ class GP(object):
             obj.has_box = 1
             _lib.fill_bounds(obj.lo, obj.hi, bounds, self.ndim)
         o = self._opt_opts(method, options)
-        x, f, nfev = np.empty_like(x0), np.empty(R), np.zeros(R, dtype=np.int64)
+        x, f, stats = np.empty_like(x0), np.empty(R), np.zeros((R, 3), dtype=np.int64)
         _lib.check(self._lib.apgp_minimize_utility(self._h, C.byref(obj), C.byref(o), _lib.ptr(x0), R, _lib.ptr(x),
-                                                   _lib.ptr(f), _lib.ptr(nfev), 1 if evaluate_only else 0),
+                                                   _lib.ptr(f), _lib.ptr(stats), 1 if evaluate_only else 0),
                    "apgp_minimize_utility")
-        return x, f, nfev
+        self.last_opt_stats = stats          # per start: evaluations, iterations, SM clock cycles
+        return x, f, stats[:, 0].copy()
 
     def can_minimize_nll(self):
         """True when the training set fits the one-restart-per-CTA shared-memory optimiser (N <= ~220)."""
@@ -391,12 +392,13 @@ class GP(object):
             self._upload_training()
         R = P0.shape[0]
         o = self._opt_opts(method, options)
-        p, f, nfev = np.empty_like(P0), np.empty(R), np.zeros(R, dtype=np.int64)
+        p, f, stats = np.empty_like(P0), np.empty(R), np.zeros((R, 3), dtype=np.int64)
         _lib.check(self._lib.apgp_minimize_nll(self._h, C.byref(o), _lib.ptr(P0), R, P0.shape[1],
                                                1 if self.kernel.fit_amp else 0, self.white_noise,
-                                               1 if default_prior else 0, _lib.ptr(p), _lib.ptr(f), _lib.ptr(nfev),
+                                               1 if default_prior else 0, _lib.ptr(p), _lib.ptr(f), _lib.ptr(stats),
                                                1 if evaluate_only else 0), "apgp_minimize_nll")
-        return p, f, nfev
+        self.last_opt_stats = stats
+        return p, f, stats[:, 0].copy()
 
     # ------------------------------------------------------------------ sampler
     def run_ensembles(self, y, p0, nsteps, bounds, nens=1, a=2.0, seed=0, thin=1, lnprior_const=0.0, replay=None):

@@ -145,10 +145,11 @@ typedef struct apgp_opt_opts {
  * for R starts at once on the current factorisation.  fn = obj->utility in {AGP, BAPE, JONES} evaluated as
  * utility.py:99-250 does (single-query predict with variance + epilogue; +inf outside obj's box when has_box,
  * the priorFn gate), or NEGMEAN = -(GP mean) with the same gate (findMAP, approx.py:909-914).
- * x0, x_out [R][d], f_out [R] = fn(x_out[r]), nfev [R] or NULL; all host buffers.  evaluate_only=1 returns
+ * x0, x_out [R][d], f_out [R] = fn(x_out[r]); stats [R][3] or NULL = (function evaluations, optimiser iterations,
+ * SM clock cycles spent by that start's CTA); all host buffers.  evaluate_only=1 returns
  * fn(x0[r]) without optimising (x_out = x0): the exact function the optimiser minimises, for tests. */
 int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const apgp_opt_opts* opt, const double* x0,
-                          int R, double* x_out, double* f_out, long long* nfev, int evaluate_only);
+                          int R, double* x_out, double* f_out, long long* stats, int evaluate_only);
 
 /* gpUtils.optimizeGP's inner loop (gpUtils.py:223-247): scipy.optimize.minimize(_nll, p0[r], method=...)["x"] for
  * R restarts at once; _nll as gpUtils.py:46-80 (+inf when default_prior and any |p[1:]| > 20 -- gpUtils.py:22-43 --,
@@ -157,7 +158,7 @@ int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const ap
  * (apgp_minimize_nll_fits() == 1, N <= ~220); otherwise drive apgp_loglik_batch from a host optimiser.
  * Does not disturb the handle's current factorisation. */
 int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0, int R, int P, int fit_amp,
-                      double white_noise, int default_prior, double* p_out, double* f_out, long long* nfev,
+                      double white_noise, int default_prior, double* p_out, double* f_out, long long* stats,
                       int evaluate_only);
 int apgp_minimize_nll_fits(const apgp_handle* h, int P);
 
@@ -167,6 +168,8 @@ int apgp_get_linv(apgp_handle* h, double* linv);
 int apgp_get_chol(apgp_handle* h, double* L);
 /* exp(-s), s >= 0, as evaluated inside the fused predict kernel (table + degree-5 polynomial); host buffers */
 int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out);
+/* profiling builds (-DAPGP_PROF): read and reset 16 per-phase SM-cycle counters of the log-likelihood objective */
+int apgp_debug_read_prof(long long* out16);
 /* select the variance-kernel tiling (queries x L^-1 rows per CTA tile): 0 = 64x256, 1 = 128x128,
  * 2 = 256x64 (default).  Call before factorize. */
 int apgp_set_variant(apgp_handle* h, int variant);
