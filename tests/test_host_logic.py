@@ -344,3 +344,59 @@ def test_generator_lockstep_batches_restarts():
     assert max(sizes) == len(x0s) and rounds == len(sizes) and evals == sum(sizes) and rounds < evals
     for (x, fx) in out:
         assert np.allclose(x, 1.5, atol=1e-3) and fx < 1e-6
+
+
+# ---------------------------------------------------------------- device-optimiser host protocol (no GPU: fake GP)
+class _FakeDeviceGP(object):
+    """Stands in for approxposterior_b200.GP on the CPU: ``minimize_utility`` / ``minimize_nll`` run the host
+    restatements of SciPy's algorithms on an analytic objective, recording how they were called."""
+    computed = True
+
+    def __init__(self, fail_first=0):
+        self.calls = []
+        self.fail_first = fail_first
+
+    def minimize_utility(self, y, x0, utility, bounds=None, method="nelder-mead", options=None, zeta=0.01,
+                         evaluate_only=False):
+        from approxposterior_b200 import _optimizers as opt
+        x0 = np.atleast_2d(x0)
+        self.calls.append(dict(kind=utility, R=len(x0), bounds=bounds, method=method, options=options))
+        fn = lambda P: [float(np.sum((np.asarray(p) - 1.0) ** 2)) for p in P]
+        out, _, evals = opt.run_generators([opt.nelder_mead_gen(t, **(options or {})) for t in x0], fn)
+        xs = np.array([o[0] for o in out]); fs = np.array([o[1] for o in out])
+        if len(self.calls) <= self.fail_first:
+            xs[0] = np.nan                                   # a restart that must be redrawn and re-run
+        return xs, fs, np.full(len(x0), evals // len(x0))
+
+
+def test_minimize_objective_device_engine_protocol():
+    from approxposterior_b200 import utility as ut, likelihood as lh
+    prior = lh.BoxPrior([(-5, 5), (-5, 5)])
+    gp = _FakeDeviceGP(fail_first=1)
+    np.random.seed(11)
+    y = np.zeros(4)
+    x, f = ut.minimizeObjective(ut.BAPEUtility, y, gp, sampleFn=prior.sample, priorFn=prior, nRestarts=4,
+                                args=(y, gp, prior))
+    assert np.allclose(x, [1.0, 1.0], atol=1e-3) and f < 1e-6
+    assert ut.minimizeObjective.last_stats["scheduler"] == "device"
+    # first launch carried all 4 restarts with the reference's default options; the failed one was redrawn alone
+    assert [c["R"] for c in gp.calls] == [4, 1]
+    assert gp.calls[0]["kind"] == "bape" and gp.calls[0]["options"] == {"adaptive": True}
+    assert gp.calls[0]["bounds"] == prior.bounds
+    # a Python prior without .bounds, or engine="lockstep", never takes the device path
+    gp2 = _FakeDeviceGP()
+    with pytest.raises(AttributeError):                      # falls through to the lock-step path -> predict_utility
+        ut.minimizeObjective(ut.BAPEUtility, y, gp2, sampleFn=prior.sample, priorFn=prior, nRestarts=2,
+                             args=(y, gp2, prior), engine="lockstep")
+    assert gp2.calls == []
+
+
+def test_device_optimizer_option_mapping():
+    from approxposterior_b200 import _lib
+    from approxposterior_b200.gp import GP
+    o = GP._opt_opts("nelder-mead", {"adaptive": True, "xatol": 1e-6, "maxfev": 77})
+    assert (o.method, o.adaptive, o.xtol, o.ftol, o.maxiter, o.maxfev) == (0, 1, 1e-6, 1e-4, -1, 77)
+    o = GP._opt_opts("Powell", {"ftol": 1e-8, "maxiter": np.inf})
+    assert (o.method, o.adaptive, o.xtol, o.ftol, o.maxiter, o.maxfev) == (1, 0, 1e-4, 1e-8, _lib.OPT_INF, -1)
+    with pytest.raises(KeyError):
+        GP._opt_opts("l-bfgs-b", None)
