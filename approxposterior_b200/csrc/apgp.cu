@@ -52,6 +52,7 @@ struct apgp_handle {
   int N = 0, d = 0, Np = 0, Npad = 0;
   int variant = 2;       // requested tiling: 2 = 256x64 (fastest measured, profiles/), 1 = 128x128, 0 = 64x256
   int variant_eff = 2;   // tiling the current factorisation was packed for
+  int group = -1;        // CTAs per query tile in the variance kernel: 0 = one tile per CTA, -1 = automatic, G = fixed
   bool has_training = false, has_hyper = false, factored = false;
   double mean = 0, amp = 1, white_noise = -12;
   double log_metric[APGP_MAX_DIM];
@@ -65,6 +66,8 @@ struct apgp_handle {
   DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
   DevBuf o_in, o_x, o_f, o_stats;      // device optimiser staging
+  DevBuf g_arrive, g_part, g_plan;     // grouped variance kernel: barrier counters, partial sums, work-split tables
+  int plan_Npad = -1, plan_G = -1, plan_d = -1;   // what g_plan currently holds
 };
 
 namespace {
@@ -109,6 +112,8 @@ int apgp_create(apgp_handle** out, int device) {
   CU(cudaHostAlloc((void**)&h->pin, apgp_handle::PIN_DOUBLES * 8, cudaHostAllocDefault));
   const char* v = getenv("APGP_PREDICT_VARIANT");
   if (v) { int vv = atoi(v); h->variant = (vv >= 0 && vv <= 2) ? vv : 2; }
+  const char* gv = getenv("APGP_PREDICT_GROUP");
+  if (gv) h->group = atoi(gv);
   *out = h;
   return APGP_OK;
 }
@@ -120,7 +125,7 @@ int apgp_destroy(apgp_handle* h) {
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
                     &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->ap_k, &h->ap_l, &h->ap_u, &h->ap_x, &h->bK,
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
-                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats};
+                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan};
   for (DevBuf* b : bufs) b->release();
   if (h->pin) cudaFreeHost(h->pin);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -148,6 +153,12 @@ int apgp_synchronize(apgp_handle* h) {
 }
 
 long long apgp_launch_count(const apgp_handle* h) { return h ? h->launches : 0; }
+
+int apgp_set_group(apgp_handle* h, int group) {
+  if (!h || group < -1 || group > 64) return fail(APGP_ERR_ARG, "apgp_set_group");
+  h->group = group;
+  return APGP_OK;
+}
 
 int apgp_set_variant(apgp_handle* h, int variant) {
   if (!h || variant < 0 || variant > 2) return fail(APGP_ERR_ARG, "apgp_set_variant");
@@ -338,10 +349,38 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
   }
   int nl = 0;
   if (o->want_var) {
-    const size_t sb = predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff);
-    CUI(h->scratch.reserve(sb));
-    p.scratch = h->scratch.as<double>();
-    CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant_eff, &nl));
+    const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d);
+    if (G > 1) {
+      CUI(h->scratch.reserve(predict_group_scratch_bytes(h->Npad, h->num_sms, G)));
+      CUI(h->g_arrive.reserve(sizeof(int) * ((h->num_sms + G - 1) / G)));
+      CUI(h->g_part.reserve(predict_group_part_bytes(h->Npad, h->num_sms, G)));
+      CUI(h->g_plan.reserve(4 * 128 * sizeof(int)));
+      p.scratch = h->scratch.as<double>();
+      p.grp_arrive = h->g_arrive.as<int>(); p.grp_part = h->g_part.as<double>(); p.grp_plan = h->g_plan.as<int>();
+      if (h->plan_Npad != h->Npad || h->plan_G != G || h->plan_d != d) {      // re-plan only when the shape changes
+        int tab[4 * 128];
+        predict_group_plan(h->Npad, h->num_sms, G, d, tab);
+        CU(cudaMemcpyAsync(h->g_plan.p, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->plan_Npad = h->Npad; h->plan_G = G; h->plan_d = d;
+      }
+      const int ge = launch_predict_var_grouped(p, h->num_sms, G, h->stream, &nl);
+      if (ge == (int)cudaErrorCooperativeLaunchTooLarge) {
+        // the GPU is shared (fewer SMs free than the grid needs for its spin barriers): one tile per CTA instead
+        (void)cudaGetLastError();
+        --nl;
+        CUI(h->scratch.reserve(predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff)));
+        p.scratch = h->scratch.as<double>();
+        CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant_eff, &nl));
+      } else {
+        CUI(ge);
+      }
+    } else {
+      const size_t sb = predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff);
+      CUI(h->scratch.reserve(sb));
+      p.scratch = h->scratch.as<double>();
+      CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant_eff, &nl));
+    }
   } else {
     CUI(launch_predict_mean(p, h->num_sms, h->stream, &nl));
   }

@@ -28,6 +28,9 @@ struct PredictParams {
   double* util;            // [Q] out (may be null)
   int utility_kind;        // 0 none, 1 AGP, 2 BAPE, 3 Jones
   double ybest, zeta;
+  int* grp_arrive;         // grouped kernel: [ngroups] arrival counters (zeroed per launch)
+  double* grp_part;        // grouped kernel: [ngroups][2 (mu, ss)][2 buffers][Npad/64][256] per-block partial sums
+  int* grp_plan;           // grouped kernel: work-split tables (plan_group_split), 4 x 128 ints
 };
 
 int predict_variant_bn(int variant);   // block-row height BN of the LinvF tiling used by a kernel variant
@@ -37,6 +40,13 @@ int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int
 int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st);
 int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, int* launches);
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant);
+// grouped 256x64 kernel: G CTAs share one query tile so the K* panels in flight stay in L2 (predict.cu).
+// requested < 0: automatic choice; returns 1 when grouping is off / not applicable
+int predict_group_size(int Npad, int num_sms, int variant, int requested, int d);
+void predict_group_plan(int Npad, int num_sms, int G, int d, int* tab /*[4*128]*/);
+size_t predict_group_scratch_bytes(int Npad, int num_sms, int G);
+size_t predict_group_part_bytes(int Npad, int num_sms, int G);
+int launch_predict_var_grouped(const PredictParams& p, int num_sms, int G, cudaStream_t st, int* launches);
 int launch_pack_linv(const double* Linv, int ld, int N, int Npad, int BN, double amp, double* LinvF, cudaStream_t st);
 int launch_pack_xs(const double* X, int N, int d, int Npad, const double* qscale_dev, double* Xs, cudaStream_t st);
 

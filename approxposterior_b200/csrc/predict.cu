@@ -24,6 +24,8 @@
 // FP64 pipe on B200 (profiles/r01_fp64_pipe_probe.txt), so recomputing K* per output block
 // would come straight out of the GEMM's budget.
 #include "apgp_internal.h"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace apgp {
 
@@ -270,6 +272,295 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grouped variant of predict_var_kernel (256x64 tiling): G CTAs share ONE query tile so that the K* panels
+// in flight fit in L2 instead of streaming through HBM.
+//
+// With one tile per CTA the 148 panels in flight are 148 x 256 x Npad x 8 B (620 MB at N = 2048): every one of
+// the N/(2 BN) re-reads of a panel misses the 126 MB L2 (294 GB of DRAM traffic per 2^20 queries, ncu).  Here
+// the CTAs of a group (G consecutive blockIdx) split the tile's work instead:
+//   phase 1  rank r builds the panel columns of ITS share of the 64-column blocks (and the partial mean);
+//   barrier  one group barrier per tile (arrival counter in global memory, acquire spin, co-resident grid);
+//   phase 2  rank r runs the triangular DMMA GEMM for ITS block-rows of L^-1 (longest-first balanced so that
+//            every rank streams the same number of k-steps), reading the whole panel through TMA from L2;
+//   epilogue the per-rank partial row sums / means meet in a small global buffer; the tile is finalised (var,
+//            prior gate, utility) by the ranks, one slice of the queries each, after the NEXT tile's barrier,
+//            so a single barrier per tile orders everything.  Panels and partials are double-buffered.
+// Panels in flight: 2 x (grid/G) x 256 x Npad x 8 B (74 MB at N = 2048, G = 16).  Results are bit-identical to
+// the ungrouped kernel for the mean (same summation order within a column block; blocks are then added in rank
+// order) up to the order of the block partial sums, and within 1e-13 relative for the variance.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int GROUP_MAX_BLOCKS = 128;       // Npad <= 8192 at BN = 64
+
+template <int BM, int BN, int NSTAGE>
+__global__ void __launch_bounds__(8 * 32 + 32, 1)
+predict_var_group_kernel(const __grid_constant__ PredictParams p, const int G) {
+  using C = VarCfg<BM, BN, NSTAGE, 8>;
+  constexpr int NCW = 8, NCONS = C::NCONS;
+  static_assert(C::WARPS_N == 1, "grouped kernel is written for the 256x64 tiling");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  double* qs = ring + C::RING;                          // [d][BM] scaled queries
+  double* mu_s = qs + (size_t)p.d * BM;                 // [BM] partial mean of my column blocks
+  double* ss_s = mu_s + BM;                             // [BM] partial row sums of my block-rows
+  double* etab = ss_s + BM;                             // [64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(etab + 64);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* stagebar = empty + NSTAGE;
+  __shared__ int owner_s[GROUP_MAX_BLOCKS];             // block-row of L^-1 (phase 2) -> rank
+  __shared__ int myblk_s[GROUP_MAX_BLOCKS];             // the 64-column blocks of the panel this rank builds (phase 1)
+  __shared__ int nmine_s;
+  __shared__ double mu_keep[2][BM];                     // my slice's complete means, per buffer
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = p.d, Npad = p.Npad, nblk = Npad / BN;
+  const int grp = blockIdx.x / G, rank = blockIdx.x % G;
+  const int gs = min(G, (int)gridDim.x - grp * G);      // ranks in my group
+  const long long ntiles = (p.Q + BM - 1) / BM;
+  // contiguous share of the tiles, proportional to the group's size
+  const long long t_begin = ntiles * (long long)(grp * G) / gridDim.x;
+  const long long t_end = ntiles * (long long)(grp * G + gs) / gridDim.x;
+  const int sl0 = BM * rank / gs, sl1 = BM * (rank + 1) / gs;                                            // my query slice
+  int* arrive = p.grp_arrive + grp;
+  // partial sums are kept per 64-column block (mean) and per block-row (variance) and added in block order by the
+  // finaliser, so a query's result does not depend on which rank -- or how large a group -- computed the pieces
+  double* part_mu = p.grp_part + (size_t)grp * 4 * nblk * BM;       // [2 buffers][nblk][BM]
+  double* part_ss = part_mu + (size_t)2 * nblk * BM;                // [2 buffers][nblk][BM]
+
+  if (tid < 64) etab[tid] = exp2((double)tid * (1.0 / 64.0));
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+    mbar_init(stagebar, 1);
+    mbar_fence_init();
+  }
+  {   // work split planned on the host (plan_group_split): full groups use table 0, a smaller last group table 1
+    const int* tab = p.grp_plan + (gs == G ? 0 : 2 * GROUP_MAX_BLOCKS);
+    for (int e = tid; e < nblk; e += blockDim.x) owner_s[e] = tab[e];
+    if (tid == 0) {
+      int n = 0;
+      for (int e = 0; e < nblk; ++e) if (tab[GROUP_MAX_BLOCKS + e] == rank) myblk_s[n++] = e;
+      nmine_s = n;
+    }
+  }
+  __syncthreads();
+  const int nmine = nmine_s;
+
+  uint32_t it = 0, nstaged = 0;
+  int nbar = 0;                                          // group barriers passed so far
+
+  for (long long tile = t_begin; tile <= t_end; ++tile) {
+    const int b = (int)((tile - t_begin) & 1);
+    const long long q0 = tile * BM;
+    const bool live = tile < t_end;                      // the extra trip only finalises the last tile
+    double* panel = p.scratch + ((size_t)grp * 2 + b) * BM * Npad;
+
+    // ------------------------------------------------------------ phase 1: my column blocks of the panel
+    if (live && warp < NCW) {
+      for (int e = tid; e < d * BM; e += NCONS) {
+        int i = e / BM, m = e - i * BM;
+        long long q = q0 + m;
+        qs[e] = (q < p.Q) ? p.Xq[q * d + i] * p.qscale[i] : 0.0;
+      }
+      // my 64-column blocks, up to CAPB per staging round (each block: d+1 bulk copies into consecutive ring slots)
+      const int CAPB = min(8, (C::RING / (d + 1)) / BN);
+      const int JCHT = CAPB * BN;                        // ring row stride
+      constexpr int R = BM / (8 * NCW);
+      for (int s0 = 0; s0 < nmine; s0 += CAPB) {
+        const int ns = min(CAPB, nmine - s0);
+        named_bar_sync(1, NCONS);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(stagebar, (uint32_t)((d + 1) * ns * BN * 8));
+          for (int sl = 0; sl < ns; ++sl) {
+            const int j0 = myblk_s[s0 + sl] * BN;
+            for (int i = 0; i < d; ++i) bulk_g2s(ring + i * JCHT + sl * BN, p.Xs + (size_t)i * Npad + j0, BN * 8, stagebar);
+            bulk_g2s(ring + d * JCHT + sl * BN, p.alphaA + j0, BN * 8, stagebar);
+          }
+        }
+        mbar_wait(stagebar, nstaged & 1u);
+        ++nstaged;
+        for (int sl = 0; sl < ns; ++sl) {
+          const int cb = myblk_s[s0 + sl];
+          const int j0 = cb * BN;
+          const double* al = ring + d * JCHT + sl * BN;
+          double macc[R] = {};
+          for (int jb = 0; jb < BN; jb += 16) {
+            const int jj = jb + (lane & 3);
+            double s[R][4] = {};
+            for (int i = 0; i < d; ++i) {
+              const double* xr = ring + i * JCHT + sl * BN + jj;
+              const double x0 = xr[0], x1 = xr[4], x2 = xr[8], x3 = xr[12];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const double qv = qs[i * BM + (warp + r * NCW) * 8 + (lane >> 2)];
+                const double d0 = x0 - qv, d1 = x1 - qv, d2 = x2 - qv, d3 = x3 - qv;
+                s[r][0] = fma(d0, d0, s[r][0]); s[r][1] = fma(d1, d1, s[r][1]);
+                s[r][2] = fma(d2, d2, s[r][2]); s[r][3] = fma(d3, d3, s[r][3]);
+              }
+            }
+            const double a0 = al[jj], a1 = al[jj + 4], a2 = al[jj + 8], a3 = al[jj + 12];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const int mb = warp + r * NCW;
+              const double e0 = exp_neg(s[r][0], etab), e1 = exp_neg(s[r][1], etab);
+              const double e2 = exp_neg(s[r][2], etab), e3 = exp_neg(s[r][3], etab);
+              macc[r] = fma(e0, a0, macc[r]); macc[r] = fma(e1, a1, macc[r]);
+              macc[r] = fma(e2, a2, macc[r]); macc[r] = fma(e3, a3, macc[r]);
+              double* dst = panel + ((size_t)((j0 + jb) >> 2) * (BM / 8) + mb) * 32 + lane;
+              dst[0] = e0; dst[(BM / 8) * 32] = e1; dst[2 * (BM / 8) * 32] = e2; dst[3 * (BM / 8) * 32] = e3;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {                  // this block's contribution to the means
+            double v = macc[r];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if ((lane & 3) == 0) part_mu[((size_t)b * nblk + cb) * BM + (warp + r * NCW) * 8 + (lane >> 2)] = v;
+          }
+        }
+      }
+      __threadfence();                                   // panel + partial means visible GPU-wide before we arrive
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ group barrier (one per tile)
+    if (tid == 0) {
+      ++nbar;
+      __threadfence();                                   // cumulative: everything this CTA wrote before the bar.sync
+      atomicAdd(arrive, 1);
+      const int target = nbar * gs;
+      while (ld_acquire_gpu(arrive) < target) __nanosleep(40);
+      __threadfence();
+    }
+    __syncthreads();
+    fence_proxy_async();                                 // other CTAs' panel stores (generic proxy) -> our TMA reads
+
+    // ------------------------------------------------------------ finalise the previous tile, keep this tile's means
+    if (warp < NCW) {
+      const int m = sl0 + tid;
+      if (tid < sl1 - sl0) {
+        if (live) {
+          double mu = 0.0;
+          for (int cb = 0; cb < nblk; ++cb) mu += __ldcg(part_mu + ((size_t)b * nblk + cb) * BM + m);
+          mu_keep[b][tid] = mu;
+        }
+        if (tile > t_begin) {
+          const long long q = (tile - 1) * BM + m;
+          if (q < p.Q) {
+            double tot = 0.0;
+            for (int ib = 0; ib < nblk; ++ib) tot += __ldcg(part_ss + ((size_t)(b ^ 1) * nblk + ib) * BM + m);
+            const double mu = p.mean + mu_keep[b ^ 1][tid];
+            const double var = p.amp - tot;
+            if (p.mu) p.mu[q] = mu;
+            if (p.var) p.var[q] = var;
+            if (p.util) {
+              bool ok = true;
+              if (p.has_box) {
+                for (int i = 0; i < d; ++i) {
+                  const double x = p.Xq[q * d + i];
+                  ok = ok && (x >= p.lo[i]) && (x <= p.hi[i]);
+                }
+              }
+              p.util[q] = ok ? utility_eval(p.utility_kind, mu, var, p.ybest, p.zeta) : INFINITY;
+            }
+          }
+        }
+      }
+    }
+    if (!live) break;
+
+    // ------------------------------------------------------------ phase 2: my block-rows of the triangular GEMM
+    if (warp == NCW) {
+      if (lane == 0) {
+        for (int ib = 0; ib < nblk; ++ib) {
+          if (owner_s[ib] != rank) continue;
+          const int nk = (ib + 1) * (BN / BK);
+          const double* bsrc = p.LinvF + (size_t)linvf_tile_index(ib, 0, BN) * C::B_TILE;
+          for (int kb = 0; kb < nk; ++kb, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (it / NSTAGE) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            double* dstA = ring + (size_t)s * C::STAGE;
+            mbar_arrive_expect_tx(&full[s], C::STAGE * 8);
+            bulk_g2s(dstA, panel + (size_t)kb * C::A_TILE, C::A_TILE * 8, &full[s]);
+            bulk_g2s(dstA + C::A_TILE, bsrc + (size_t)kb * C::B_TILE, C::B_TILE * 8, &full[s]);
+          }
+        }
+      }
+    } else {
+      const int wm = warp;
+      for (int ib = 0; ib < nblk; ++ib) {
+        if (owner_s[ib] != rank) continue;
+        double acc[4][8][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+        const int nk = (ib + 1) * (BN / BK);
+        const int kdiag = ib * (BN / BK);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1u;
+          mbar_wait(&full[s], ph);
+          const double* As = ring + (size_t)s * C::STAGE + (wm * 4) * 32 + lane;
+          const double* Bs = ring + (size_t)s * C::STAGE + C::A_TILE + lane;
+          if (kb < kdiag) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              double a[4], bb[8];
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb) a[mb] = As[(k4 * (BM / 8) + mb) * 32];
+#pragma unroll
+              for (int nb = 0; nb < 8; ++nb) bb[nb] = Bs[(k4 * (BN / 8) + nb) * 32];
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bb[nb]);
+            }
+          } else {
+            const int kloc = (kb - kdiag) * BK;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              double a[4];
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb) a[mb] = As[(k4 * (BM / 8) + mb) * 32];
+#pragma unroll
+              for (int nb = 0; nb < 8; ++nb) {
+                if (kloc + k4 * 4 <= nb * 8 + 7) {
+                  const double bv = Bs[(k4 * (BN / 8) + nb) * 32];
+#pragma unroll
+                  for (int mb = 0; mb < 4; ++mb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bv);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {                 // this block-row's contribution to rowsum(W^2)
+          double sacc = 0.0;
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) {
+            sacc = fma(acc[mb][nb][0], acc[mb][nb][0], sacc);
+            sacc = fma(acc[mb][nb][1], acc[mb][nb][1], sacc);
+          }
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+          if ((lane & 3) == 0) part_ss[((size_t)b * nblk + ib) * BM + wm * 32 + mb * 8 + (lane >> 2)] = sacc;
+        }
+      }
+      __threadfence();                                   // partial row sums visible before the next barrier's arrival
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Mean-only predict (the emcee lnprob form, approx.py:178-180): one query per thread, training
 // set streamed through shared memory in SoA chunks; exp-bound (no GEMM).
 // ---------------------------------------------------------------------------------------------
@@ -406,6 +697,95 @@ int predict_variant_bn(int variant) { return variant_bn(variant); }
 
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant) {
   return (size_t)num_sms * variant_bm(variant) * Npad * 8;
+}
+
+// ---- grouped launch (256x64 tiling only) ------------------------------------------------------------
+// Work split inside a group of gs ranks.  Phase 2: block-row ib of L^-1 costs ib + 1 units (one unit = 64 k-columns
+// of DMMA for the 256x64 tile); longest-first onto the least loaded rank.  Phase 1: building one 64-column block of
+// the panel costs (2d + 12)/64 of a unit (exp + distances on the same FP64 pipe); the blocks go, one by one, to the
+// rank with the least combined load, which also evens out what phase 2 could not.  Returns max load / mean load.
+double plan_group_split(int nblk, int gs, int d, int* owner2, int* owner1) {
+  double load[64];
+  for (int r = 0; r < gs; ++r) load[r] = 0.0;
+  for (int ib = nblk - 1; ib >= 0; --ib) {
+    int best = 0;
+    for (int r = 1; r < gs; ++r) if (load[r] < load[best]) best = r;
+    owner2[ib] = best; load[best] += ib + 1;
+  }
+  const double c1 = (2.0 * d + 12.0) / 64.0;
+  for (int cb = 0; cb < nblk; ++cb) {
+    int best = 0;
+    for (int r = 1; r < gs; ++r) if (load[r] < load[best]) best = r;
+    owner1[cb] = best; load[best] += c1;
+  }
+  double mx = 0.0, tot = 0.0;
+  for (int r = 0; r < gs; ++r) { tot += load[r]; if (load[r] > mx) mx = load[r]; }
+  return mx * gs / tot;
+}
+
+int predict_group_size(int Npad, int num_sms, int variant, int requested, int d) {
+  if (variant != 2 || Npad / 64 > GROUP_MAX_BLOCKS) return 1;
+  const int nblk = Npad / 64;
+  int G = requested;
+  if (G < 0) {
+    // auto.  Gmin = smallest group whose panels being READ (one of the two buffers per group) fit ~80 MB of L2
+    // (measured at N = 2048: G = 8 keeps the speed of one tile per CTA with 8.8x less DRAM traffic).  Among
+    // Gmin/2 .. 64 take the group size with the best balanced split (a group waits for its slowest rank every
+    // tile: N = 1536 with G = 8 is 9 % imbalanced, G = 6 is exact); ties go to the smallest G >= Gmin.
+    if (Npad < 1024) return 1;                      // below, the 148 one-tile panels already (nearly) fit
+    int Gmin = 2;
+    while (Gmin < 64 && (size_t)((num_sms + Gmin - 1) / Gmin) * 256 * Npad * 8 > ((size_t)80 << 20)) ++Gmin;
+    int o2[GROUP_MAX_BLOCKS], o1[GROUP_MAX_BLOCKS];
+    int bestG = 1; double bestS = 1e30;
+    for (int g = (Gmin / 2 > 2 ? Gmin / 2 : 2); g <= 64 && 2 * g <= nblk; ++g) {
+      double imb = plan_group_split(nblk, g, d, o2, o1);
+      const int tail = num_sms % g;                 // a smaller last group: weigh its imbalance by its share of the SMs
+      if (tail > 1) imb = (imb * (num_sms - tail) + plan_group_split(nblk, tail, d, o2, o1) * tail) / num_sms;
+      else if (tail == 1) imb += 1.0 / num_sms;     // a lone CTA does whole tiles: fine, but it cannot share a panel
+      const double score = imb + (g < Gmin ? 0.005 : 0.0) + 1e-4 * g;   // L2 fit is worth 0.5 % of balance; then small G
+      if (score < bestS) { bestS = score; bestG = g; }
+    }
+    if (getenv("APGP_DEBUG_GROUP")) fprintf(stderr, "[apgp] Npad=%d nblk=%d Gmin=%d -> G=%d (score %.4f)\n", Npad, nblk, Gmin, bestG, bestS);
+    return bestG;
+  }
+  while (G > 1 && 2 * G > nblk) --G;              // every rank needs block-rows from both ends to balance
+  if (G > 64) G = 64;
+  return G < 1 ? 1 : G;
+}
+// work-split tables for the kernel: [full group | last (smaller) group] x [phase-2 owner | phase-1 owner] x 128
+void predict_group_plan(int Npad, int num_sms, int G, int d, int* tab) {
+  const int nblk = Npad / 64, tail = num_sms % G;
+  for (int i = 0; i < 4 * GROUP_MAX_BLOCKS; ++i) tab[i] = 0;
+  plan_group_split(nblk, G, d, tab, tab + GROUP_MAX_BLOCKS);
+  plan_group_split(nblk, tail > 0 ? tail : G, d, tab + 2 * GROUP_MAX_BLOCKS, tab + 3 * GROUP_MAX_BLOCKS);
+}
+size_t predict_group_scratch_bytes(int Npad, int num_sms, int G) {
+  return (size_t)2 * ((num_sms + G - 1) / G) * 256 * Npad * 8;
+}
+size_t predict_group_part_bytes(int Npad, int num_sms, int G) { return (size_t)((num_sms + G - 1) / G) * 4 * (Npad / 64) * 256 * 8; }
+
+int launch_predict_var_grouped(const PredictParams& p, int num_sms, int G, cudaStream_t st, int* launches) {
+  if (p.Q <= 0) return 0;
+  using C = VarCfg<256, 64, 4, 8>;
+  const size_t smem = C::smem_bytes(p.d);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(predict_var_group_kernel<256, 64, 4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int ngroups = (num_sms + G - 1) / G;
+  cudaError_t e = cudaMemsetAsync(p.grp_arrive, 0, sizeof(int) * ngroups, st);
+  if (e != cudaSuccess) return (int)e;
+  // the group barrier spins: every CTA of the grid must be resident at once -> cooperative launch (one CTA per SM)
+  PredictParams pc = p;
+  int Gc = G;
+  void* args[] = {(void*)&pc, (void*)&Gc};
+  e = cudaLaunchCooperativeKernel((const void*)predict_var_group_kernel<256, 64, 4>, dim3(num_sms), dim3(C::NTHREADS),
+                                  args, smem, st);
+  if (launches) ++*launches;
+  return (int)e;
 }
 
 int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches) {

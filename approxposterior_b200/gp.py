@@ -112,6 +112,11 @@ class GP(object):
     def launch_count(self):
         return int(self._lib.apgp_launch_count(self._h))
 
+    def set_group(self, group):
+        """CTAs sharing one query tile in the variance kernel (0: one tile per CTA, -1: automatic, 2..64: fixed);
+        with groups the K* panels in flight stay in L2 instead of streaming through HBM."""
+        _lib.check(self._lib.apgp_set_group(self._h, int(group)), "apgp_set_group")
+
     # ------------------------------------------------------------------ factorisation
     def _parse(self, t):
         t = np.asarray(t, dtype=np.float64)

@@ -271,15 +271,26 @@ def run_gpu(args):
     best_pack = torch.zeros(1 + DIM, dtype=torch.float64, device=dev)
     gathered = [torch.zeros_like(best_pack) for _ in range(world)] if world > 1 else None
 
-    def step(i):
+    kev = []
+
+    def step(i, timed=False):
+        """One pass of the hot path over one batch of candidates (+ arg-min and the single exchange).  The result
+        tensors die with the call, so the caching allocator hands the same blocks to the next step (keeping them
+        alive across iterations forced a cudaMalloc -- an implicit device sync of 3-100 ms -- inside timed step 1)."""
         c = cands[i % nbuf]
+        if timed:
+            k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+            k0.record()
         mu, var, u = gp._predict_raw(c, True, utility="bape", bounds=BOUNDS, ybest=ybest)
+        if timed:
+            k1.record()
+            kev.append((k0, k1))
         u2 = torch.nan_to_num(u, nan=float("inf"))
         ib = torch.argmin(u2)
         best_pack[0] = u2[ib]; best_pack[1:] = c[ib]
         if world > 1:
             dist.all_gather(gathered, best_pack)     # the single exchange: candidate scores
-        return u
+        return None
 
     def barrier():
         if world > 1:
@@ -297,22 +308,11 @@ def run_gpu(args):
     barrier()
     clocks.mark()
     l0 = gp.launch_count
-    kev = []
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(args.steps):
-        k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
-        c = cands[(args.warmup + i) % nbuf]
-        k0.record()
-        mu, var, u = gp._predict_raw(c, True, utility="bape", bounds=BOUNDS, ybest=ybest)
-        k1.record()
-        kev.append((k0, k1))
-        u2 = torch.nan_to_num(u, nan=float("inf"))
-        ib = torch.argmin(u2)
-        best_pack[0] = u2[ib]; best_pack[1:] = c[ib]
-        if world > 1:
-            dist.all_gather(gathered, best_pack)
+        step(args.warmup + i, timed=True)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)

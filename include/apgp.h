@@ -173,6 +173,9 @@ int apgp_debug_read_prof(long long* out16);
 /* select the variance-kernel tiling (queries x L^-1 rows per CTA tile): 0 = 64x256, 1 = 128x128,
  * 2 = 256x64 (default).  Call before factorize. */
 int apgp_set_variant(apgp_handle* h, int variant);
+/* CTAs that share one query tile in the 256x64 variance kernel (their K* panels then stay in L2 instead of streaming
+ * through HBM): 0 = one tile per CTA, -1 = automatic (by training-set size), 2..64 = fixed group size. */
+int apgp_set_group(apgp_handle* h, int group);
 
 #ifdef __cplusplus
 }

@@ -371,3 +371,31 @@ def test_sampler_argument_errors_are_reported():
         gp.run_ensembles(y, np.zeros((4, 2)), 0, b)             # no steps
     with pytest.raises(ValueError):
         gp.run_ensembles(y, np.zeros((10, 2)), 10, b, nens=3)   # rows not a multiple of nens
+
+
+@pytest.mark.parametrize("N,d,Q,group", [(1024, 2, 40000, -1), (2048, 5, 70001, 16), (2048, 5, 70001, 8),
+                                         (1100, 3, 30011, 6), (1100, 3, 700, 4), (4096, 2, 20000, -1)])
+def test_grouped_variance_kernel_matches_one_tile_per_cta(N, d, Q, group):
+    """G CTAs sharing one query tile (L2-resident K* panels) must reproduce the one-tile-per-CTA kernel.  The variance
+    agrees to ~1e-15; the mean adds the same per-column terms in a different order, so it agrees to the rounding of a
+    length-N sum of terms bounded by max|alpha| (alpha reaches 6e5 with cancellation on these problems)."""
+    import torch
+    from approxposterior_b200 import GP, kernels
+    X, y, logM, _ = synthetic_gp_problem(N, d, seed=N + d)
+    gp = GP(kernel=kernels.ExpSquaredKernel(np.exp(logM), ndim=d), fit_mean=True, mean=0.1, white_noise=-12.0)
+    gp.compute(X, y=y)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    q = -5.5 + 11.0 * torch.rand((Q, d), dtype=torch.float64, device="cuda", generator=g)
+    bounds = [(-5.0, 5.0)] * d
+    gp.set_group(0)
+    mu0, var0, u0 = gp._predict_raw(q, True, utility="agp", bounds=bounds)
+    gp.set_group(group)
+    mu_tol = 2.3e-16 * N * float(np.abs(gp._alpha()).max())
+    for rep in range(2):                                   # twice: the barrier counters are reset per launch
+        mu1, var1, u1 = gp._predict_raw(q, True, utility="agp", bounds=bounds)
+        assert float((mu1 - mu0).abs().max()) <= mu_tol
+        assert torch.allclose(var1, var0, rtol=0, atol=1e-12)
+        fin = torch.isfinite(u0)
+        assert torch.equal(fin, torch.isfinite(u1))
+        assert float((u1[fin] - u0[fin]).abs().max()) <= mu_tol + 1e-9
+    gp.set_group(0)
