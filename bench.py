@@ -32,7 +32,7 @@ N_TRAIN, DIM, Q_PER_GPU = 2048, 5, 1 << 20
 METRIC = "GP-surrogate lnprob evals/s (fp64 mean+var, N=2048, d=5)"
 UNIT = "evals/s"
 BOUNDS = [(-5.0, 5.0)] * DIM
-NCU_TRAFFIC_BYTES = 294.4e9      # dram__bytes_read.sum + dram__bytes_write.sum of one predict_var launch (profiles/)
+NCU_TRAFFIC_BYTES = 36.5e9       # dram__bytes_read.sum + dram__bytes_write.sum of one predict_var_group launch (profiles/)
 
 
 def flops_per_eval(N, d):
@@ -55,7 +55,8 @@ def workload_config(extra=None):
                        "2^20 candidates per GPU per step (BASELINE.json configs[2])",
            "N_train": N_TRAIN, "d": DIM, "candidates_per_gpu_per_step": Q_PER_GPU, "utility": "bape",
            "l2_policy": "candidate buffers rotate through 4 x 40 MB (> 126 MB L2 with outputs); the 16.8 MB "
-                        "L^-1 operand is the kernel's own L2-resident working set by design"}
+                        "L^-1 operand and the K* panels in flight (19 groups x 4 MB being read) are the kernel's own "
+                        "L2-resident working set by design"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -370,11 +371,13 @@ def run_gpu(args):
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
                              "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture "
-                                             "profiles/r01_predict_var_256x64_ncu_summary.txt): the K* slab is written "
-                                             "once (17 GB) and streamed back N/(2*64) times through a 13%-hit L2; "
-                                             "algorithmic I/O is 67 MB -- the kernel is FP64-pipe bound (DMMA pipe 94% "
-                                             "active), DRAM at 28% of peak",
-                             "kernel": "predict_var_kernel<256,64,4> (fused K* panel + DMMA triangular GEMM + utility)",
+                                             "profiles/r01_predict_var_grouped_ncu_summary.txt): every K* panel is written "
+                                             "once (17 GB per 2^20 queries) and re-read from L2 (84% hit) because 8 CTAs "
+                                             "share one query tile; the one-tile-per-CTA kernel of the same round moved "
+                                             "294 GB.  Algorithmic I/O is 67 MB -- the kernel is FP64-tensor-pipe bound "
+                                             "(DMMA pipe 93% active)",
+                             "kernel": "predict_var_group_kernel<256,64,4>, G=8 CTAs per 256-query tile (fused K* panel + "
+                                       "DMMA triangular GEMM + utility)",
                              "kernel_ms": kernel_ms, "kernel_ms_each": [round(v, 3) for v in kernel_each],
                              "flops_per_eval": flops_per_eval(N_TRAIN, DIM),
                              "peak_source": "cuBLAS DGEMM 8192^3 best-of-6 measured in this run "
