@@ -255,6 +255,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) belong on stderr: stdout carries
+        # exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     X, y, logM, mean = make_problem()
