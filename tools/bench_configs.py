@@ -118,7 +118,7 @@ if "cfg4" in which:
     def branin(u, v):
         return (v - 5.1 / (4 * np.pi ** 2) * u ** 2 + 5 / np.pi * u - 6) ** 2 + 10 * (1 - 1 / (8 * np.pi)) * np.cos(u) + 10
     rng = np.random.default_rng(64)
-    for N in (64, 128, 256, 512):
+    for N in (64, 128, 200, 256, 512):
         X = rng.uniform(-5, 5, size=(N, 10))
         U = (X + 5) / 10
         y = -sum(branin(15 * U[:, 2 * i] - 5, 15 * U[:, 2 * i + 1]) for i in range(5)) / 100.0
@@ -139,12 +139,19 @@ if "cfg4" in which:
         emit(config="cfg4", kernel="loglik_batch", N=N, d=10, restarts=64, ms_per_batch=dt * 1e3,
              nll_evals_per_s=64 / dt, cpu_oracle_ms_per_eval=cpu * 1e3, cpu_nll_evals_per_s=1 / cpu,
              finite=int(np.isfinite(ll).sum()))
-        if N == 256:
+        for engine in ("device", "lockstep"):
+            if engine == "device" and not gp.can_minimize_nll():
+                continue
+            if engine == "lockstep" and N not in (64, 200, 256):
+                continue
             np.random.seed(64)
+            keep = gp.get_parameter_vector()
             t0 = time.perf_counter()
-            gpUtils.optimizeGP(gp, X, y, nGPRestarts=64, method="powell", options={"maxiter": 3})
-            emit(config="cfg4-optGP", N=N, restarts=64, seconds=time.perf_counter() - t0,
-                 stats=gpUtils.optimizeGP.last_stats, note="Powell capped at 3 outer iterations per restart")
+            gpUtils.optimizeGP(gp, X, y, nGPRestarts=64, method="powell", options={"maxiter": 3}, engine=engine)
+            emit(config="cfg4-optGP", N=N, restarts=64, engine=engine, seconds=time.perf_counter() - t0,
+                 stats=gpUtils.optimizeGP.last_stats, best_ll=float(gp.log_likelihood(y)),
+                 note="Powell capped at 3 outer iterations per restart")
+            gp.set_parameter_vector(keep); gp.recompute()
 
 if "cfg1" in which:
     # README configuration: m0=50, m=20, nmax=2, 20 walkers x 2e4 steps, nGPRestarts=3
@@ -176,8 +183,12 @@ if "cfg1" in which:
         return theta, y
 
     bounds = [(-5, 5), (-5, 5)]
-    for label, engine, scan in (("lock-step restarts", "device", None), ("lock-step restarts", "host-rng", None),
+    from approxposterior_b200 import utility as ut
+    for label, engine, scan in (("device optimisers (one CTA per restart)", "device", None),
+                                ("host lock-step restarts", "device", None),
+                                ("host lock-step restarts", "host-rng", None),
                                 ("device scan 65536 + device polish", "device", 65536)):
+        ut.DEVICE_OPTIMIZER = gpUtils.DEVICE_OPTIMIZER = label.startswith("device optimisers") or scan is not None
         theta, y = readme_problem()
         gp = gpUtils.defaultGP(theta, y, white_noise=-12)
         prior = lh.BoxPrior(bounds) if engine == "device" else lh.rosenbrockLnprior
@@ -193,6 +204,7 @@ if "cfg1" in which:
              mcmcTime=ap.mcmcTime, bape_iteration_s=float(np.mean(ap.trainingTime)),
              posterior_mean=s.mean(axis=0).tolist(), posterior_std=s.std(axis=0).tolist(), iburn=int(ap.iburns[-1]),
              note="README.md:84-121 configuration")
+    ut.DEVICE_OPTIMIZER = gpUtils.DEVICE_OPTIMIZER = True
     # the same drivers on the CPU oracle (one BAPE iteration + a 2000-step per-half-step-batched MCMC)
     theta, y = readme_problem()
     g0 = default_gp_oracle(theta, y)

@@ -25,7 +25,26 @@ for N, d, amp in ((70, 2, None), (200, 3, 2.0), (300, 5, None)):
     gp.predict(y2, q[:100], return_cov=False, return_var=True)
     p0 = rng.uniform(-5, 5, size=(2 * 4 * d, d))
     gp.run_ensembles(y2, p0, 20, [(-5, 5)] * d, nens=2, seed=3)
+    # device-resident optimisers (one CTA per start) and their evaluate-only entry
+    starts = rng.uniform(-4, 4, size=(3, d))
+    for kind in ("bape", "negmean"):
+        gp.minimize_utility(y2, starts, kind, bounds=[(-5, 5)] * d, evaluate_only=True)
+        gp.minimize_utility(y2, starts, kind, bounds=[(-5, 5)] * d, options={"adaptive": True, "maxfev": 40})
+        gp.minimize_utility(y2, starts, kind, bounds=[(-5, 5)] * d, method="powell", options={"maxfev": 40})
+    if gp.can_minimize_nll():
+        gp.minimize_nll(P[:3], y2, evaluate_only=True)
+        gp.minimize_nll(P[:3], y2, method="powell", options={"maxfev": 25})
+        gp.minimize_nll(P[:3], y2, method="nelder-mead", options={"maxfev": 25})
     os.environ["APGP_LOGLIK_TILED"] = "1"
     gp.log_likelihood_batch(P, y2)
     del os.environ["APGP_LOGLIK_TILED"]
+# grouped variance kernel (G CTAs per query tile, cooperative launch): N >= 1024 selects it automatically
+N, d = 1100, 3
+X = rng.uniform(-5, 5, size=(N, d)); y = np.sin(X).sum(axis=1)
+gp = GP(kernel=kernels.ExpSquaredKernel(np.full(d, 3.0), ndim=d), fit_mean=True, mean=0.0, white_noise=-12.0)
+gp.compute(X, y=y)
+q = rng.uniform(-5, 5, size=(3000, d))
+gp.predict_utility(y, q, "bape", bounds=[(-5, 5)] * d)
+gp.set_group(4)
+gp.predict_utility(y, q[:300], "agp", bounds=[(-5, 5)] * d)
 print("sanitize_smoke ok")
