@@ -112,6 +112,44 @@ def test_1d_bayes_opt():
     assert np.allclose(soln["valMAPBest"], -trueSoln["fun"], rtol=5.0e-2)
 
 
+@pytest.mark.parametrize("box_prior", [False, True])
+def test_2d_bayes_opt(box_prior):
+    """reference tests/test_2DBayesOpt.py:16-75 (sphere function, Jones utility, bayesOpt + findMAP).  With the
+    reference's function prior the optimisers run in host lock step; with the equivalent BoxPrior every multistart
+    (utility, findMAP, hyper-parameter fit) is one device launch."""
+    from approxposterior_b200 import approx, gpUtils, likelihood as lh, utility as ut
+    seed = 91
+    np.random.seed(seed)
+    bounds = [[-5, 5], [-5, 5]]
+    fn = lambda x: -(lh.sphereLnlike(x) + lh.sphereLnprior(x))
+    trueSoln = minimize(fn, lh.sphereSample(1), method="nelder-mead")
+    theta = lh.sphereSample(10)
+    y = np.array([lh.sphereLnlike(t) + lh.sphereLnprior(t) for t in theta])
+    gp = gpUtils.defaultGP(theta, y, fitAmp=True)
+    prior = lh.BoxPrior([(-2, 2), (-2, 2)]) if box_prior else lh.sphereLnprior
+    ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=prior, lnlike=lh.sphereLnlike,
+                                priorSample=lh.sphereSample, bounds=bounds, algorithm="jones")
+    soln = ap.bayesOpt(nmax=10, tol=1.0e-3, kmax=3, seed=seed, cache=False, gpMethod="powell", optGPEveryN=1,
+                       nGPRestarts=3, nMinObjRestarts=5, initGPOpt=True, minObjMethod="nelder-mead", verbose=False,
+                       findMAP=True, gpHyperPrior=gpUtils.defaultHyperPrior)
+    assert ut.minimizeObjective.last_stats["scheduler"] == ("device" if box_prior else "generators")
+    assert gpUtils.optimizeGP.last_stats["scheduler"] == "device"
+    assert np.allclose(soln["thetaBest"], trueSoln["x"], atol=1.0e-2)
+    assert np.allclose(soln["valBest"], trueSoln["fun"], atol=1.0e-2)
+    assert np.allclose(soln["thetaMAPBest"], trueSoln["x"], atol=1.0e-2)
+    assert np.allclose(soln["valMAPBest"], trueSoln["fun"], atol=1.0e-2)
+
+
+def test_test_functions():
+    """reference tests/test_TestFns.py: optima of the fixture functions."""
+    from approxposterior_b200 import likelihood as lh
+    assert np.allclose(lh.rosenbrockLnlike([1.0, 1.0]), 0.0)
+    assert np.isneginf(lh.rosenbrockLnprior([5.1, 0.0])) and lh.rosenbrockLnprior([4.9, -4.9]) == 0.0
+    res = minimize(lambda x: -lh.testBOFn(x), [0.0], method="nelder-mead")
+    assert np.allclose(res["x"], -0.359, atol=1e-3) and np.allclose(-res["fun"], 0.5004, atol=1e-3)
+    assert lh.sphereLnlike([0.0, 0.0]) == 0.0 and np.isneginf(lh.sphereLnprior([2.1, 0.0]))
+
+
 @pytest.mark.parametrize("engine", ["device", "host-rng"])
 def test_run_posterior(engine, tmp_path):
     """reference tests/test_APRun.py:17-75 (shortened): BAPE on the Rosenbrock posterior; marginal means
