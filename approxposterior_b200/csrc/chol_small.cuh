@@ -32,11 +32,17 @@ __device__ long long g_prof[16];
 #endif
 
 // K: packed lower triangle (row i at i(i+1)/2), overwritten by L (entries of the diagonal blocks are written back
-//    only when store_diag).  r: [N] rhs in, z = L^{-1} r out.  diag: [N] out, L_ii.  *badflag is set to 1 (never
-//    cleared here) when a pivot is not positive and finite.  NT = blockDim.x.  Ends with a barrier.
-template <int NT>
+//    only when store_diag).  r: nrhs right-hand sides, row q at r + q*ldr, [N] each: rhs in, L^{-1} rhs out (with
+//    the N unit vectors as right-hand sides the rows come back as the columns of L^{-1}).  diag: [N] out, L_ii.
+//    *badflag receives the 1-based index of the first pivot that is not positive and finite (never cleared here).  NT = blockDim.x >= N + nrhs,
+//    nrhs >= 1.  Ends with a barrier.
+//    FAST_PIVOT: pivots by rsqrt (<= 1 ulp, ~75 cycles) instead of IEEE sqrt + divide (~190 cycles): used by the
+//    optimiser objectives, where the pivot chain is the critical path; the factorisation behind predict keeps the
+//    correctly rounded pair (its errors are amplified by cond(K) into alpha and L^{-1}).
+template <int NT, bool FAST_PIVOT = true>
 __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, double* __restrict__ r,
-                                                    double* __restrict__ diag, int N, int* badflag, bool store_diag) {
+                                                    double* __restrict__ diag, int N, int* badflag, bool store_diag,
+                                                    int nrhs = 1, int ldr = 0) {
   const int tid = threadIdx.x;
   for (int J0 = 0; J0 < N; J0 += CHOL_B) {
     const int bw = (N - J0 < CHOL_B) ? (N - J0) : CHOL_B;
@@ -44,11 +50,11 @@ __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, doub
     if (J0 > 0) {
       // items = (row, column) dot products of length J0, one item per thread pass; 32-bit index math
       // (N < 256, so i(i+1)/2 < 2^15).  (Splitting short item lists over 2-8 lanes + shuffles measured slower.)
-      const int nitems = (N - J0 + 1) * CHOL_B;                 // rows J0..N-1 and the rhs row, CHOL_B columns each
+      const int nitems = (N - J0 + nrhs) * CHOL_B;              // rows J0..N-1 and the rhs rows, CHOL_B columns each
       for (int it = tid; it < nitems; it += NT) {
         const int i = J0 + (it >> 3), c = it & (CHOL_B - 1);
         if (c >= bw || (i < N && J0 + c > i)) continue;
-        const double* Li = (i < N) ? K + i * (i + 1) / 2 : r;
+        const double* Li = (i < N) ? K + i * (i + 1) / 2 : r + (i - N) * ldr;
         const double* Lc = K + (J0 + c) * (J0 + c + 1) / 2;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;             // J0 is a multiple of 8
 #pragma unroll 2
@@ -56,7 +62,7 @@ __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, doub
           s0 = fma(Li[k], Lc[k], s0); s1 = fma(Li[k + 1], Lc[k + 1], s1);
           s2 = fma(Li[k + 2], Lc[k + 2], s2); s3 = fma(Li[k + 3], Lc[k + 3], s3);
         }
-        double* dst = (i < N) ? K + i * (i + 1) / 2 + J0 + c : r + J0 + c;
+        double* dst = (i < N) ? K + i * (i + 1) / 2 + J0 + c : r + (i - N) * ldr + J0 + c;
         *dst -= ((s0 + s1) + (s2 + s3));
       }
       PROF_ADD(4, t_p1);
@@ -64,9 +70,9 @@ __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, doub
     }
     PROF_ADD(0, t_p1);
     PROF_T(t_p2);
-    const int nbelow = N - J0 - bw;                              // rows under the diagonal block; + 1 rhs row (needs N < NT)
+    const int nbelow = N - J0 - bw;                              // rows under the diagonal block; then the rhs rows
     double D[CHOL_B][CHOL_B];
-    if (tid <= nbelow) {
+    if (tid < nbelow + nrhs) {
       double inv[CHOL_B];
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c)
@@ -75,14 +81,16 @@ __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, doub
           D[c][c2] = (c < bw) ? K[(size_t)(J0 + c) * (J0 + c + 1) / 2 + J0 + c2] : ((c == c2) ? 1.0 : 0.0);
       PROF_ADD(8, t_p2);
       PROF_T(t_f);
-      bool bad = false;
+      int bad = 0;                                                // 1-based index of the first failing pivot
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c) {
         double dj = D[c][c];
-        if (!(dj > 0.0 && dj < INFINITY)) { bad = true; dj = 1.0; }
-        const double iv = rsqrt(dj);
+        if (!(dj > 0.0 && dj < INFINITY)) { if (!bad) bad = J0 + c + 1; dj = 1.0; }
+        double iv, sq;
+        if (FAST_PIVOT) { iv = rsqrt(dj); sq = dj * iv; }
+        else { sq = sqrt(dj); iv = 1.0 / sq; }
         inv[c] = iv;
-        D[c][c] = dj * iv;
+        D[c][c] = sq;
 #pragma unroll
         for (int c2 = c + 1; c2 < CHOL_B; ++c2) D[c2][c] *= iv;
 #pragma unroll
@@ -92,7 +100,8 @@ __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, doub
       }
       PROF_ADD(9, t_f);
       PROF_T(t_r);
-      double* row = (tid < nbelow) ? K + (size_t)(J0 + bw + tid) * (J0 + bw + tid + 1) / 2 + J0 : r + J0;
+      double* row = (tid < nbelow) ? K + (size_t)(J0 + bw + tid) * (J0 + bw + tid + 1) / 2 + J0
+                                   : r + (tid - nbelow) * ldr + J0;
       double x[CHOL_B];
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c) x[c] = (c < bw) ? row[c] : 0.0;
@@ -106,8 +115,8 @@ __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, doub
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c) if (c < bw) row[c] = x[c];
       PROF_ADD(10, t_r);
-      if (tid == nbelow) {                                       // the rhs-row thread also publishes the pivots
-        if (bad) *badflag = 1;
+      if (tid == nbelow) {                                       // the first rhs-row thread also publishes the pivots
+        if (bad && *badflag == 0) *badflag = bad;
 #pragma unroll
         for (int c = 0; c < CHOL_B; ++c) if (c < bw) diag[J0 + c] = D[c][c];
       }

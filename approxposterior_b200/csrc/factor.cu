@@ -23,7 +23,6 @@ constexpr int T = 64;          // tile edge
 constexpr int LDS_ = 68;       // padded smem leading dimension: conflict-free DMMA fragment loads
 constexpr int GT = 128;        // threads per tile group: 4 warps, each a 32x32 sub-tile
 constexpr size_t TILE_SMEM = (size_t)2 * T * LDS_ * sizeof(double);
-constexpr size_t DIAG_SMEM = (size_t)(2 * T * (T + 1) + T) * sizeof(double);
 
 // ---- tile movers ------------------------------------------------------------------------
 // dst[r][c] (smem, ld 68) = src[r*ld + c]          (row-major 64x64 block)
@@ -129,57 +128,50 @@ __global__ void build_K_kernel(const double* __restrict__ X, const double* __res
 }
 
 // ---- step k, diagonal block: D = chol(A_kk), Dinv = D^{-1}, z_k = Dinv r_k, logdet += 2 sum log D_ii
-__global__ void __launch_bounds__(T) chol_diag_kernel(FactorBatch fb, int k) {
+// One CTA per restart.  The 64x64 block is factored by the blocked in-shared-memory routine of chol_small.cuh with
+// 65 right-hand sides riding along: r_k (-> z_k) and the 64 unit vectors, whose solutions are the columns of D^{-1}.
+// (The first version -- one thread per row, three barriers per column, then a 64-step substitution per column of the
+// inverse -- took 127 us per block and was the whole cost of a tiled factorisation: 0.14 ms per block column at any
+// batch size up to 8.)
+constexpr int DIAG_THREADS = 256;
+constexpr int DIAG_LDR = T + 1;                 // odd row stride of the right-hand-side block: conflict-free row threads
+constexpr size_t DIAG_SMEM = (size_t)(T * (T + 1) / 2 + (T + 1) * DIAG_LDR + T) * sizeof(double);
+__global__ void __launch_bounds__(DIAG_THREADS, 1) chol_diag_kernel(FactorBatch fb, int k) {
   extern __shared__ __align__(16) double dsm[];
-  double (*S)[T + 1] = reinterpret_cast<double (*)[T + 1]>(dsm);
-  double (*Xi)[T + 1] = reinterpret_cast<double (*)[T + 1]>(dsm + T * (T + 1));
-  double* rs = dsm + 2 * T * (T + 1);
+  double* S = dsm;                              // packed lower triangle of the block
+  double* R = S + T * (T + 1) / 2;              // [1 + T][DIAG_LDR]: row 0 = r_k, row 1 + c = e_c
+  double* dg = R + (T + 1) * DIAG_LDR;          // [T] pivots
+  __shared__ int bad;
+  __shared__ double red[DIAG_THREADS / 32];
   const int rr = blockIdx.x, tid = threadIdx.x;
   const int Np = fb.Np;
   double* A = fb.K + (size_t)rr * Np * Np + (size_t)k * T * Np + k * T;
-  for (int e = tid; e < T * T; e += T) { int i = e >> 6, j = e & 63; S[i][j] = (j <= i) ? A[(size_t)i * Np + j] : 0.0; }
-  __syncthreads();
-  for (int j = 0; j < T; ++j) {
-    const double dj = S[j][j];
-    __syncthreads();
-    double s;
-    if (dj > 0.0 && dj < INFINITY) s = sqrt(dj);
-    else { s = 1.0; if (tid == 0) atomicCAS(&fb.info[rr], 0, k * T + j + 1); }
-    const double inv = 1.0 / s;
-    // thread tid owns row tid
-    if (tid == j) S[j][j] = s;
-    double lij = 0.0;
-    if (tid > j) { lij = S[tid][j] * inv; S[tid][j] = lij; }
-    __syncthreads();
-    if (tid > j) {
-      for (int c = j + 1; c <= tid; ++c) S[tid][c] -= lij * S[c][j];
-    }
-    __syncthreads();
-  }
-  // inverse: thread c solves D x = e_c (column c of D^{-1})
-  {
-    const int c = tid;
-    for (int i = 0; i < T; ++i) {
-      double acc = (i == c) ? 1.0 : 0.0;
-      for (int j = c; j < i; ++j) acc -= S[i][j] * Xi[j][c];
-      Xi[i][c] = (i >= c) ? acc / S[i][i] : 0.0;
-    }
-  }
-  __syncthreads();
-  double* Dg = fb.Dinv + ((size_t)rr * (Np / T) + k) * T * T;
-  for (int e = tid; e < T * T; e += T) { int i = e >> 6, j = e & 63; A[(size_t)i * Np + j] = S[i][j]; Dg[e] = Xi[i][j]; }
-  // z_k = Dinv * r_k ; logdet
   double* rk = fb.r + (size_t)rr * Np + k * T;
-  rs[tid] = rk[tid];
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < T * T; e += DIAG_THREADS) {
+    const int i = e >> 6, j = e & 63;
+    if (j <= i) S[i * (i + 1) / 2 + j] = A[(size_t)i * Np + j];
+    R[(1 + i) * DIAG_LDR + j] = (i == j) ? 1.0 : 0.0;
+  }
+  if (tid < T) R[tid] = rk[tid];
   __syncthreads();
-  double z = 0.0;
-  for (int j = 0; j <= tid; ++j) z += Xi[tid][j] * rs[j];
-  rk[tid] = z;
-  double lg = log(S[tid][tid]);
+  chol_packed_blocked<DIAG_THREADS, false>(S, R, dg, T, &bad, true, T + 1, DIAG_LDR);
+  double* Dg = fb.Dinv + ((size_t)rr * (Np / T) + k) * T * T;
+  for (int e = tid; e < T * T; e += DIAG_THREADS) {
+    const int i = e >> 6, j = e & 63;
+    A[(size_t)i * Np + j] = (j <= i) ? S[i * (i + 1) / 2 + j] : 0.0;
+    Dg[e] = (j <= i) ? R[(1 + j) * DIAG_LDR + i] : 0.0;       // D^{-1}[i][j] = (solution for e_j)[i]
+  }
+  if (tid < T) rk[tid] = R[tid];
+  double lg = (tid < T) ? log(dg[tid]) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+  if ((tid & 31) == 0) red[tid >> 5] = lg;
   __syncthreads();
-  rs[tid] = lg;
-  __syncthreads();
-  if (tid == 0) { double tot = 0.0; for (int j = 0; j < T; ++j) tot += rs[j]; fb.logdet[rr] += 2.0 * tot; }
+  if (tid == 0) {
+    fb.logdet[rr] += 2.0 * (red[0] + red[1]);
+    if (bad) atomicCAS(&fb.info[rr], 0, k * T + bad);        // 1-based index of the first failing pivot
+  }
 }
 
 // ---- step k, panel: L_ik = A_ik * Dinv_k^T ; r_i -= L_ik z_k        grid (nb-k-1, R)
@@ -585,7 +577,7 @@ int launch_cholesky(const FactorBatch& fb, int num_sms, cudaStream_t st, int* la
   int e = ensure_attrs(); if (e) return e;
   const int nb = fb.Np / T;
   for (int k = 0; k < nb; ++k) {
-    chol_diag_kernel<<<fb.R, T, DIAG_SMEM, st>>>(fb, k);
+    chol_diag_kernel<<<fb.R, DIAG_THREADS, DIAG_SMEM, st>>>(fb, k);
     if (launches) ++*launches;
     const int rem = nb - k - 1;
     if (rem > 0) {
