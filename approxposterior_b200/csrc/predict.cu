@@ -285,9 +285,11 @@ predict_var_kernel(const __grid_constant__ PredictParams p) {
 //   epilogue the per-rank partial row sums / means meet in a small global buffer; the tile is finalised (var,
 //            prior gate, utility) by the ranks, one slice of the queries each, after the NEXT tile's barrier,
 //            so a single barrier per tile orders everything.  Panels and partials are double-buffered.
-// Panels in flight: 2 x (grid/G) x 256 x Npad x 8 B (74 MB at N = 2048, G = 16).  Results are bit-identical to
-// the ungrouped kernel for the mean (same summation order within a column block; blocks are then added in rank
-// order) up to the order of the block partial sums, and within 1e-13 relative for the variance.
+// Panels in flight: 2 x (grid/G) x 256 x Npad x 8 B (152 MB at N = 2048, G = 8, of which the 76 MB being read
+// stay L2-resident).  Partial sums are kept per 64-column block (mean) and per block-row (variance) and added in
+// block order, so a query's result does not depend on its position in the batch, on G, or on the size of the last
+// group; against the one-tile-per-CTA kernel the variance agrees to ~1e-15 and the mean to the rounding of a
+// length-N sum (tests/test_gpu_parity.py::test_grouped_variance_kernel_matches_one_tile_per_cta).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -306,9 +308,7 @@ predict_var_group_kernel(const __grid_constant__ PredictParams p, const int G) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
   double* qs = ring + C::RING;                          // [d][BM] scaled queries
-  double* mu_s = qs + (size_t)p.d * BM;                 // [BM] partial mean of my column blocks
-  double* ss_s = mu_s + BM;                             // [BM] partial row sums of my block-rows
-  double* etab = ss_s + BM;                             // [64]
+  double* etab = qs + (size_t)p.d * BM + 2 * BM;        // [64] (same carve-up as predict_var_kernel: VarCfg::smem_bytes)
   uint64_t* full = reinterpret_cast<uint64_t*>(etab + 64);
   uint64_t* empty = full + NSTAGE;
   uint64_t* stagebar = empty + NSTAGE;

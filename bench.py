@@ -263,8 +263,9 @@ def run_gpu(args):
     X, y, logM, mean = make_problem()
     gp = GP(kernel=kernels.ExpSquaredKernel(np.exp(logM), ndim=DIM), fit_mean=True, mean=mean, white_noise=-12.0,
             device=local)
+    gp.compute(X, y=y)                       # first call: module load + buffer allocation
     t0 = time.perf_counter()
-    gp.compute(X, y=y)
+    gp.compute(X, y=y)                       # steady state: covariance build, Cholesky, L^-1, packing
     t_factor = time.perf_counter() - t0
     ybest = float(np.max(y))
 
