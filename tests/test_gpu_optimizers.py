@@ -187,3 +187,24 @@ def test_find_map_on_device():
     MAP, val = ap.findMAP(nRestarts=8)
     assert ut.minimizeObjective.last_stats["scheduler"] == "device"
     assert np.allclose(MAP, [0.0, 0.0], atol=5e-2) and abs(val) < 5e-2
+
+
+@pytest.mark.parametrize("method,options", [("nelder-mead", {"adaptive": True}), ("powell", None),
+                                            ("nelder-mead", {"maxfev": 1}), ("powell", {"maxfev": 2})])
+def test_device_optimisers_one_dimensional(method, options):
+    """ndim = 1 (the reference's 1-D Bayesian-optimisation example): simplex of two points, one Powell direction."""
+    from approxposterior_b200 import _optimizers as opt
+    gp, X, y = _gp(N=30, d=1, seed=8)
+    bounds = [(-5.0, 5.0)]
+    starts = np.array([[-3.0], [0.0], [4.5], [5.5]])          # the last start is outside the prior: +inf everywhere
+    xd, fd, nd = gp.minimize_utility(y, starts, "jones", bounds=bounds, method=method, options=options)
+    o = dict(options or {})
+    make = (lambda t0: opt.nelder_mead_gen(t0, _stable=True, **o)) if method == "nelder-mead" else (lambda t0: opt.powell_gen(t0, **o))
+    xh, fh, evals = _run_host(make, starts, lambda P: gp.minimize_utility(y, np.array(P), "jones", bounds=bounds,
+                                                                        evaluate_only=True)[1])
+    assert np.array_equal(xd, xh, equal_nan=True) and np.array_equal(fd, fh, equal_nan=True)
+    assert int(np.sum(nd)) == evals
+    P0 = np.array([[np.median(y), 0.3], [np.median(y), -1.0]])
+    pd_, fnd, nn = gp.minimize_nll(P0, y, method=method, options=options)
+    ph, fnh, ev2 = _run_host(make, P0, lambda Q: gp.minimize_nll(np.array(Q), y, evaluate_only=True)[1])
+    assert np.array_equal(pd_, ph, equal_nan=True) and np.array_equal(fnd, fnh, equal_nan=True) and int(np.sum(nn)) == ev2
