@@ -509,9 +509,9 @@ int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* o, const double* p
   if (!h->factored) return fail(APGP_NOT_COMPUTED, "apgp_sampler_run: GP not computed");
   if (o->nens < 1 || o->nwalkers < 2 || (o->nwalkers & 1) || o->nwalkers > 1024 || o->nsteps < 1 || o->thin < 1)
     return fail(APGP_ERR_ARG, "apgp_sampler_run: need nens>=1, even 2<=nwalkers<=1024, nsteps>=1, thin>=1");
-  if ((size_t)o->nwalkers * (3 * h->d + 6) * 8 + (size_t)o->nwalkers * 16 + 64 > 200 * 1024)
+  if ((size_t)o->nwalkers * (24 * h->d + 72) + 64 > 200 * 1024)
     return fail(APGP_ERR_ARG, "apgp_sampler_run: nwalkers x ndim too large for one CTA's shared memory "
-                              "(need nwalkers * (24 ndim + 64) bytes <= 200 KB); use more ensembles of fewer walkers");
+                              "(need nwalkers * (24 ndim + 72) bytes <= 200 KB); use more ensembles of fewer walkers");
   Guard g(h->device);
   const int d = h->d;
   const size_t W = (size_t)o->nens * o->nwalkers;

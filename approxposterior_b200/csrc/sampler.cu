@@ -24,14 +24,17 @@ struct Smem {
   double* q;       // [nw][d]   proposals (initial pass evaluates all nw walkers)
   double* sq;      // [nw][d]   the same rows scaled for the kernel distance
   double* nlp;     // [nw]
-  double* fac;     // [nw]
-  double* logu;    // [nw]
   const double* etab;  // [64] 2^(j/64) for exp_neg
-  unsigned long long* key;  // [nw] random keys for the colouring
-  int* colour;     // [nw]
-  int* sidx;       // [nw]
-  int* cidx;       // [nw]
   int* ok;         // [nw]
+  // everything random about a step is independent of the chain's state, so it is drawn for SB steps at a time by
+  // all threads in parallel (the per-step critical path is then: propose, evaluate, accept)
+  unsigned long long* key;  // [SB][nw] random keys for the colouring
+  int* colour;     // [SB][nw]
+  int* list;       // [SB][2][Ns] walkers of colour 0 / colour 1, in walker order
+  int* rint;       // [SB][2][Ns] partner index into the complementary list
+  double* zz;      // [SB][2][Ns] stretch factor
+  double* fac;     // [SB][2][Ns] (d-1) ln zz
+  double* logu;    // [SB][2][Ns] ln u of the accept test
 };
 
 // lnprob for the `np` rows of sm.q.  A warp takes two rows per pass (they share every training-set load),
@@ -114,7 +117,7 @@ __device__ __forceinline__ int stage_row(const SamplerParams& p, const Smem& sm,
   return ok;
 }
 
-__global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ SamplerParams p, int xs_in_smem) {
+__global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ SamplerParams p, int xs_in_smem, int SB) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int e = blockIdx.x, tid = threadIdx.x;
   const int nw = p.nwalk, d = p.d, Ns = nw / 2, Npad = p.Npad;
@@ -132,13 +135,14 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
   sm.q = f; f += nw * d;
   sm.sq = f; f += nw * d;
   sm.nlp = f; f += nw;
-  sm.fac = f; f += nw;
-  sm.logu = f; f += nw;
-  sm.key = reinterpret_cast<unsigned long long*>(f); f += nw;
+  sm.zz = f; f += (size_t)SB * nw;
+  sm.fac = f; f += (size_t)SB * nw;
+  sm.logu = f; f += (size_t)SB * nw;
+  sm.key = reinterpret_cast<unsigned long long*>(f); f += (size_t)SB * nw;
   int* ip = reinterpret_cast<int*>(f);
-  sm.colour = ip; ip += nw;
-  sm.sidx = ip; ip += nw;
-  sm.cidx = ip; ip += nw;
+  sm.colour = ip; ip += (size_t)SB * nw;
+  sm.list = ip; ip += (size_t)SB * nw;
+  sm.rint = ip; ip += (size_t)SB * nw;
   sm.ok = ip; ip += nw;
 
   if (xs_in_smem) {
@@ -160,81 +164,102 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
   Philox rng; rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
   const bool replay = p.r_zz != nullptr;
 
-  for (int step = 0; step < p.nsteps; ++step) {
-    // ---- colours
+  for (int step0 = 0; step0 < p.nsteps; step0 += SB) {
+    const int sb = min(SB, p.nsteps - step0);
+    // ---------------------------------------------------------------- randomness of the next sb steps, in parallel
     if (replay) {
-      for (int w = tid; w < nw; w += blockDim.x) sm.colour[w] = p.r_inds[((size_t)e * p.nsteps + step) * nw + w];
+      for (int idx = tid; idx < sb * nw; idx += blockDim.x) {
+        const int s = idx / nw, w = idx - s * nw;
+        sm.colour[idx] = p.r_inds[((size_t)e * p.nsteps + step0 + s) * nw + w];
+      }
     } else {
       // uniformly random half/half colouring (same law as emcee's shuffle of arange(nw) % 2): every walker
       // draws a key, the nw/2 smallest keys are colour 0.  Fully parallel -- no serial Fisher-Yates.
-      for (int w = tid; w < nw; w += blockDim.x) {
-        uint32_t o[4]; rng.gen((uint32_t)e, (uint32_t)step, 0x10000u, (uint32_t)w, o);
-        sm.key[w] = ((uint64_t)o[0] << 32) | o[1];
+      for (int idx = tid; idx < sb * nw; idx += blockDim.x) {
+        const int s = idx / nw, w = idx - s * nw;
+        uint32_t o[4]; rng.gen((uint32_t)e, (uint32_t)(step0 + s), 0x10000u, (uint32_t)w, o);
+        sm.key[idx] = ((uint64_t)o[0] << 32) | o[1];
       }
       __syncthreads();
-      for (int w = tid; w < nw; w += blockDim.x) {
-        const uint64_t kw = sm.key[w];
+      for (int idx = tid; idx < sb * nw; idx += blockDim.x) {
+        const int s = idx / nw, w = idx - s * nw;
+        const unsigned long long* ks = sm.key + (size_t)s * nw;
+        const uint64_t kw = ks[w];
         int rank = 0;
-        for (int v = 0; v < nw; ++v) { const uint64_t kv = sm.key[v]; rank += (kv < kw) || (kv == kw && v < w); }
-        sm.colour[w] = rank < Ns ? 0 : 1;
+        for (int v = 0; v < nw; ++v) { const uint64_t kv = ks[v]; rank += (kv < kw) || (kv == kw && v < w); }
+        sm.colour[idx] = rank < Ns ? 0 : 1;
       }
     }
     __syncthreads();
-    for (int split = 0; split < 2; ++split) {
-      for (int w = tid; w < nw; w += blockDim.x) {       // position of w among the walkers of its colour
-        const int cw = sm.colour[w];
-        int pos = 0;
-        for (int v = 0; v < w; ++v) pos += (sm.colour[v] == cw);
-        if (cw == split) sm.sidx[pos] = w; else sm.cidx[pos] = w;
-      }
-      __syncthreads();
-      for (int i = tid; i < Ns; i += blockDim.x) {
-        double zz, lu; int r;
-        if (replay) {
-          size_t off = (((size_t)e * p.nsteps + step) * 2 + split) * Ns + i;
-          zz = p.r_zz[off]; r = p.r_rint[off]; lu = p.r_logu[off];
-        } else {
-          uint32_t o[4], o2[4];
-          rng.gen((uint32_t)e, (uint32_t)step, (uint32_t)split, (uint32_t)i, o);
-          rng.gen((uint32_t)e, (uint32_t)step, (uint32_t)(split + 2), (uint32_t)i, o2);
-          double u = u01_from_bits(o[0], o[1]);
-          double t = (p.a - 1.0) * u + 1.0;
-          zz = t * t / p.a;
-          lu = log(u01_from_bits(o[2], o[3]));
-          r = (int)(((uint64_t)o2[0] * (uint64_t)Ns) >> 32);
-        }
-        const double* cs = sm.coords + sm.cidx[r] * d;
-        const double* ss = sm.coords + sm.sidx[i] * d;
-        for (int c = 0; c < d; ++c) sm.q[i * d + c] = cs[c] - (cs[c] - ss[c]) * zz;
-        sm.fac[i] = (d - 1.0) * log(zz);
-        sm.logu[i] = lu;
-        sm.ok[i] = stage_row(p, sm, i);
-      }
-      __syncthreads();
-      eval_rows(p, sm, Ns);
-      __syncthreads();
-      for (int i = tid, k = 0; i < Ns; i += blockDim.x, ++k) {
-        const int j = sm.sidx[i];
-        const double diff = sm.fac[i] + sm.nlp[i] - sm.lp[j];
-        if (diff > sm.logu[i]) {
-          for (int c = 0; c < d; ++c) sm.coords[j * d + c] = sm.q[i * d + c];
-          sm.lp[j] = sm.nlp[i];
-          sm.blob[j] = sm.ok[i] ? p.lnprior_const : NAN;
-          atomicAdd(&p.naccept[(size_t)e * nw + j], 1);
-        }
-      }
-      __syncthreads();
+    for (int idx = tid; idx < sb * nw; idx += blockDim.x) {     // position of w among the walkers of its colour
+      const int s = idx / nw, w = idx - s * nw;
+      const int* cs = sm.colour + (size_t)s * nw;
+      const int cw = cs[w];
+      int pos = 0;
+      for (int v = 0; v < w; ++v) pos += (cs[v] == cw);
+      sm.list[((size_t)s * 2 + cw) * Ns + pos] = w;
     }
-    if ((step + 1) % p.thin == 0) {
-      const long srow = (step + 1) / p.thin - 1;
-      for (int idx = tid; idx < nw * d; idx += blockDim.x)
-        p.chain[(srow * W + (size_t)e * nw) * d + idx] = sm.coords[idx];
-      for (int w = tid; w < nw; w += blockDim.x) {
-        p.logp[srow * W + (size_t)e * nw + w] = sm.lp[w];
-        p.blob[srow * W + (size_t)e * nw + w] = sm.blob[w];
+    for (int idx = tid; idx < sb * 2 * Ns; idx += blockDim.x) {   // stretch factor, partner, accept threshold
+      const int s = idx / (2 * Ns), rem = idx - s * 2 * Ns, split = rem / Ns, i = rem - split * Ns;
+      const int step = step0 + s;
+      double zz, lu; int r;
+      if (replay) {
+        const size_t off = (((size_t)e * p.nsteps + step) * 2 + split) * Ns + i;
+        zz = p.r_zz[off]; r = p.r_rint[off]; lu = p.r_logu[off];
+      } else {
+        uint32_t o[4], o2[4];
+        rng.gen((uint32_t)e, (uint32_t)step, (uint32_t)split, (uint32_t)i, o);
+        rng.gen((uint32_t)e, (uint32_t)step, (uint32_t)(split + 2), (uint32_t)i, o2);
+        const double u = u01_from_bits(o[0], o[1]);
+        const double t = (p.a - 1.0) * u + 1.0;
+        zz = t * t / p.a;
+        lu = log(u01_from_bits(o[2], o[3]));
+        r = (int)(((uint64_t)o2[0] * (uint64_t)Ns) >> 32);
       }
+      sm.zz[idx] = zz; sm.rint[idx] = r; sm.logu[idx] = lu; sm.fac[idx] = (d - 1.0) * log(zz);
     }
-    // no sync needed: next writes to coords happen after the next __syncthreads chain
+    __syncthreads();
+
+    // ---------------------------------------------------------------- the sb steps themselves
+    for (int s = 0; s < sb; ++s) {
+      const int step = step0 + s;
+      for (int split = 0; split < 2; ++split) {
+        const int* sidx = sm.list + ((size_t)s * 2 + split) * Ns;          // walkers being moved
+        const int* cidx = sm.list + ((size_t)s * 2 + (split ^ 1)) * Ns;    // the complementary half
+        const size_t boff = ((size_t)s * 2 + split) * Ns;
+        for (int i = tid; i < Ns; i += blockDim.x) {
+          const double zz = sm.zz[boff + i];
+          const double* cs = sm.coords + cidx[sm.rint[boff + i]] * d;
+          const double* ss = sm.coords + sidx[i] * d;
+          for (int c = 0; c < d; ++c) sm.q[i * d + c] = cs[c] - (cs[c] - ss[c]) * zz;
+          sm.ok[i] = stage_row(p, sm, i);
+        }
+        __syncthreads();
+        eval_rows(p, sm, Ns);
+        __syncthreads();
+        for (int i = tid; i < Ns; i += blockDim.x) {
+          const int j = sidx[i];
+          const double diff = sm.fac[boff + i] + sm.nlp[i] - sm.lp[j];
+          if (diff > sm.logu[boff + i]) {
+            for (int c = 0; c < d; ++c) sm.coords[j * d + c] = sm.q[i * d + c];
+            sm.lp[j] = sm.nlp[i];
+            sm.blob[j] = sm.ok[i] ? p.lnprior_const : NAN;
+            atomicAdd(&p.naccept[(size_t)e * nw + j], 1);
+          }
+        }
+        __syncthreads();
+      }
+      if ((step + 1) % p.thin == 0) {
+        const long srow = (step + 1) / p.thin - 1;
+        for (int idx = tid; idx < nw * d; idx += blockDim.x)
+          p.chain[(srow * W + (size_t)e * nw) * d + idx] = sm.coords[idx];
+        for (int w = tid; w < nw; w += blockDim.x) {
+          p.logp[srow * W + (size_t)e * nw + w] = sm.lp[w];
+          p.blob[srow * W + (size_t)e * nw + w] = sm.blob[w];
+        }
+      }
+      // no sync needed: the next writes to coords/lp/blob happen after two more __syncthreads
+    }
   }
   if (p.final_state) {
     __syncthreads();
@@ -246,10 +271,20 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
 
 int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   if (p.nwalk < 2 || (p.nwalk & 1) || p.nwalk > 1024 || p.nens < 1) return (int)cudaErrorInvalidValue;
-  const size_t small = (size_t)p.nwalk * (3 * p.d + 6) * 8 + (size_t)p.nwalk * 4 * 4 + 64;
+  // shared memory: per-walker state, then SB steps' worth of pre-drawn randomness (44 bytes per walker per step),
+  // then -- if it still fits -- the scaled training set
+  const size_t cap = 200 * 1024;
+  const size_t state = (size_t)p.nwalk * (3 * p.d + 3) * 8 + (size_t)p.nwalk * 4 + 64;
+  const size_t per_step = (size_t)p.nwalk * 44;
   const size_t xs_bytes = (size_t)(p.d + 1) * p.Npad * 8;
-  int xs_in_smem = (small + xs_bytes <= 200 * 1024) ? 1 : 0;
-  const size_t smem = small + (xs_in_smem ? xs_bytes : 0);
+  if (state + per_step > cap) return (int)cudaErrorInvalidValue;
+  int xs_in_smem = (state + per_step + xs_bytes <= cap) ? 1 : 0;
+  const size_t room = cap - state - (xs_in_smem ? xs_bytes : 0);
+  int SB = (int)(room / per_step);
+  if (SB > 32) SB = 32;
+  if (SB > p.nsteps) SB = p.nsteps;
+  if (SB < 1) SB = 1;
+  const size_t smem = state + (size_t)SB * per_step + (xs_in_smem ? xs_bytes : 0);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -259,7 +294,7 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   int Ns = p.nwalk / 2;
   int nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : 8;
   cudaMemsetAsync(p.naccept, 0, sizeof(int) * (size_t)p.nens * p.nwalk, st);
-  sampler_kernel<<<p.nens, nwarps * 32, smem, st>>>(p, xs_in_smem);
+  sampler_kernel<<<p.nens, nwarps * 32, smem, st>>>(p, xs_in_smem, SB);
   if (launches) ++*launches;
   return (int)cudaGetLastError();
 }
