@@ -139,7 +139,7 @@ def run_reference(args):
                                        "george predict+BAPE, all BLAS threads" % nq},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -255,9 +255,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) belong on stderr: stdout carries
-        # exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     X, y, logM, mean = make_problem()
@@ -389,10 +386,27 @@ def run_gpu(args):
                                             "measured by tools/fp64_pipe_probe is 37.0 TFLOP/s"},
                 "cpu_baseline": cpu,
                 "bape_iteration": bape}
-        print(json.dumps(line))
+        emit_line(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    """The ONE JSON line goes to the process's real stdout; everything else libraries print to fd 1 (NCCL's
+    "NCCL version ..." banner, for one) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the rest of the run (native libraries print there too)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
