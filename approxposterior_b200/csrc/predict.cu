@@ -566,10 +566,15 @@ predict_var_group_kernel(const __grid_constant__ PredictParams p, const int G) {
 // ---------------------------------------------------------------------------------------------
 constexpr int MEAN_THREADS = 256;
 constexpr int MEAN_QPT = 2;                       // queries per thread
+// D > 0: input dimensionality known at compile time -- the thread's scaled query coordinates live in registers and
+// the dimension loop is unrolled, which halves the shared-memory wavefronts per (query, point) pair (the kernel was
+// at 67 % of the DFMA peak; N=2048, d=5: 16.0 -> 14.7 ms, 72 %).  D == 0: any d, coordinates re-read from shared
+// memory inside the loop.
+template <int D>
 __global__ void __launch_bounds__(MEAN_THREADS)
 predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
   extern __shared__ __align__(16) double sm[];
-  const int d = p.d, Npad = p.Npad;
+  const int d = (D > 0) ? D : p.d, Npad = p.Npad;
   double* xs = sm;                                // [d+1][JCH]
   double* qs = sm + (size_t)(d + 1) * JCH;        // [d][MEAN_QPT*MEAN_THREADS]
   __shared__ double etab[64];
@@ -585,6 +590,14 @@ predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
       long long q = q0 + m;
       qs[i * QB + m] = (q < p.Q) ? p.Xq[q * d + i] * p.qscale[i] : 0.0;
     }
+    double qv[MEAN_QPT][D > 0 ? D : 1];
+    if (D > 0) {
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < MEAN_QPT; ++u)
+#pragma unroll
+        for (int i = 0; i < D; ++i) qv[u][i] = qs[i * QB + u * MEAN_THREADS + tid];
+    }
     double acc[MEAN_QPT] = {};
     for (int j0 = 0; j0 < Npad; j0 += JCH) {
       const int jn = min(JCH, Npad - j0);
@@ -597,23 +610,40 @@ predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
       const double* al = xs + (size_t)d * JCH;
       for (int j = 0; j < jn; j += 4) {
         double s[MEAN_QPT][4] = {};
-        for (int i = 0; i < d; ++i) {
-          const double* xr = xs + i * JCH + j;
-          const double x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
+        if (D > 0) {
 #pragma unroll
-          for (int u = 0; u < MEAN_QPT; ++u) {
-            const double qv = qs[i * QB + u * MEAN_THREADS + tid];
-            double d0 = x0 - qv, d1 = x1 - qv, d2 = x2 - qv, d3 = x3 - qv;
-            s[u][0] = fma(d0, d0, s[u][0]); s[u][1] = fma(d1, d1, s[u][1]);
-            s[u][2] = fma(d2, d2, s[u][2]); s[u][3] = fma(d3, d3, s[u][3]);
+          for (int i = 0; i < D; ++i) {
+            const double2 xa = *reinterpret_cast<const double2*>(xs + i * JCH + j);       // JCH, j multiples of 4
+            const double2 xb = *reinterpret_cast<const double2*>(xs + i * JCH + j + 2);
+#pragma unroll
+            for (int u = 0; u < MEAN_QPT; ++u) {
+              const double qq = qv[u][i];
+              const double d0 = xa.x - qq, d1 = xa.y - qq, d2 = xb.x - qq, d3 = xb.y - qq;
+              s[u][0] = fma(d0, d0, s[u][0]); s[u][1] = fma(d1, d1, s[u][1]);
+              s[u][2] = fma(d2, d2, s[u][2]); s[u][3] = fma(d3, d3, s[u][3]);
+            }
+          }
+        } else {
+          for (int i = 0; i < d; ++i) {
+            const double* xr = xs + i * JCH + j;
+            const double x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
+#pragma unroll
+            for (int u = 0; u < MEAN_QPT; ++u) {
+              const double qq = qs[i * QB + u * MEAN_THREADS + tid];
+              double d0 = x0 - qq, d1 = x1 - qq, d2 = x2 - qq, d3 = x3 - qq;
+              s[u][0] = fma(d0, d0, s[u][0]); s[u][1] = fma(d1, d1, s[u][1]);
+              s[u][2] = fma(d2, d2, s[u][2]); s[u][3] = fma(d3, d3, s[u][3]);
+            }
           }
         }
+        const double2 aa = *reinterpret_cast<const double2*>(al + j);
+        const double2 ab = *reinterpret_cast<const double2*>(al + j + 2);
 #pragma unroll
         for (int u = 0; u < MEAN_QPT; ++u) {
-          acc[u] = fma(exp_neg(s[u][0], etab), al[j], acc[u]);
-          acc[u] = fma(exp_neg(s[u][1], etab), al[j + 1], acc[u]);
-          acc[u] = fma(exp_neg(s[u][2], etab), al[j + 2], acc[u]);
-          acc[u] = fma(exp_neg(s[u][3], etab), al[j + 3], acc[u]);
+          acc[u] = fma(exp_neg(s[u][0], etab), aa.x, acc[u]);
+          acc[u] = fma(exp_neg(s[u][1], etab), aa.y, acc[u]);
+          acc[u] = fma(exp_neg(s[u][2], etab), ab.x, acc[u]);
+          acc[u] = fma(exp_neg(s[u][3], etab), ab.y, acc[u]);
         }
       }
     }
@@ -806,16 +836,32 @@ int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, in
   if (JCH > p.Npad) JCH = p.Npad;
   if (JCH < 4) return (int)cudaErrorInvalidValue;
   const size_t smem = (size_t)(p.d + 1) * JCH * 8 + qs_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(predict_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   long long ntiles = (p.Q + QB - 1) / QB;
   long long cap = (long long)num_sms * 2;
   int grid = (int)(ntiles < cap ? ntiles : cap);
-  predict_mean_kernel<<<grid, MEAN_THREADS, smem, st>>>(p, JCH);
+  cudaError_t e = cudaSuccess;
+#define APGP_MEAN_LAUNCH(DD)                                                                                         \
+  do {                                                                                                               \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      e = cudaFuncSetAttribute(predict_mean_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);  \
+      if (e != cudaSuccess) return (int)e;                                                                           \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    predict_mean_kernel<DD><<<grid, MEAN_THREADS, smem, st>>>(p, JCH);                                             \
+  } while (0)
+  switch (p.d) {
+    // d <= 2: the exponential dominates and the generic kernel measured 2 % faster (5.85 vs 5.96 ms, N=1024, d=2)
+    case 3: APGP_MEAN_LAUNCH(3); break;
+    case 4: APGP_MEAN_LAUNCH(4); break;
+    case 5: APGP_MEAN_LAUNCH(5); break;
+    case 6: APGP_MEAN_LAUNCH(6); break;
+    case 7: APGP_MEAN_LAUNCH(7); break;
+    case 8: APGP_MEAN_LAUNCH(8); break;
+    case 10: APGP_MEAN_LAUNCH(10); break;
+    default: APGP_MEAN_LAUNCH(0); break;
+  }
+#undef APGP_MEAN_LAUNCH
   if (launches) ++*launches;
   return (int)cudaGetLastError();
 }
