@@ -349,7 +349,7 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
   }
   int nl = 0;
   if (o->want_var) {
-    const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d);
+    const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d, Q);
     if (G > 1) {
       CUI(h->scratch.reserve(predict_group_scratch_bytes(h->Npad, h->num_sms, G)));
       CUI(h->g_arrive.reserve(sizeof(int) * ((h->num_sms + G - 1) / G)));

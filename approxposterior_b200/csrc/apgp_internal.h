@@ -42,7 +42,7 @@ int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, in
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant);
 // grouped 256x64 kernel: G CTAs share one query tile so the K* panels in flight stay in L2 (predict.cu).
 // requested < 0: automatic choice; returns 1 when grouping is off / not applicable
-int predict_group_size(int Npad, int num_sms, int variant, int requested, int d);
+int predict_group_size(int Npad, int num_sms, int variant, int requested, int d, long long Q);
 void predict_group_plan(int Npad, int num_sms, int G, int d, int* tab /*[4*128]*/);
 size_t predict_group_scratch_bytes(int Npad, int num_sms, int G);
 size_t predict_group_part_bytes(int Npad, int num_sms, int G);

@@ -322,9 +322,10 @@ predict_var_group_kernel(const __grid_constant__ PredictParams p, const int G) {
   const int grp = blockIdx.x / G, rank = blockIdx.x % G;
   const int gs = min(G, (int)gridDim.x - grp * G);      // ranks in my group
   const long long ntiles = (p.Q + BM - 1) / BM;
-  // contiguous share of the tiles, proportional to the group's size
-  const long long t_begin = ntiles * (long long)(grp * G) / gridDim.x;
-  const long long t_end = ntiles * (long long)(grp * G + gs) / gridDim.x;
+  // contiguous share of the tiles, proportional to the group's size; rounding up hands the odd tiles to the first
+  // (full-size) groups -- a single-tile call must not land on the smaller last group
+  const long long t_begin = (ntiles * (long long)(grp * G) + gridDim.x - 1) / gridDim.x;
+  const long long t_end = (ntiles * (long long)(grp * G + gs) + gridDim.x - 1) / gridDim.x;
   const int sl0 = BM * rank / gs, sl1 = BM * (rank + 1) / gs;                                            // my query slice
   int* arrive = p.grp_arrive + grp;
   // partial sums are kept per 64-column block (mean) and per block-row (variance) and added in block order by the
@@ -753,29 +754,47 @@ double plan_group_split(int nblk, int gs, int d, int* owner2, int* owner1) {
   return mx * gs / tot;
 }
 
-int predict_group_size(int Npad, int num_sms, int variant, int requested, int d) {
+int predict_group_size(int Npad, int num_sms, int variant, int requested, int d, long long Q) {
   if (variant != 2 || Npad / 64 > GROUP_MAX_BLOCKS) return 1;
   const int nblk = Npad / 64;
   int G = requested;
   if (G < 0) {
-    // auto.  Gmin = smallest group whose panels being READ (one of the two buffers per group) fit ~80 MB of L2
-    // (measured at N = 2048: G = 8 keeps the speed of one tile per CTA with 8.8x less DRAM traffic).  Among
-    // Gmin/2 .. 64 take the group size with the best balanced split (a group waits for its slowest rank every
-    // tile: N = 1536 with G = 8 is 9 % imbalanced, G = 6 is exact); ties go to the smallest G >= Gmin.
-    if (Npad < 1024) return 1;                      // below, the 148 one-tile panels already (nearly) fit
-    int Gmin = 2;
-    while (Gmin < 64 && (size_t)((num_sms + Gmin - 1) / Gmin) * 256 * Npad * 8 > ((size_t)80 << 20)) ++Gmin;
     int o2[GROUP_MAX_BLOCKS], o1[GROUP_MAX_BLOCKS];
+    // (a) throughput regime.  Gmin = smallest group whose panels being READ (one of the two buffers per group) fit
+    // ~80 MB of L2 (measured at N = 2048: G = 8 keeps the speed of one tile per CTA with 8.8x less DRAM traffic).
+    // Among Gmin/2 .. 64 take the group size with the best balanced split (a group waits for its slowest rank
+    // every tile: N = 1536 with G = 8 is 9 % imbalanced, G = 6 is exact); ties go to the smallest G >= Gmin.
+    // Below N = 1024 the 148 one-tile panels already (nearly) fit: no grouping.
     int bestG = 1; double bestS = 1e30;
-    for (int g = (Gmin / 2 > 2 ? Gmin / 2 : 2); g <= 64 && 2 * g <= nblk; ++g) {
-      double imb = plan_group_split(nblk, g, d, o2, o1);
-      const int tail = num_sms % g;                 // a smaller last group: weigh its imbalance by its share of the SMs
-      if (tail > 1) imb = (imb * (num_sms - tail) + plan_group_split(nblk, tail, d, o2, o1) * tail) / num_sms;
-      else if (tail == 1) imb += 1.0 / num_sms;     // a lone CTA does whole tiles: fine, but it cannot share a panel
-      const double score = imb + (g < Gmin ? 0.005 : 0.0) + 1e-4 * g;   // L2 fit is worth 0.5 % of balance; then small G
-      if (score < bestS) { bestS = score; bestG = g; }
+    int Gmin = 1;
+    if (Npad >= 1024) {
+      Gmin = 2;
+      while (Gmin < 64 && (size_t)((num_sms + Gmin - 1) / Gmin) * 256 * Npad * 8 > ((size_t)80 << 20)) ++Gmin;
+      for (int g = (Gmin / 2 > 2 ? Gmin / 2 : 2); g <= 64 && 2 * g <= nblk; ++g) {
+        double imb = plan_group_split(nblk, g, d, o2, o1);
+        const int tail = num_sms % g;               // a smaller last group: weigh its imbalance by its share of the SMs
+        if (tail > 1) imb = (imb * (num_sms - tail) + plan_group_split(nblk, tail, d, o2, o1) * tail) / num_sms;
+        else if (tail == 1) imb += 1.0 / num_sms;   // a lone CTA does whole tiles: fine, but it cannot share a panel
+        const double score = imb + (g < Gmin ? 0.005 : 0.0) + 1e-4 * g;   // L2 fit is worth 0.5 % of balance; then small G
+        if (score < bestS) { bestS = score; bestG = g; }
+      }
     }
-    if (getenv("APGP_DEBUG_GROUP")) fprintf(stderr, "[apgp] Npad=%d nblk=%d Gmin=%d -> G=%d (score %.4f)\n", Npad, nblk, Gmin, bestG, bestS);
+    // (b) latency regime: a call with fewer query tiles than would fill half the GPU (optimiser rounds, refinement
+    // passes: a handful of queries) spreads each tile over as many CTAs as the balance allows -- one 256-query tile
+    // at N = 2048 is 32 block-rows for ONE CTA otherwise.
+    const long long ntiles = (Q + 255) / 256;
+    if (ntiles * bestG * 2 <= num_sms && nblk >= 4) {
+      long long cap = num_sms / ntiles;
+      if (cap > 64) cap = 64;
+      if (cap > nblk / 2) cap = nblk / 2;
+      int fillG = bestG; double fillS = (bestG > 1) ? plan_group_split(nblk, bestG, d, o2, o1) / bestG : 1.0;
+      for (int g = bestG + 1; g <= (int)cap; ++g) {
+        const double t = plan_group_split(nblk, g, d, o2, o1) / g;      // time per tile ~ imbalance / ranks
+        if (t < fillS * 0.97) { fillS = t; fillG = g; }
+      }
+      bestG = fillG;
+    }
+    if (getenv("APGP_DEBUG_GROUP")) fprintf(stderr, "[apgp] Npad=%d nblk=%d Q=%lld Gmin=%d -> G=%d\n", Npad, nblk, Q, Gmin, bestG);
     return bestG;
   }
   while (G > 1 && 2 * G > nblk) --G;              // every rank needs block-rows from both ends to balance

@@ -377,7 +377,8 @@ def test_sampler_argument_errors_are_reported():
 
 
 @pytest.mark.parametrize("N,d,Q,group", [(1024, 2, 40000, -1), (2048, 5, 70001, 16), (2048, 5, 70001, 8),
-                                         (1100, 3, 30011, 6), (1100, 3, 700, 4), (4096, 2, 20000, -1)])
+                                         (1100, 3, 30011, 6), (1100, 3, 700, 4), (4096, 2, 20000, -1),
+                                         (2048, 5, 5, -1), (512, 2, 300, -1), (300, 3, 1, -1)])
 def test_grouped_variance_kernel_matches_one_tile_per_cta(N, d, Q, group):
     """G CTAs sharing one query tile (L2-resident K* panels) must reproduce the one-tile-per-CTA kernel.  The variance
     agrees to ~1e-15; the mean adds the same per-column terms in a different order, so it agrees to the rounding of a
