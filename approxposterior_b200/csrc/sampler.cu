@@ -12,9 +12,12 @@
 // Random draws come from Philox4x32-10, or from replay buffers recorded by the CPU oracle so
 // that chains can be compared draw-for-draw.
 #include "apgp_internal.h"
+#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace apgp {
 namespace {
+namespace cg = cooperative_groups;
 
 struct Smem {
   double* xs;      // [d+1][Npad] (alphaA is row d) or null when it does not fit
@@ -77,10 +80,11 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
   }
 }
 
-__device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np) {
+// rows [r0, np) of sm.q (r0 even)
+__device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np, int r0 = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int d = p.d, Npad = p.Npad;
-  for (int i0 = 2 * warp; i0 < np; i0 += 2 * nwarps) {
+  for (int i0 = r0 + 2 * warp; i0 < np; i0 += 2 * nwarps) {
     const int i1 = (i0 + 1 < np) ? i0 + 1 : i0;
     const int ok0 = sm.ok[i0], ok1 = sm.ok[i1];
     __syncwarp();
@@ -117,9 +121,17 @@ __device__ __forceinline__ int stage_row(const SamplerParams& p, const Smem& sm,
   return ok;
 }
 
-__global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ SamplerParams p, int xs_in_smem, int SB) {
+// C = CTAs per ensemble (a thread-block cluster when C > 1).  A single ensemble is the reference's own usage
+// (one emcee.EnsembleSampler of 20*ndim walkers, mcmcUtils.py:75) and would otherwise live on ONE SM: with a cluster
+// every CTA keeps a full replica of the ensemble state and of the pre-drawn randomness, proposes / evaluates /
+// accepts its slice of each half-step's walkers, writes the accepted moves into every replica through distributed
+// shared memory, and the cluster meets at one hardware cluster barrier per half-step.  Same draws, same arithmetic
+// per walker: chains are bit-identical to C = 1.
+__global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ SamplerParams p, int xs_in_smem, int SB,
+                                                       int C) {
   extern __shared__ __align__(16) unsigned char raw[];
-  const int e = blockIdx.x, tid = threadIdx.x;
+  const int e = blockIdx.x / C, rank = blockIdx.x % C, tid = threadIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
   const int nw = p.nwalk, d = p.d, Ns = nw / 2, Npad = p.Npad;
   const long W = (long)p.nens * nw;
   Smem sm;
@@ -160,6 +172,11 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
   __syncthreads();
   for (int w = tid; w < nw; w += blockDim.x) { sm.lp[w] = sm.nlp[w]; sm.blob[w] = sm.ok[w] ? p.lnprior_const : NAN; }
   __syncthreads();
+  if (C > 1) cluster.sync();                 // every replica initialised before anyone writes into a peer
+  // my slice of each half-step's Ns proposals (even boundaries: a warp evaluates rows in pairs) and of the walkers
+  // whose chain entries I store
+  const int i_lo = ((Ns * rank) / C) & ~1, i_hi = (rank == C - 1) ? Ns : (((Ns * (rank + 1)) / C) & ~1);
+  const int w_lo = (nw * rank) / C, w_hi = (nw * (rank + 1)) / C;
 
   Philox rng; rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
   const bool replay = p.r_zz != nullptr;
@@ -227,7 +244,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
         const int* sidx = sm.list + ((size_t)s * 2 + split) * Ns;          // walkers being moved
         const int* cidx = sm.list + ((size_t)s * 2 + (split ^ 1)) * Ns;    // the complementary half
         const size_t boff = ((size_t)s * 2 + split) * Ns;
-        for (int i = tid; i < Ns; i += blockDim.x) {
+        for (int i = i_lo + tid; i < i_hi; i += blockDim.x) {
           const double zz = sm.zz[boff + i];
           const double* cs = sm.coords + cidx[sm.rint[boff + i]] * d;
           const double* ss = sm.coords + sidx[i] * d;
@@ -235,36 +252,48 @@ __global__ void __launch_bounds__(256) sampler_kernel(const __grid_constant__ Sa
           sm.ok[i] = stage_row(p, sm, i);
         }
         __syncthreads();
-        eval_rows(p, sm, Ns);
+        eval_rows(p, sm, i_hi, i_lo);
         __syncthreads();
-        for (int i = tid; i < Ns; i += blockDim.x) {
+        for (int i = i_lo + tid; i < i_hi; i += blockDim.x) {
           const int j = sidx[i];
           const double diff = sm.fac[boff + i] + sm.nlp[i] - sm.lp[j];
           if (diff > sm.logu[boff + i]) {
-            for (int c = 0; c < d; ++c) sm.coords[j * d + c] = sm.q[i * d + c];
-            sm.lp[j] = sm.nlp[i];
-            sm.blob[j] = sm.ok[i] ? p.lnprior_const : NAN;
+            const double nl = sm.nlp[i], bl = sm.ok[i] ? p.lnprior_const : NAN;
+            if (C > 1) {
+              for (int r = 0; r < C; ++r) {                    // the move goes into every replica of the state
+                double* rc = cluster.map_shared_rank(sm.coords, r);
+                for (int c = 0; c < d; ++c) rc[j * d + c] = sm.q[i * d + c];
+                cluster.map_shared_rank(sm.lp, r)[j] = nl;
+                cluster.map_shared_rank(sm.blob, r)[j] = bl;
+              }
+            } else {
+              for (int c = 0; c < d; ++c) sm.coords[j * d + c] = sm.q[i * d + c];
+              sm.lp[j] = nl;
+              sm.blob[j] = bl;
+            }
             atomicAdd(&p.naccept[(size_t)e * nw + j], 1);
           }
         }
-        __syncthreads();
+        if (C > 1) cluster.sync(); else __syncthreads();
       }
       if ((step + 1) % p.thin == 0) {
         const long srow = (step + 1) / p.thin - 1;
-        for (int idx = tid; idx < nw * d; idx += blockDim.x)
+        for (int idx = w_lo * d + tid; idx < w_hi * d; idx += blockDim.x)
           p.chain[(srow * W + (size_t)e * nw) * d + idx] = sm.coords[idx];
-        for (int w = tid; w < nw; w += blockDim.x) {
+        for (int w = w_lo + tid; w < w_hi; w += blockDim.x) {
           p.logp[srow * W + (size_t)e * nw + w] = sm.lp[w];
           p.blob[srow * W + (size_t)e * nw + w] = sm.blob[w];
         }
+        if (C > 1) cluster.sync();           // my reads of the replica finish before a peer's next accepted move lands
       }
       // no sync needed: the next writes to coords/lp/blob happen after two more __syncthreads
     }
   }
-  if (p.final_state) {
+  if (p.final_state && rank == 0) {
     __syncthreads();
     for (int idx = tid; idx < nw * d; idx += blockDim.x) p.final_state[(size_t)e * nw * d + idx] = sm.coords[idx];
   }
+  if (C > 1) cluster.sync();                 // no replica may disappear while a peer can still write into it
 }
 
 }  // namespace
@@ -292,9 +321,32 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
     attr = true;
   }
   int Ns = p.nwalk / 2;
-  int nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : 8;
+  // CTAs per ensemble: clusters only pay when there are few ensembles (the grid would not fill the GPU anyway) and a
+  // half-step carries enough work to amortise the cluster barrier: >= 8 proposals per CTA and >= 6000 kernel
+  // evaluations per CTA per half-step (measured, tools/bench_single_ensemble.py: 100 walkers at N = 500 / 1000 gain
+  // 1.3x / 1.45x with C = 4, 40 walkers at N = 90 lose 20 %).  APGP_SAMPLER_CLUSTER overrides (1, 2, 4, 8) for A/B runs.
+  int C = 1;
+  if (p.nens <= 32) {
+    for (int c = 8; c >= 2; c >>= 1)
+      if (Ns / c >= 8 && (long long)Ns * p.N / c >= 6000) { C = c; break; }
+  }
+  if (const char* cv = getenv("APGP_SAMPLER_CLUSTER")) { int c = atoi(cv); if (c == 1 || c == 2 || c == 4 || c == 8) C = c; }
+  while (C > 1 && Ns / C < 2) C >>= 1;
+  // one warp per pair of proposals of a CTA's slice (a warp evaluates two rows per pass), 8..32 warps: a single large
+  // ensemble lives on few SMs, so its parallelism is warps (APGP_SAMPLER_WARPS overrides, for A/B runs)
+  const int pairs = ((Ns + C - 1) / C + 1) / 2;
+  int nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : (pairs < 8 ? 8 : (pairs > 32 ? 32 : pairs));
+  if (const char* wv = getenv("APGP_SAMPLER_WARPS")) { int w = atoi(wv); if (w >= 1 && w <= 32) nwarps = w; }
   cudaMemsetAsync(p.naccept, 0, sizeof(int) * (size_t)p.nens * p.nwalk, st);
-  sampler_kernel<<<p.nens, nwarps * 32, smem, st>>>(p, xs_in_smem, SB);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.nens * C)); cfg.blockDim = dim3((unsigned)(nwarps * 32));
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = (unsigned)C; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, sampler_kernel, p, xs_in_smem, SB, C);
+  if (le != cudaSuccess) return (int)le;
   if (launches) ++*launches;
   return (int)cudaGetLastError();
 }

@@ -403,3 +403,29 @@ def test_grouped_variance_kernel_matches_one_tile_per_cta(N, d, Q, group):
         assert torch.equal(fin, torch.isfinite(u1))
         assert float((u1[fin] - u0[fin]).abs().max()) <= mu_tol + 1e-9
     gp.set_group(0)
+
+
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+def test_sampler_cluster_replicas_give_the_same_chain(cluster, monkeypatch):
+    """A thread-block cluster per ensemble (state replicated in every CTA's shared memory, accepted moves written to
+    all replicas through DSMEM, one cluster barrier per half-step) must reproduce the single-CTA chain bit for bit,
+    with Philox draws and with replayed draws."""
+    from oracle.sampler_oracle import gpll_batch, stretch_move_oracle
+    X, y, logM, _ = synthetic_gp_problem(300, 3, seed=12)
+    gp, orc = make_pair(X, y, logM)
+    bounds = [(-5.0, 5.0)] * 3
+    rng = np.random.default_rng(4)
+    p0 = rng.uniform(-3, 3, size=(2 * 60, 3))                 # two ensembles of 60 walkers
+    monkeypatch.setenv("APGP_SAMPLER_CLUSTER", "1")
+    a = gp.run_ensembles(y, p0, 120, bounds, nens=2, seed=5, thin=3)
+    monkeypatch.setenv("APGP_SAMPLER_CLUSTER", str(cluster))
+    b = gp.run_ensembles(y, p0, 120, bounds, nens=2, seed=5, thin=3)
+    for k in ("chain", "log_prob", "blobs", "naccepted"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    rs = np.random.RandomState(3)
+    q0 = rs.uniform(-2, 2, size=(24, 3))
+    lo, hi = np.full(3, -5.0), np.full(3, 5.0)
+    ref = stretch_move_oracle(lambda q: gpll_batch(orc, y, q, lo, hi), q0, 40, rng=rs, record=True)
+    out = gp.run_ensembles(y, q0, 40, bounds, nens=1, replay={k: ref[k][None] for k in ("inds", "zz", "rint", "logu")})
+    np.testing.assert_allclose(out["chain"], ref["chain"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(out["naccepted"], ref["naccepted"])
