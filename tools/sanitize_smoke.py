@@ -47,4 +47,11 @@ q = rng.uniform(-5, 5, size=(3000, d))
 gp.predict_utility(y, q, "bape", bounds=[(-5, 5)] * d)
 gp.set_group(4)
 gp.predict_utility(y, q[:300], "agp", bounds=[(-5, 5)] * d)
+# latency regime of the grouped kernel (few tiles -> many CTAs per tile) and the sampler as a thread-block cluster
+gp.set_group(-1)
+gp.predict_utility(y, q[:5], "bape", bounds=[(-5, 5)] * d)
+os.environ["APGP_SAMPLER_CLUSTER"] = "4"
+p0 = rng.uniform(-5, 5, size=(64, d))
+gp.run_ensembles(y, p0, 30, [(-5, 5)] * d, nens=1, seed=3, thin=2)
+del os.environ["APGP_SAMPLER_CLUSTER"]
 print("sanitize_smoke ok")
