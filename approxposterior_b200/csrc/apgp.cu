@@ -670,6 +670,15 @@ int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out) {
   CU(cudaStreamSynchronize(h->stream));
   return APGP_OK;
 }
+int apgp_debug_group_plan(int N, int num_sms, int d, long long Q, int requested, int* G_out, int* tab512) {
+  // host-only: the work split the grouped variance kernel would use (no device needed; exercised by the CPU tests)
+  if (!G_out || N < 1 || num_sms < 1 || d < 1) return fail(APGP_ERR_ARG, "apgp_debug_group_plan");
+  const int Npad = (N + 63) / 64 * 64;
+  const int G = predict_group_size(Npad, num_sms, 2, requested, d, Q);
+  *G_out = G;
+  if (tab512 && G > 1) predict_group_plan(Npad, num_sms, G, d, tab512);
+  return APGP_OK;
+}
 int apgp_debug_read_prof(long long* out16) { return out16 ? read_prof(out16) : APGP_ERR_ARG; }
 int apgp_get_linv(apgp_handle* h, double* linv) { return get_square(h, h->Linv, linv); }
 int apgp_get_chol(apgp_handle* h, double* L) { return get_square(h, h->K, L); }

@@ -400,3 +400,51 @@ def test_device_optimizer_option_mapping():
     assert (o.method, o.adaptive, o.xtol, o.ftol, o.maxiter, o.maxfev) == (1, 0, 1e-4, 1e-8, _lib.OPT_INF, -1)
     with pytest.raises(KeyError):
         GP._opt_opts("l-bfgs-b", None)
+
+
+# ---------------------------------------------------------------- grouped variance kernel: host-side work split
+def _group_plan(N, Q, requested=-1, sms=148, d=5):
+    from approxposterior_b200 import _lib
+    lib = _lib.load()
+    G = ctypes.c_int()
+    tab = np.zeros(512, dtype=np.int32)
+    assert lib.apgp_debug_group_plan(N, sms, d, Q, requested, ctypes.byref(G), tab.ctypes.data) == 0
+    return G.value, tab
+
+
+@pytest.mark.parametrize("N,G_expected", [(256, 1), (512, 1), (1024, 4), (1536, 6), (2048, 8), (3000, 12), (4096, 16),
+                                          (8192, 32)])
+def test_group_plan_throughput_regime(N, G_expected):
+    """2^20 queries: group size by L2 footprint and balance; every block-row / column block owned by exactly one rank
+    of the group; load (block-row ib costs ib + 1, a column block (2d+12)/64) within 1 % of the mean."""
+    G, tab = _group_plan(N, 1 << 20)
+    assert G == G_expected
+    if G == 1:
+        return
+    nblk = (N + 63) // 64
+    tail = 148 % G
+    for base, gs in ((0, G), (256, tail if tail > 0 else G)):
+        own2, own1 = tab[base:base + nblk], tab[base + 128:base + 128 + nblk]
+        assert own2.min() >= 0 and own2.max() < gs and own1.min() >= 0 and own1.max() < gs
+        if 2 * gs > nblk:
+            continue                                         # a tiny last group may be unbalanced; it is weighted in
+        load = np.zeros(gs)
+        for ib in range(nblk):
+            load[own2[ib]] += ib + 1
+        for cb in range(nblk):
+            load[own1[cb]] += (2 * 5 + 12) / 64.0
+        assert load.max() / load.mean() < 1.011, (N, gs, load)
+
+
+def test_group_plan_latency_regime_and_overrides():
+    # a handful of queries: the single tile is spread over as many CTAs as the balance allows (nblk / 2 at most)
+    assert _group_plan(2048, 5)[0] == 16
+    assert _group_plan(1024, 5)[0] == 8
+    assert _group_plan(512, 300)[0] == 4
+    assert _group_plan(100, 5)[0] == 1                       # 2 block-rows: nothing to share
+    # many tiles at small N: one tile per CTA
+    assert _group_plan(512, 1 << 20)[0] == 1
+    # explicit requests are clamped to nblk / 2 and 64; 0 is handled by the caller (grouping off)
+    assert _group_plan(2048, 1 << 20, requested=16)[0] == 16
+    assert _group_plan(1024, 1 << 20, requested=64)[0] == 8
+    assert _group_plan(8192, 1 << 20, requested=64)[0] == 64
