@@ -43,7 +43,7 @@ __device__ __forceinline__ double cta_sum(double v, double* red /*[OW]*/) {
 }
 
 // The objectives are __noinline__ on purpose: the optimisers call them from ~20 places, and inlining every copy
-// made 600 KB of SASS per kernel whose instruction fetches dominated the run time (profiles/r01_optimizers.md).
+// made 600 KB of SASS per kernel (37 600 instructions; 6 400 now, +11 % speed: profiles/r01_optimizers.md).
 // A non-inlined member cannot see that the struct's pointers are shared-memory addresses, so the structs carry
 // OFFSETS (in doubles) from the dynamic shared-memory base and eval() rebuilds typed shared pointers from them.
 
