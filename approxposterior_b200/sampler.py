@@ -22,32 +22,34 @@ class AutocorrError(Exception):
         super(AutocorrError, self).__init__(*args, **kwargs)
 
 
-def _next_pow_two(n):
-    i = 1
-    while i < n:
-        i = i << 1
-    return i
-
-
-def _acf_1d_batch(x):
-    """Normalised autocorrelation of every column of x[n_t, n_w] via FFT.  Large chains (the device
-    sampler produces tens of thousands of walkers) are transformed with torch.fft on the GPU."""
+def _mean_norm_acf(x):
+    """Mean over walkers of each walker's normalised autocorrelation function, x[n_t, n_w] -> [n_t]
+    (what emcee's ``integrated_time`` averages).  Linear autocorrelation by zero-padded FFT; because the inverse
+    transform is linear, the per-walker normalisation acf_w[0] = sum_t x_w(t)^2 is applied to the power spectra and
+    ONE inverse transform serves all walkers.  Large chains (the device sampler produces tens of thousands of
+    walkers) are transformed with torch.fft on the GPU when torch is already loaded."""
+    import sys
     n_t = x.shape[0]
-    n = _next_pow_two(n_t)
-    if x.size >= (1 << 22):
+    if x.size >= (1 << 22) and "torch" in sys.modules:
         try:
             import torch
             if torch.cuda.is_available():
                 t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
                 t = t - t.mean(dim=0, keepdim=True)
-                f = torch.fft.rfft(t, n=2 * n, dim=0)
-                acf = torch.fft.irfft(f * f.conj(), n=2 * n, dim=0)[:n_t]
-                return (acf / acf[0]).cpu().numpy()
+                c0 = (t * t).sum(dim=0)
+                f = torch.fft.rfft(t, n=2 * n_t, dim=0)
+                p = (f.real ** 2 + f.imag ** 2) / c0
+                return torch.fft.irfft(p.mean(dim=1), n=2 * n_t)[:n_t].cpu().numpy()
         except Exception:
             pass
-    f = np.fft.fft(x - np.mean(x, axis=0), n=2 * n, axis=0)
-    acf = np.fft.ifft(f * np.conjugate(f), axis=0)[:n_t].real
-    return acf / acf[0]
+    from scipy import fft as sfft
+    n = sfft.next_fast_len(2 * n_t, real=True)
+    xc = np.ascontiguousarray((x - np.mean(x, axis=0)).T)            # [n_w, n_t]: transforms along contiguous rows
+    c0 = np.einsum("wt,wt->w", xc, xc)
+    f = sfft.rfft(xc, n=n, axis=1, workers=-1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = (f.real ** 2 + f.imag ** 2) / c0[:, None]                # a walker that never moved gives nan, as emcee does
+    return sfft.irfft(np.mean(p, axis=0), n=n)[:n_t]
 
 
 def integrated_time(x, c=5, tol=50, quiet=False):
@@ -63,7 +65,7 @@ def integrated_time(x, c=5, tol=50, quiet=False):
     n_t, n_w, n_d = x.shape
     tau_est = np.empty(n_d)
     for d in range(n_d):
-        f = np.mean(_acf_1d_batch(x[:, :, d]), axis=1)
+        f = _mean_norm_acf(x[:, :, d])
         taus = 2.0 * np.cumsum(f) - 1.0
         m = np.arange(len(taus)) < c * taus
         window = np.argmin(m) if np.any(m) else len(taus) - 1
