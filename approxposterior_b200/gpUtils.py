@@ -125,11 +125,12 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
                  and hasattr(gp, "minimize_nll") and gp.can_minimize_nll())
 
     if on_device:
-        res, _, nfev = gp.minimize_nll(np.array(x0s), y, method=method, options=options,
-                                       default_prior=gpHyperPrior is not None)
+        res, fres, nfev = gp.minimize_nll(np.array(x0s), y, method=method, options=options,
+                                          default_prior=gpHyperPrior is not None)
         res = list(res)
         optimizeGP.last_stats = dict(batches=1, evals=int(np.sum(nfev)), scheduler="device")
-        mll = list(gp.log_likelihood_batch(np.array(res), y))
+        # the optimiser's own objective value at its optimum IS -log-likelihood there (gpUtils.py:243-247 recomputes it)
+        mll = [(-f if np.isfinite(f) else -np.inf) for f in fres]
     elif use_batch and _opt.supported(method, options):
         # thread-free lock step: SciPy's Powell / Nelder-Mead restated as coroutines (same iterates)
         make = _opt.powell_gen if str(method).lower() == "powell" else _opt.nelder_mead_gen
