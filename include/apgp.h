@@ -127,7 +127,9 @@ typedef struct apgp_sampler_opts {
 
 /* emcee.EnsembleSampler(nwalkers, ndim, log_prob_fn=_gpll).sample(initial_state, iterations)
  * as driven from approx.py:839-847.  p0 [nens*nwalkers][d];
- * chain [nsteps/thin][nens*nwalkers][d], logp/blob [nsteps/thin][nens*nwalkers], naccept [nens*nwalkers] int32. */
+ * chain [nsteps/thin][nens*nwalkers][d], logp/blob [nsteps/thin][nens*nwalkers], naccept [nens*nwalkers] int32.
+ * One CTA per ensemble, or -- few ensembles with enough work per half-step -- a thread-block cluster of 2/4/8 CTAs
+ * per ensemble (same chains bit for bit).  nwalkers * (24 ndim + 72) bytes must fit one CTA's shared memory. */
 int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double* p0, double* chain, double* logp,
                      double* blob, int* naccept, int on_host);
 
@@ -178,7 +180,8 @@ int apgp_debug_read_prof(long long* out16);
  * 2 = 256x64 (default).  Call before factorize. */
 int apgp_set_variant(apgp_handle* h, int variant);
 /* CTAs that share one query tile in the 256x64 variance kernel (their K* panels then stay in L2 instead of streaming
- * through HBM): 0 = one tile per CTA, -1 = automatic (by training-set size), 2..64 = fixed group size. */
+ * through HBM): 0 = one tile per CTA, -1 = automatic (by training-set size, and by the number of query tiles of the
+ * call: a few-tile call is spread over more CTAs for latency), 2..64 = fixed group size.  Default -1. */
 int apgp_set_group(apgp_handle* h, int group);
 
 #ifdef __cplusplus
