@@ -448,3 +448,58 @@ def test_group_plan_latency_regime_and_overrides():
     assert _group_plan(2048, 1 << 20, requested=16)[0] == 16
     assert _group_plan(1024, 1 << 20, requested=64)[0] == 8
     assert _group_plan(8192, 1 << 20, requested=64)[0] == 64
+
+
+def test_optimizeGP_device_engine_protocol():
+    """gpUtils.optimizeGP on the device engine: start points drawn as the reference draws them (gpUtils.py:227), ONE
+    minimize_nll call for all restarts, the best restart (by the optimiser's own objective) installed and recomputed;
+    custom hyper-priors, unsupported methods and large training sets stay on the host path."""
+    from approxposterior_b200 import gpUtils
+
+    class FakeGP(object):
+        def __init__(self, fits=True):
+            self.p = np.array([0.0, 1.0, 2.0]); self.calls = []; self.fits = fits; self.recomputed = 0
+
+        def __len__(self):
+            return 3
+
+        def get_parameter_vector(self):
+            return self.p.copy()
+
+        def set_parameter_vector(self, p):
+            self.p = np.asarray(p, dtype=float).copy()
+
+        def recompute(self, quiet=False):
+            self.recomputed += 1
+            return True
+
+        def can_minimize_nll(self):
+            return self.fits
+
+        def minimize_nll(self, P0, y, method="powell", options=None, default_prior=True, evaluate_only=False):
+            self.calls.append(dict(P0=np.array(P0), method=method, options=options, default_prior=default_prior))
+            P0 = np.atleast_2d(P0)
+            res = P0 + 1.0
+            f = np.array([3.0, -7.0, np.inf, 1.0])[:len(P0)]          # restart 1 wins; restart 2 failed
+            return res, f, np.full(len(P0), 11)
+
+        def log_likelihood_batch(self, P, y, return_grad=False):
+            raise AssertionError("the device engine ranks restarts by the optimiser's own objective values")
+
+    y = np.arange(5.0)
+    gp = FakeGP()
+    np.random.seed(9)
+    out = gpUtils.optimizeGP(gp, None, y, nGPRestarts=4, method="powell")
+    np.random.seed(9)
+    expect_x0 = np.array([[np.median(y)] + [np.random.randn() for _ in range(2)] for _ in range(4)])
+    assert out is gp and len(gp.calls) == 1 and gp.recomputed == 1
+    assert np.array_equal(gp.calls[0]["P0"], expect_x0) and gp.calls[0]["default_prior"] is True
+    assert np.array_equal(gp.p, expect_x0[1] + 1.0)
+    assert gpUtils.optimizeGP.last_stats == dict(batches=1, evals=44, scheduler="device")
+    # a custom hyper-prior cannot run inside the kernel: host lock step (which needs log_likelihood_batch -> raises here)
+    with pytest.raises(AssertionError):
+        gpUtils.optimizeGP(FakeGP(), None, y, nGPRestarts=2, gpHyperPrior=lambda p: 0.0)
+    with pytest.raises(AssertionError):
+        gpUtils.optimizeGP(FakeGP(fits=False), None, y, nGPRestarts=2)
+    with pytest.raises(AssertionError):
+        gpUtils.optimizeGP(FakeGP(), None, y, nGPRestarts=2, engine="lockstep")
