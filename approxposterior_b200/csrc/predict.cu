@@ -756,6 +756,9 @@ double plan_group_split(int nblk, int gs, int d, int* owner2, int* owner1) {
 
 int predict_group_size(int Npad, int num_sms, int variant, int requested, int d, long long Q) {
   if (variant != 2 || Npad / 64 > GROUP_MAX_BLOCKS) return 1;
+  // the grouped kernel carries 4.6 KB of static shared memory (ownership tables, kept means) on top of the one-tile
+  // kernel's dynamic layout: from d = 28 the staged queries no longer fit beside the ring -> one tile per CTA
+  if (VarCfg<256, 64, 4, 8>::smem_bytes(d) > 220 * 1024) return 1;
   const int nblk = Npad / 64;
   int G = requested;
   if (G < 0) {

@@ -448,6 +448,9 @@ def test_group_plan_latency_regime_and_overrides():
     assert _group_plan(2048, 1 << 20, requested=16)[0] == 16
     assert _group_plan(1024, 1 << 20, requested=64)[0] == 8
     assert _group_plan(8192, 1 << 20, requested=64)[0] == 64
+    # from d = 28 the grouped kernel's shared-memory layout no longer fits: one tile per CTA, whatever was requested
+    assert _group_plan(2048, 1 << 20, d=27)[0] == 8
+    assert _group_plan(2048, 1 << 20, d=28)[0] == 1 and _group_plan(2048, 5, d=31, requested=16)[0] == 1
 
 
 def test_optimizeGP_device_engine_protocol():
