@@ -346,6 +346,16 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   attrs[0].val.clusterDim.x = (unsigned)C; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, sampler_kernel, p, xs_in_smem, SB, C);
+  if (le != cudaSuccess && C > 1) {
+    // the cluster could not be scheduled (e.g. a partitioned GPU): one CTA per ensemble gives the same chains
+    (void)cudaGetLastError();
+    C = 1;
+    const int pairs1 = (Ns + 1) / 2;
+    nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : (pairs1 < 8 ? 8 : (pairs1 > 32 ? 32 : pairs1));
+    cfg.gridDim = dim3((unsigned)p.nens); cfg.blockDim = dim3((unsigned)(nwarps * 32));
+    attrs[0].val.clusterDim.x = 1;
+    le = cudaLaunchKernelEx(&cfg, sampler_kernel, p, xs_in_smem, SB, C);
+  }
   if (le != cudaSuccess) return (int)le;
   if (launches) ++*launches;
   return (int)cudaGetLastError();
