@@ -1,0 +1,169 @@
+"""The reference's OWN test modules, unmodified, executed through george/emcee shims.
+
+* ``-m gpu`` half: ``approxposterior_b200.compat.install()`` -- ``import george`` / ``import emcee`` inside the
+  reference resolve to the engine, so ``approxposterior/tests/test_*.py`` (reference files, not restatements) run on
+  ``libapgp.so``.  This is what "drops in behind gpUtils.defaultGP" means (gpUtils.py:160-178, approx.py:712-717,
+  839-847).
+* CPU half: the same modules on the oracle-backed shim (``oracle/refshim.py``) -- a second pin of the oracle, this
+  time driven by the reference's own code rather than by this repo's restated drivers.
+
+The reference package is imported from ``/root/reference`` (authoring container) or from ``baseline/_ref`` (the
+``pip install --no-deps --target baseline/_ref`` copy that travels to the GPU box); both are the unmodified v0.4
+sources.  If neither exists the tests skip.
+
+One environment patch, applied to both halves and to nothing else: ``oracle.refshim.scipy_x0_compat`` flattens the 2-D
+``x0`` the reference hands to ``scipy.optimize.minimize`` (utility.py:336,364), which SciPy >= 1.11 rejects and the
+SciPy of the reference's day flattened itself.  It touches only the reference tests that reach ``minimizeObjective``.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_root():
+    forced = os.environ.get("APGP_REFERENCE_ROOT")
+    for cand in ([forced] if forced else ["/root/reference", os.path.join(ROOT, "baseline", "_ref")]):
+        if os.path.isfile(os.path.join(cand, "approxposterior", "tests", "test_GPUtil.py")):
+            return cand
+    return None
+
+
+REF = _reference_root()
+needs_ref = pytest.mark.skipif(REF is None, reason="reference package not available (/root/reference or baseline/_ref)")
+
+# reference test module -> functions; (module, function, needs the SciPy x0 patch)
+CASES = [
+    ("test_GPUtil", "testUtilsGPAmp"), ("test_GPUtil", "testUtilsGPNoAmp"),
+    ("test_InitGP", "testInitGPAmp"), ("test_InitGP", "testInitGPNoAmp"),
+    ("test_OptimizeGP", "testGPOptAmp"), ("test_OptimizeGP", "testGPOptNoAmp"),
+    ("test_Burnin", "testBurnin"), ("test_MCSE", "testMCSE"), ("test_TestFns", "testTestFns"),
+    ("test_Import", "test_import"),
+    ("test_findNewPoint", "testFindNoAmp"), ("test_MAP", "testMAPAmp"),
+    ("test_1DBayesOpt", "test_1DBO"), ("test_2DBayesOpt", "test_2DBO"), ("test_APRun", "testRun"),
+]
+# tests/test_findNewPoint.py:60 (amplitude case) depends on the Nelder-Mead path over a multi-modal surface and is not
+# reproduced by SciPy 1.18 on ANY backend: run, but do not require
+XFAIL = [("test_findNewPoint", "testFindAmp")]
+
+
+def _purge():
+    for name in [n for n in sys.modules if n == "approxposterior" or n.startswith("approxposterior.")]:
+        del sys.modules[name]
+
+
+class _Reference(object):
+    """Context: shims installed, reference importable, module cache isolated, cwd = a scratch directory
+    (the reference's drivers write their .npz caches into the working directory)."""
+
+    def __init__(self, shim, tmpdir):
+        self.shim, self.tmpdir = shim, str(tmpdir)
+
+    def __enter__(self):
+        _purge()
+        self.shim.install()
+        sys.path.insert(0, REF)
+        self.cwd = os.getcwd()
+        os.chdir(self.tmpdir)
+        from oracle.refshim import scipy_x0_compat
+        ut = importlib.import_module("approxposterior.utility")
+        scipy_x0_compat(ut)
+        return self
+
+    def run(self, module, function):
+        mod = importlib.import_module("approxposterior.tests." + module)
+        assert os.path.realpath(mod.__file__).startswith(os.path.realpath(REF)), mod.__file__
+        with np.errstate(all="ignore"):
+            getattr(mod, function)()
+
+    def __exit__(self, *exc):
+        os.chdir(self.cwd)
+        sys.path.remove(REF)
+        self.shim.uninstall()
+        _purge()
+        return False
+
+
+# ------------------------------------------------------------------------------------------ CPU: oracle-backed shim
+@needs_ref
+@pytest.mark.parametrize("module,function", CASES)
+def test_reference_tests_on_oracle_shim(module, function, tmp_path):
+    from oracle import refshim
+    with _Reference(refshim, tmp_path) as ref:
+        ref.run(module, function)
+
+
+@needs_ref
+@pytest.mark.parametrize("module,function", XFAIL)
+def test_reference_optimizer_path_dependent_on_oracle_shim(module, function, tmp_path):
+    from oracle import refshim
+    with _Reference(refshim, tmp_path) as ref:
+        try:
+            ref.run(module, function)
+        except AssertionError:
+            pytest.xfail("optimiser-path dependent golden (SURVEY 4.3)")
+
+
+# ------------------------------------------------------------------------------------------ GPU: engine-backed shim
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("module,function", CASES)
+def test_reference_tests_on_engine(module, function, tmp_path):
+    from approxposterior_b200 import compat
+    import approxposterior_b200._lib as _lib
+    with _Reference(compat, tmp_path) as ref:
+        george = sys.modules["george"]
+        from approxposterior_b200 import GP
+        assert george.GP is GP
+        ref.run(module, function)
+    assert _lib._lib is not None, "libapgp.so was not loaded"
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("module,function", XFAIL)
+def test_reference_optimizer_path_dependent_on_engine(module, function, tmp_path):
+    from approxposterior_b200 import compat
+    with _Reference(compat, tmp_path) as ref:
+        try:
+            ref.run(module, function)
+        except AssertionError:
+            pytest.xfail("optimiser-path dependent golden (SURVEY 4.3)")
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_run_uses_the_engine_for_every_hot_call(tmp_path):
+    """The reference's ApproxPosterior.run (README configuration, shortened) on the engine: the GP object the
+    reference holds is the engine's, the kernels were launched, and the batched _gpll seam of the emcee shim
+    returns what the reference's own scalar _gpll returns."""
+    from approxposterior_b200 import compat, GP
+    with _Reference(compat, tmp_path):
+        import approxposterior as apx
+        from approxposterior import approx, gpUtils, likelihood as lh
+        np.random.seed(57)
+        theta = lh.rosenbrockSample(50)
+        y = np.array([lh.rosenbrockLnlike(t) + lh.rosenbrockLnprior(t) for t in theta])
+        gp = gpUtils.defaultGP(theta, y, white_noise=-12)
+        assert isinstance(gp, GP)
+        ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lh.rosenbrockLnprior, lnlike=lh.rosenbrockLnlike,
+                                    priorSample=lh.rosenbrockSample, bounds=[(-5, 5), (-5, 5)], algorithm="bape")
+        before = gp.launch_count
+        ap.run(m=3, nmax=1, estBurnin=True, nGPRestarts=2, mcmcKwargs={"iterations": 400}, cache=False,
+               samplerKwargs={"nwalkers": 20}, verbose=False, thinChains=False, onlyLastMCMC=True)
+        assert isinstance(ap.gp, GP) and ap.gp.launch_count > 0 and before > 0
+        assert ap.sampler.get_chain().shape == (400, 20, 2)
+        assert ap.theta.shape == (53, 2) and np.all(np.isfinite(ap.y))
+        q = np.vstack([lh.rosenbrockSample(6), [[7.0, 0.0]], [[np.nan, np.nan]]])
+        lp_b, blob_b = ap.sampler.log_prob_fn(q)
+        for i, t in enumerate(q):
+            lp_s, blob_s = ap._gpll(t)
+            if np.isfinite(lp_s):
+                assert abs(lp_b[i] - float(lp_s)) <= 1e-12 * max(1.0, abs(float(lp_s))) and blob_b[i] == blob_s
+            else:
+                assert lp_b[i] == -np.inf and np.isnan(blob_b[i])
+        assert apx.__version__ == "0.4"
