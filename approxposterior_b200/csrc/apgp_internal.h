@@ -6,6 +6,19 @@
 
 namespace apgp {
 
+// cudaFuncSetAttribute applies to the CURRENT device only, and a process may hold handles on several GPUs
+// (apgp_create(device)): remember the opt-in per device ordinal, not per process.
+struct PerDeviceOnce {
+  unsigned long long done[2] = {0ull, 0ull};
+  int dev = -1;
+  // true when the attribute still has to be set on the current device; call mark() after it was set
+  bool needed() {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) { dev = -1; return true; }
+    return !((done[dev >> 6] >> (dev & 63)) & 1ull);
+  }
+  void mark() { if (dev >= 0) done[dev >> 6] |= 1ull << (dev & 63); }
+};
+
 // ---- predict ---------------------------------------------------------------------
 struct PredictParams {
   const double* Xq;        // [Q][d] queries, row-major (device)

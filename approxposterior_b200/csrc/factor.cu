@@ -549,16 +549,16 @@ __global__ void __launch_bounds__(256) append_finish_kernel(double* __restrict__
   }
 }
 
-bool g_attr_done = false;
+PerDeviceOnce g_attr_done;
 int ensure_attrs() {
-  if (g_attr_done) return 0;
+  if (!g_attr_done.needed()) return 0;
   cudaError_t e;
   e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(gemm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(loglik_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); if (e) return (int)e;
-  g_attr_done = true;
+  g_attr_done.mark();
   return 0;
 }
 

@@ -674,13 +674,13 @@ __global__ void __launch_bounds__(OT, 1) minimize_nll_kernel(const __grid_consta
 }
 
 constexpr size_t SMEM_CAP = 220 * 1024;
-bool g_opt_attr = false;
+PerDeviceOnce g_opt_attr;
 int ensure_opt_attrs() {
-  if (g_opt_attr) return 0;
+  if (!g_opt_attr.needed()) return 0;
   cudaError_t e;
   e = cudaFuncSetAttribute(minimize_utility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP); if (e) return (int)e;
   e = cudaFuncSetAttribute(minimize_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP); if (e) return (int)e;
-  g_opt_attr = true;
+  g_opt_attr.mark();
   return 0;
 }
 

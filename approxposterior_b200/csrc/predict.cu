@@ -702,12 +702,12 @@ template <int BM, int BN, int NSTAGE, int NCW = 8>
 int launch_var_t(const PredictParams& p, int num_sms, cudaStream_t st) {
   using C = VarCfg<BM, BN, NSTAGE, NCW>;
   const size_t smem = C::smem_bytes(p.d);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.needed()) {
     cudaError_t e = cudaFuncSetAttribute(predict_var_kernel<BM, BN, NSTAGE, NCW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / C::CTAS_PER_SM);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr.mark();
   }
   long long ntiles = (p.Q + BM - 1) / BM;
   const long long cap = (long long)num_sms * C::CTAS_PER_SM;
@@ -820,12 +820,12 @@ int launch_predict_var_grouped(const PredictParams& p, int num_sms, int G, cudaS
   if (p.Q <= 0) return 0;
   using C = VarCfg<256, 64, 4, 8>;
   const size_t smem = C::smem_bytes(p.d);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.needed()) {
     cudaError_t e = cudaFuncSetAttribute(predict_var_group_kernel<256, 64, 4>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr.mark();
   }
   const int ngroups = (num_sms + G - 1) / G;
   cudaError_t e = cudaMemsetAsync(p.grp_arrive, 0, sizeof(int) * ngroups, st);
@@ -864,11 +864,11 @@ int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, in
   cudaError_t e = cudaSuccess;
 #define APGP_MEAN_LAUNCH(DD)                                                                                         \
   do {                                                                                                               \
-    static bool attr_set = false;                                                                                    \
-    if (!attr_set) {                                                                                                 \
+    static PerDeviceOnce attr;                                                                                       \
+    if (attr.needed()) {                                                                                             \
       e = cudaFuncSetAttribute(predict_mean_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);  \
       if (e != cudaSuccess) return (int)e;                                                                           \
-      attr_set = true;                                                                                               \
+      attr.mark();                                                                                                   \
     }                                                                                                                \
     predict_mean_kernel<DD><<<grid, MEAN_THREADS, smem, st>>>(p, JCH);                                             \
   } while (0)

@@ -314,11 +314,11 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   if (SB > p.nsteps) SB = p.nsteps;
   if (SB < 1) SB = 1;
   const size_t smem = state + (size_t)SB * per_step + (xs_in_smem ? xs_bytes : 0);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.needed()) {
     cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
+    attr.mark();
   }
   int Ns = p.nwalk / 2;
   // CTAs per ensemble: clusters only pay when there are few ensembles (the grid would not fill the GPU anyway) and a

@@ -84,3 +84,31 @@ def test_sharded_equals_single_gpu():
     assert np.array_equal(res[0][3], np.concatenate([h["chain"] for h in halves], axis=1))
     assert np.array_equal(res[0][4], np.concatenate([h["naccepted"] for h in halves]))
     assert res[0][6] == -5.0 and res[0][5][0] == 0
+
+
+def test_two_handles_on_two_devices_in_one_process():
+    """A process may hold GP handles on several GPUs (apgp_create(device)).  The > 48 KB dynamic shared-memory opt-in
+    of every kernel is a per-device function attribute: each device must get it (the guards were
+    process-global, so the second GPU's launches failed with invalid-value).  Same problem on both devices ->
+    identical results, kernel by kernel."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = []
+    rng = np.random.default_rng(2)
+    Xq = rng.uniform(-5, 5, size=(3000, 3))
+    p0 = rng.uniform(-3, 3, size=(24, 3))
+    bounds = [(-5.0, 5.0)] * 3
+    gps = [_make_gp(dev) for dev in (0, 1)]            # both handles alive at once; device 1 used first
+    for gp, y in reversed(gps):
+        mu, var, u = gp.predict_utility(y, Xq, "bape", bounds=bounds)           # predict_var (+ grouped) kernels
+        m2 = gp.predict(y, Xq, return_cov=False)                                # predict_mean
+        ch = gp.run_ensembles(y, p0, 40, bounds, nens=2, seed=9)["chain"]       # sampler
+        P = np.array([gp.get_parameter_vector(), gp.get_parameter_vector() + 0.2])
+        ll, g = gp.log_likelihood_batch(P, y, return_grad=True)                 # loglik_small (+ gradient)
+        xs, fs, _ = gp.minimize_utility(y, Xq[:4], "bape", bounds=bounds, options={"adaptive": True})   # optimisers
+        ps, fn, _ = gp.minimize_nll(P, y, method="powell", options={"maxiter": 1})
+        gl = gp.grad_log_likelihood(y)                                           # tiled GEMM path
+        outs.append((mu, var, u, m2, ch, ll, g, xs, fs, ps, fn, gl))
+    for a, b in zip(*outs):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
