@@ -133,10 +133,15 @@ class GPOracle(object):
         return cho_solve((self._L, True), b, check_finite=False)
 
     def _compute_alpha(self, y):
-        y = np.asarray(y, dtype=np.float64).ravel()
-        if y.size != self._x.shape[0]:
+        if self._alpha is not None and self._alpha_y is y:      # george caches alpha per y as well
+            return self._alpha
+        yv = np.asarray(y, dtype=np.float64).ravel()
+        if yv.size != self._x.shape[0]:
             raise ValueError("dimension mismatch")
-        return self.apply_inverse(y - self.mean)
+        alpha = self.apply_inverse(yv - self.mean)
+        if isinstance(y, np.ndarray) and not y.flags.writeable:
+            self._alpha, self._alpha_y = alpha, y                 # only immutable targets are safe to key by identity
+        return alpha
 
     # ---- george.GP.predict(y, t, return_cov=False, return_var=...) ------------
     def predict(self, y, t, return_cov=False, return_var=False):
