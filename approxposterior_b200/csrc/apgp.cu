@@ -64,6 +64,7 @@ struct apgp_handle {
   double* pin = nullptr;               // pinned host staging for small calls (latency path)
   static constexpr size_t PIN_DOUBLES = 32768;   // 256 KB: [0, PIN/2) inputs, [PIN/2, PIN) outputs
   DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
+  DevBuf gws;                                                // fused cluster-per-restart workspace (chol_group.cuh)
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
   DevBuf o_in, o_x, o_f, o_stats;      // device optimiser staging
   DevBuf g_arrive, g_part, g_plan;     // grouped variance kernel: barrier counters, partial sums, work-split tables
@@ -125,7 +126,7 @@ int apgp_destroy(apgp_handle* h) {
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
                     &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->ap_k, &h->ap_l, &h->ap_u, &h->ap_x, &h->bK,
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
-                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan};
+                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->gws};
   for (DevBuf* b : bufs) b->release();
   if (h->pin) cudaFreeHost(h->pin);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -261,6 +262,11 @@ int apgp_factorize(apgp_handle* h, double* logdet, double* loglik, int* info) {
   CUI(launch_tri_inverse(h->K.as<double>(), h->Dinv.as<double>(), Np, h->Linv.as<double>(), h->work.as<double>(),
                          h->stream, &nl));
   CUI(launch_linvT_matvec(h->Linv.as<double>(), Np, h->r.as<double>(), h->alpha.as<double>(), h->stream)); ++nl;
+  if (!getenv("APGP_NO_REFINE")) {
+    CUI(h->ap_k.reserve((size_t)Np * 8)); CUI(h->ap_l.reserve((size_t)Np * 8));
+    CUI(launch_refine_alpha(h->X.as<double>(), h->y.as<double>(), N, d, Np, h->hyper.as<double>(), h->Linv.as<double>(),
+                            h->alpha.as<double>(), h->ap_k.as<double>(), h->ap_l.as<double>(), h->stream, &nl));
+  }
   { int st_ = pack_predict_operands(h, &nl); if (st_ != APGP_OK) return st_; }
   CU(cudaStreamSynchronize(h->stream));
   h->launches += nl;
@@ -431,14 +437,22 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
   if (P != 1 + (fit_amp ? 1 : 0) + d) return fail(APGP_ERR_ARG, "apgp_loglik_batch: P != 1 + fit_amp + d");
   if (R < 1) return APGP_OK;
   Guard g(h->device);
-  const bool small = loglik_small_smem(N, d) <= 220 * 1024 && !getenv("APGP_LOGLIK_TILED");
+  // three paths: one restart per CTA in shared memory (N <= ~224); one CLUSTER per restart with the matrix in L2
+  // (fused single launch, chol_group.cuh); the multi-launch tiled sequence (APGP_LOGLIK_PATH=tiled, kept for A/B runs)
+  const char* pathv = getenv("APGP_LOGLIK_PATH");
+  const bool force_tiled = getenv("APGP_LOGLIK_TILED") || (pathv && !strcmp(pathv, "tiled"));
+  const bool force_group = pathv && !strcmp(pathv, "group");
+  const bool small = loglik_small_smem(N, d) <= 220 * 1024 && !force_tiled && !force_group;
+  const bool group = !small && !force_tiled;
   if (grad_host && !small)
     return fail(APGP_ERR_ARG, "apgp_loglik_batch: batched gradients need the shared-memory path (N <= ~224); "
                               "use apgp_grad_log_likelihood per vector");
   // chunk the restart axis so the tiled path's workspace stays below ~4 GiB
   size_t per = (size_t)Np * Np * 8;
   int Rc = small ? R : (int)((4ull << 30) / per); if (Rc < 1) Rc = 1; if (Rc > R) Rc = R;
-  if (!small) {
+  if (group) {
+    CUI(h->gws.reserve(chol_group_ws_bytes(Np, Rc)));
+  } else if (!small) {
     CUI(h->bK.reserve(per * Rc));
     CUI(h->bDinv.reserve((size_t)Rc * Np * 64 * 8));
     CUI(h->br.reserve((size_t)Rc * Np * 8));
@@ -475,6 +489,9 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
                               h->bll.as<double>(), grad_host ? h->bgrad.as<double>() : nullptr, h->stream)); ++nl;
       if (grad_host)
         CU(cudaMemcpyAsync(gtmp.data(), h->bgrad.p, (size_t)rc * (2 + d) * 8, cudaMemcpyDeviceToHost, h->stream));
+    } else if (group) {
+      CUI(launch_loglik_group(h->X.as<double>(), h->y.as<double>(), N, d, Np, h->bhyper.as<double>(), rc, h->num_sms,
+                              h->gws.p, h->bll.as<double>(), h->stream)); ++nl;
     } else {
       FactorBatch fb{rc, N, Np, h->bK.as<double>(), h->bDinv.as<double>(), h->br.as<double>(), h->bscal.as<double>(),
                      h->binfo.as<int>()};
@@ -613,9 +630,13 @@ int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const ap
   return opt_fetch(h, (size_t)R * d, R, x_out, f_out, stats);
 }
 
+// largest training set the cluster-per-restart optimiser takes: beyond it one objective evaluation is so long that a
+// host-driven optimiser over apgp_loglik_batch loses nothing, and R x Np^2 workspaces get large
+static const int GROUP_OPT_MAX_N = 4096;
 int apgp_minimize_nll_fits(const apgp_handle* h, int P) {
   if (!h || !h->has_training) return 0;
-  return minimize_nll_fits(h->N, h->d, P) ? 1 : 0;
+  if (minimize_nll_fits(h->N, h->d, P) && !getenv("APGP_NLL_GROUP")) return 1;
+  return (minimize_nll_group_fits(P) && h->N <= GROUP_OPT_MAX_N) ? 2 : 0;
 }
 
 int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0, int R, int P, int fit_amp,
@@ -625,19 +646,38 @@ int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0
   if (!h->has_training) return fail(APGP_ERR_ARG, "apgp_minimize_nll: no training set");
   const int d = h->d, N = h->N;
   if (P != 1 + (fit_amp ? 1 : 0) + d) return fail(APGP_ERR_ARG, "apgp_minimize_nll: P != 1 + fit_amp + d");
-  if (!minimize_nll_fits(N, d, P))
-    return fail(APGP_ERR_ARG, "apgp_minimize_nll: training set too large for the one-restart-per-CTA shared-memory "
-                              "path (N <= ~220); drive apgp_loglik_batch from the host optimiser instead");
+  const int path = apgp_minimize_nll_fits(h, P);
+  if (!path)
+    return fail(APGP_ERR_ARG, "apgp_minimize_nll: training set too large for the device optimisers (N <= 4096); "
+                              "drive apgp_loglik_batch from the host optimiser instead");
   if (R < 1) return APGP_OK;
   Guard g(h->device);
   OptimizeParams q;
   if (resolve_opt(opt, P, q)) return fail(APGP_ERR_ARG, "apgp_minimize_nll: bad method");
-  { int st_ = opt_stage(h, p0, (size_t)R * P, (size_t)R * P, R); if (st_ != APGP_OK) return st_; }
-  CUI(launch_minimize_nll(h->X.as<double>(), h->y.as<double>(), N, d, P, fit_amp ? 1 : 0, default_prior ? 1 : 0,
-                          exp(white_noise) + TINY2, q, R, h->o_in.as<double>(), h->o_x.as<double>(), h->o_f.as<double>(),
-                          h->o_stats.as<long long>(), evaluate_only ? 0 : 1, h->stream));
-  h->launches += 1;
-  return opt_fetch(h, (size_t)R * P, R, p_out, f_out, stats);
+  if (path == 1) {
+    { int st_ = opt_stage(h, p0, (size_t)R * P, (size_t)R * P, R); if (st_ != APGP_OK) return st_; }
+    CUI(launch_minimize_nll(h->X.as<double>(), h->y.as<double>(), N, d, P, fit_amp ? 1 : 0, default_prior ? 1 : 0,
+                            exp(white_noise) + TINY2, q, R, h->o_in.as<double>(), h->o_x.as<double>(), h->o_f.as<double>(),
+                            h->o_stats.as<long long>(), evaluate_only ? 0 : 1, h->stream));
+    h->launches += 1;
+    return opt_fetch(h, (size_t)R * P, R, p_out, f_out, stats);
+  }
+  // one cluster per restart, matrices in L2-resident global workspace; the restart axis is chunked to ~4 GiB of it
+  const int Np = h->Np;
+  int Rc = (int)((4ull << 30) / ((size_t)Np * Np * 8)); if (Rc < 1) Rc = 1; if (Rc > R) Rc = R;
+  CUI(h->gws.reserve(chol_group_ws_bytes(Np, Rc)));
+  for (int r0 = 0; r0 < R; r0 += Rc) {
+    const int rc = (R - r0 < Rc) ? (R - r0) : Rc;
+    { int st_ = opt_stage(h, p0 + (size_t)r0 * P, (size_t)rc * P, (size_t)rc * P, rc); if (st_ != APGP_OK) return st_; }
+    CUI(launch_minimize_nll_group(h->X.as<double>(), h->y.as<double>(), N, d, Np, P, fit_amp ? 1 : 0, default_prior ? 1 : 0,
+                                  exp(white_noise) + TINY2, q, rc, h->num_sms, h->gws.p, h->o_in.as<double>(),
+                                  h->o_x.as<double>(), h->o_f.as<double>(), h->o_stats.as<long long>(),
+                                  evaluate_only ? 0 : 1, h->stream));
+    h->launches += 1;
+    { int st_ = opt_fetch(h, (size_t)rc * P, rc, p_out + (size_t)r0 * P, f_out + r0, stats ? stats + 3 * (size_t)r0 : nullptr);
+      if (st_ != APGP_OK) return st_; }
+  }
+  return APGP_OK;
 }
 
 int apgp_get_alpha(apgp_handle* h, double* alpha) {

@@ -82,6 +82,10 @@ int launch_tri_inverse(const double* L, const double* Dinv, int Np, double* Linv
 // alpha = L^{-T} z  using the explicit inverse
 int launch_linvT_matvec(const double* Linv, int Np, const double* z, double* alpha, cudaStream_t st);
 int launch_loglik_finish(const FactorBatch& fb, double* ll, cudaStream_t st);
+// one refinement step alpha += K^{-1}((y - m) - K alpha) through the explicit inverse, residual in double-double;
+// w1, w2: [Np] work vectors
+int launch_refine_alpha(const double* X, const double* y, int N, int d, int Np, const double* hyper_dev,
+                        const double* Linv, double* alpha, double* w1, double* w2, cudaStream_t st, int* launches);
 // bordered append of one training point to an existing factorisation (needs N + 1 <= Np)
 int launch_append_point(const double* X, int N, int d, int Np, const double* xnew_dev, const double* hyper_dev, double kappa,
                         double rnew, double* L, double* Linv, double* z, double* alpha, double* kvec, double* lvec,
@@ -90,6 +94,11 @@ int launch_append_point(const double* X, int N, int d, int Np, const double* xne
 size_t loglik_small_smem(int N, int d);
 int launch_loglik_small(const double* X, const double* y, int N, int d, const double* hyper, int R, double* ll,
                         double* grad /*[R][2+d] or null*/, cudaStream_t st);
+// fused one-CLUSTER-per-restart path for larger N (chol_group.cuh): the matrix lives in L2-resident global workspace
+int chol_group_cluster(int Np, int R, int num_sms);
+size_t chol_group_ws_bytes(int Np, int R);
+int launch_loglik_group(const double* X, const double* y, int N, int d, int Np, const double* hyper, int R, int num_sms,
+                        void* ws_bytes, double* ll, cudaStream_t st);
 // gradient pieces: Kinv = Linv^T Linv (lower), then tr-products
 int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv, const double* alpha,
                        const double* hyper_dev, int fit_amp, double* work /*[Np*Np]*/, double* grad_dev, cudaStream_t st,
@@ -119,6 +128,11 @@ int launch_minimize_utility(const UtilityPointParams& u, const OptimizeParams& q
                             double* x_out_dev, double* f_out_dev, long long* stats_dev, int mode, cudaStream_t st);
 bool minimize_nll_fits(int N, int d, int P);
 int read_prof(long long* out16);   // -DAPGP_PROF builds: per-phase cycle counters of the nll objective (zeros otherwise)
+bool minimize_nll_group_fits(int P);
+int launch_minimize_nll_group(const double* X_dev, const double* y_dev, int N, int d, int Np, int P, int fit_amp,
+                              int default_prior, double noise, const OptimizeParams& q, int R, int num_sms, void* ws_bytes,
+                              const double* p0_dev, double* p_out_dev, double* f_out_dev, long long* stats_dev, int mode,
+                              cudaStream_t st);
 int launch_minimize_nll(const double* X_dev, const double* y_dev, int N, int d, int P, int fit_amp, int default_prior,
                         double noise, const OptimizeParams& q, int R, const double* p0_dev, double* p_out_dev,
                         double* f_out_dev, long long* stats_dev, int mode, cudaStream_t st);

@@ -143,10 +143,11 @@ struct Philox {
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
   }
 };
-// 53-bit uniform in (0,1)
+// uniform in the OPEN interval (0,1) from 52 random bits: (x + 1/2) 2^-52 is exact for x < 2^52, so neither end is
+// reachable (with 53 bits the +1/2 is not representable above 2^52 and the largest value rounded to exactly 1.0)
 __device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo) {
-  uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
-  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+  uint64_t x = (((uint64_t)hi << 32) | lo) >> 12;
+  return ((double)x + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 }  // namespace apgp

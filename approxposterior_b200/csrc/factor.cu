@@ -14,7 +14,9 @@
 // the identity and the rhs with zeros; nothing downstream needs edge handling.
 #include "apgp_internal.h"
 #include "chol_small.cuh"
+#include "chol_group.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace apgp {
 namespace {
@@ -292,6 +294,48 @@ __global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restr
   if (g == 0) alpha[j] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
 }
 
+// ---- one step of iterative refinement for alpha = K^{-1}(y - m) -------------------------------------------
+// alpha comes out of the explicit inverse (alpha = L^{-T} L^{-1} r), whose forward error was measured at 3-12x the
+// LAPACK oracle's on ill-conditioned problems (cond(K) ~ 1e6: profiles/r02_parity_errors_before_refinement.txt).
+// One refinement step with the residual carried in double-double brings it to the oracle's level or below:
+//   res = (y - m) - K alpha     (K rebuilt on the fly with the expression build_K_kernel uses; one warp per row)
+//   alpha += L^{-T} (L^{-1} res)
+__global__ void __launch_bounds__(256) alpha_residual_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                             int N, int d, const double* __restrict__ h,
+                                                             const double* __restrict__ alpha, double* __restrict__ res,
+                                                             int Np) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= Np) return;
+  if (i >= N) { if (lane == 0) res[i] = 0.0; return; }
+  const double amp = h[1], noise = h[2];
+  double hi = 0.0, lo = 0.0;
+  for (int j = lane; j < N; j += 32) {
+    double s = 0.0;
+    for (int c = 0; c < d; ++c) {
+      double df = X[(size_t)i * d + c] - X[(size_t)j * d + c];
+      s += df * df * h[3 + c];
+    }
+    double v = amp * exp(-0.5 * s);
+    if (i == j) v += noise;
+    const double a = alpha[j];
+    const double p = v * a, pe = fma(v, a, -p);                 // two-product
+    const double t = hi + p, bb = t - hi;                        // two-sum
+    lo += ((hi - (t - bb)) + (p - bb)) + pe;
+    hi = t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double h2 = __shfl_xor_sync(0xffffffffu, hi, o), l2 = __shfl_xor_sync(0xffffffffu, lo, o);
+    const double t = hi + h2, bb = t - hi;
+    lo += ((hi - (t - bb)) + (h2 - bb)) + l2;
+    hi = t;
+  }
+  if (lane == 0) res[i] = ((y[i] - h[0]) - hi) - lo;
+}
+__global__ void axpy_kernel(int n, const double* __restrict__ x, double* __restrict__ y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += x[i];
+}
+
 __global__ void loglik_finish_kernel(FactorBatch fb, double* __restrict__ ll) {
   const int rr = blockIdx.x;
   __shared__ double red[256];
@@ -549,6 +593,22 @@ __global__ void __launch_bounds__(256) append_finish_kernel(double* __restrict__
   }
 }
 
+// ---- fused log-likelihood for N beyond one CTA's shared memory: one CLUSTER of C CTAs per hyper-parameter vector
+//      (chol_group.cuh).  grid = R * C CTAs, cluster dimension C; ws = per-restart workspace described by GroupWs.
+__global__ void __launch_bounds__(CG_THREADS, 1) loglik_group_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                                     int N, int d, int Np, int C,
+                                                                     const double* __restrict__ hyper, GroupWs ws,
+                                                                     double* __restrict__ ll_out) {
+  extern __shared__ __align__(16) double gsm[];
+  __shared__ double hyp[3 + APGP_MAXD];
+  const int rr = blockIdx.x / C;
+  if (threadIdx.x < 3 + d) hyp[threadIdx.x] = hyper[(size_t)rr * (3 + d) + threadIdx.x];
+  __syncthreads();
+  const CholGroup g = cg_make(ws, rr, N, Np, d, C, (C > 1) ? cg_cluster_ctarank() : 0, X, y);
+  const double ll = chol_group_loglik<true>(g, hyp, gsm, 0ull);
+  if (g.rank == 0 && threadIdx.x == 0) ll_out[rr] = ll;
+}
+
 PerDeviceOnce g_attr_done;
 int ensure_attrs() {
   if (!g_attr_done.needed()) return 0;
@@ -558,6 +618,8 @@ int ensure_attrs() {
   e = cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(gemm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM); if (e) return (int)e;
   e = cudaFuncSetAttribute(loglik_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); if (e) return (int)e;
+  e = cudaFuncSetAttribute(loglik_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CG_SMEM_DOUBLES * 8)); if (e) return (int)e;
+  e = cudaFuncSetAttribute(loglik_group_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (e) return (int)e;
   g_attr_done.mark();
   return 0;
 }
@@ -625,6 +687,40 @@ int launch_loglik_small(const double* X, const double* y, int N, int d, const do
   return (int)cudaGetLastError();
 }
 
+// cluster size for the fused group kernels: as many CTAs per restart as fit the GPU in one wave (power of two, at most
+// 16), but no more than the tile count can feed (nb - 1 panel tiles at the first step).  APGP_CHOL_CLUSTER overrides.
+int chol_group_cluster(int Np, int R, int num_sms) {
+  const int nb = Np / T;
+  int C = 1;
+  while (C * 2 <= 16 && (long)R * C * 2 <= num_sms && C * 2 <= (nb > 1 ? nb - 1 : 1) * 2) C *= 2;
+  if (const char* v = getenv("APGP_CHOL_CLUSTER")) { const int c = atoi(v); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) C = c; }
+  return C;
+}
+size_t chol_group_ws_bytes(int Np, int R) { return cg_ws_bytes(Np, R); }
+// ws: chol_group_ws_bytes(Np, R) bytes.  hyper [R][3 + d] as for launch_build_K.  One launch for all R vectors.
+int launch_loglik_group(const double* X, const double* y, int N, int d, int Np, const double* hyper, int R, int num_sms,
+                        void* ws_bytes, double* ll, cudaStream_t st) {
+  int e = ensure_attrs(); if (e) return e;
+  GroupWs ws = cg_ws_carve(ws_bytes, Np, R);
+  cudaError_t ce = cudaMemsetAsync(ws.flags, 0, (size_t)R * 16, st);
+  if (ce != cudaSuccess) return (int)ce;
+  int C = chol_group_cluster(Np, R, num_sms);
+  for (;;) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(R * C)); cfg.blockDim = dim3(CG_THREADS);
+    cfg.dynamicSmemBytes = CG_SMEM_DOUBLES * 8; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, loglik_group_kernel, X, y, N, d, Np, C, hyper, ws, ll);
+    if (ce == cudaSuccess || C == 1) break;
+    (void)cudaGetLastError();                // the cluster could not be scheduled: halve it (C = 1 always can)
+    C >>= 1;
+  }
+  return (int)ce;
+}
+
 int launch_append_point(const double* X, int N, int d, int Np, const double* xnew_dev, const double* hyper_dev, double kappa,
                         double rnew, double* L, double* Linv, double* z, double* alpha, double* kvec, double* lvec,
                         double* uvec, double* scal, int* status, cudaStream_t st, int* launches) {
@@ -639,6 +735,17 @@ int launch_append_point(const double* X, int N, int d, int Np, const double* xne
 
 int launch_linvT_matvec(const double* Linv, int Np, const double* z, double* alpha, cudaStream_t st) {
   linvT_matvec_kernel<<<Np / T, 256, 0, st>>>(Linv, Np, z, alpha);
+  return (int)cudaGetLastError();
+}
+
+int launch_refine_alpha(const double* X, const double* y, int N, int d, int Np, const double* hyper_dev,
+                        const double* Linv, double* alpha, double* w1, double* w2, cudaStream_t st, int* launches) {
+  alpha_residual_kernel<<<(Np + 7) / 8, 256, 0, st>>>(X, y, N, d, hyper_dev, alpha, w1, Np);
+  cudaMemsetAsync(w2, 0, sizeof(double) * Np, st);
+  append_linv_rows_kernel<<<(Np + 7) / 8, 256, 0, st>>>(Linv, Np, Np, w1, w2);       // w2 = L^{-1} res
+  linvT_matvec_kernel<<<Np / T, 256, 0, st>>>(Linv, Np, w2, w1);                      // w1 = L^{-T} w2
+  axpy_kernel<<<(Np + 255) / 256, 256, 0, st>>>(Np, w1, alpha);
+  if (launches) *launches += 4;
   return (int)cudaGetLastError();
 }
 

@@ -20,7 +20,9 @@
 // value to every thread.
 #include "apgp_internal.h"
 #include "chol_small.cuh"
+#include "chol_group.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace apgp {
 namespace {
@@ -187,6 +189,40 @@ struct NllObj {
     PROF_ADD(3, t_e1);                                            // log-det + |z|^2 reductions
     const double ll = -0.5 * ssq - logdet - 0.5 * N * LOG_2PI;
     if (bad || !(ll == ll) || !(fabs(ll) < INFINITY)) return INFINITY;
+    return -ll;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// Objective 2b: the same negative log-likelihood for training sets beyond one CTA's shared memory (N > ~220):
+// a CLUSTER of C CTAs evaluates it cooperatively (chol_group.cuh: matrix in L2-resident global memory, fused
+// build + look-ahead Cholesky + reductions).  Every CTA of the cluster runs the optimiser redundantly on its own
+// replica of the state; the objective returns identical bits to all of them, so they stay in lock step.
+// ------------------------------------------------------------------------------------------------------
+struct NllGroupObj {
+  int d, P, fit_amp, default_prior;
+  double noise;
+  CholGroup g;
+  int oHyp, oTiles;         // shared: hyp [3 + d], tile buffers [CG_SMEM_DOUBLES]
+  unsigned long long epoch; // evaluations that reached the factorisation (identical in every thread of the cluster)
+
+  __device__ __noinline__ double eval(int ox) {
+    extern __shared__ __align__(16) double smem_dyn[];
+    const int tid = threadIdx.x;
+    const double* p = smem_dyn + ox;
+    double* hyp = smem_dyn + oHyp;
+    __syncthreads();
+    bool fin = true;
+    for (int k = 0; k < P; ++k) { const double v = p[k]; fin = fin && (v == v) && (fabs(v) < INFINITY); }
+    if (!fin) return INFINITY;
+    if (default_prior)                                   // gpUtils.defaultHyperPrior: |p[1:]| <= 20
+      for (int k = 1; k < P; ++k) if (fabs(p[k]) > 20.0) return INFINITY;
+    if (tid == 0) { hyp[0] = p[0]; hyp[1] = fit_amp ? (double)d * exp(p[1]) : 1.0; hyp[2] = noise; }
+    if (tid < d) hyp[3 + tid] = exp(-p[1 + fit_amp + tid]);
+    __syncthreads();
+    const double ll = chol_group_loglik<true>(g, hyp, smem_dyn + oTiles, epoch);
+    ++epoch;
+    if (!(ll == ll) || !(fabs(ll) < INFINITY)) return INFINITY;
     return -ll;
   }
 };
@@ -673,6 +709,48 @@ __global__ void __launch_bounds__(OT, 1) minimize_nll_kernel(const __grid_consta
   }
 }
 
+struct NllGroupKernelParams {
+  int N, d, Np, P, fit_amp, default_prior, C;
+  double noise;
+  const double* X; const double* y;
+  GroupWs ws;
+  const double* p0; double* p_out; double* f_out; long long* stats;
+  int mode;
+  OptOpts opt;
+};
+
+__global__ void __launch_bounds__(OT, 1) minimize_nll_group_kernel(const __grid_constant__ NllGroupKernelParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, n = p.P;
+  const int rr = blockIdx.x / p.C;
+  const int rank = (p.C > 1) ? cg_cluster_ctarank() : 0;
+  double* cur = sm;
+  double* tiles = cur; cur += CG_SMEM_DOUBLES;
+  double* hyp = cur; cur += 4 + APGP_MAXD;
+  OptWork w; w.carve(cur, n); w.base = sm;
+  NllGroupObj f;
+  f.d = p.d; f.P = p.P; f.fit_amp = p.fit_amp; f.default_prior = p.default_prior; f.noise = p.noise;
+  f.g = cg_make(p.ws, rr, p.N, p.Np, p.d, p.C, rank, p.X, p.y);
+  f.oHyp = (int)(hyp - sm); f.oTiles = (int)(tiles - sm); f.epoch = 0ull;
+  const double* x0 = p.p0 + (size_t)rr * n;
+  double* start = (p.opt.method == 1 && p.mode == 1) ? w.v0 : w.sim;
+  if (tid < n) start[tid] = x0[tid];
+  __syncthreads();
+  double fbest; long long nfev = 1, nit = 0;
+  const long long t_start = clock64();
+  if (p.mode == 0) fbest = f.eval(w.off(start));
+  else if (p.opt.method == 0) fbest = nelder_mead_dev(f, n, p.opt, w, nfev, nit);
+  else fbest = powell_dev(f, n, p.opt, w, nfev, nit);
+  __syncthreads();
+  if (rank == 0) {
+    if (tid < n) p.p_out[(size_t)rr * n + tid] = start[tid];
+    if (tid == 0) {
+      p.f_out[rr] = fbest;
+      if (p.stats) { p.stats[3 * rr] = nfev; p.stats[3 * rr + 1] = nit; p.stats[3 * rr + 2] = clock64() - t_start; }
+    }
+  }
+}
+
 constexpr size_t SMEM_CAP = 220 * 1024;
 PerDeviceOnce g_opt_attr;
 int ensure_opt_attrs() {
@@ -680,6 +758,8 @@ int ensure_opt_attrs() {
   cudaError_t e;
   e = cudaFuncSetAttribute(minimize_utility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP); if (e) return (int)e;
   e = cudaFuncSetAttribute(minimize_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP); if (e) return (int)e;
+  e = cudaFuncSetAttribute(minimize_nll_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP); if (e) return (int)e;
+  e = cudaFuncSetAttribute(minimize_nll_group_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (e) return (int)e;
   g_opt_attr.mark();
   return 0;
 }
@@ -749,6 +829,40 @@ int launch_minimize_nll(const double* X_dev, const double* y_dev, int N, int d, 
   fill_opt(p.opt, q, P);
   minimize_nll_kernel<<<R, OT, minimize_nll_smem(N, d, P), st>>>(p);
   return (int)cudaGetLastError();
+}
+
+size_t minimize_nll_group_smem(int P) { return (CG_SMEM_DOUBLES + 4 + APGP_MAXD + OptWork::doubles(P)) * sizeof(double); }
+bool minimize_nll_group_fits(int P) { return minimize_nll_group_smem(P) <= SMEM_CAP && P + 1 <= OT; }
+
+// One CLUSTER of C CTAs per restart; ws_bytes: chol_group_ws_bytes(Np, R).  Same contract as launch_minimize_nll.
+int launch_minimize_nll_group(const double* X_dev, const double* y_dev, int N, int d, int Np, int P, int fit_amp,
+                              int default_prior, double noise, const OptimizeParams& q, int R, int num_sms, void* ws_bytes,
+                              const double* p0_dev, double* p_out_dev, double* f_out_dev, long long* stats_dev, int mode,
+                              cudaStream_t st) {
+  int e = ensure_opt_attrs(); if (e) return e;
+  NllGroupKernelParams p;
+  p.N = N; p.d = d; p.Np = Np; p.P = P; p.fit_amp = fit_amp; p.default_prior = default_prior; p.noise = noise;
+  p.X = X_dev; p.y = y_dev; p.ws = cg_ws_carve(ws_bytes, Np, R);
+  p.p0 = p0_dev; p.p_out = p_out_dev; p.f_out = f_out_dev; p.stats = stats_dev; p.mode = mode;
+  fill_opt(p.opt, q, P);
+  cudaError_t ce = cudaMemsetAsync(p.ws.flags, 0, (size_t)R * 16, st);
+  if (ce != cudaSuccess) return (int)ce;
+  int C = chol_group_cluster(Np, R, num_sms);
+  for (;;) {
+    p.C = C;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(R * C)); cfg.blockDim = dim3(OT);
+    cfg.dynamicSmemBytes = minimize_nll_group_smem(P); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, minimize_nll_group_kernel, p);
+    if (ce == cudaSuccess || C == 1) break;
+    (void)cudaGetLastError();
+    C >>= 1;
+  }
+  return (int)ce;
 }
 
 }  // namespace apgp

@@ -35,8 +35,8 @@ def check_mean(mu, mu_o, orc, y, Xq):
     misses that strict bound -- cond(K) reaches 1e6-1e8 on the d = 1, 2 problems and BOTH fp64 implementations carry
     forward errors of order cond(K) eps in alpha -- the disagreement is arbitrated against extended-precision truth
     (conftest.extended_truth): the engine may be at most 4x as far from the truth as the LAPACK oracle is.
-    Measured errors vs truth (engine / oracle), N,d = (20,2): 2e-12 / 2e-12, (64,1): 3e-10 / 2e-10, (256,2): 2e-9 / 2e-9
-    (profiles/r02_parity_errors.txt, which also holds the pre-9d0af3d diagonal kernel's numbers)."""
+    Measured max errors vs truth are in profiles/r02_parity_errors.txt (current library and the pre-9d0af3d diagonal
+    kernel, next to the oracle's own)."""
     scale = max(np.max(np.abs(y)), 1.0)
     strict = np.abs(mu - mu_o) <= RTOL * np.abs(mu_o) + RTOL * scale
     if np.all(strict):
@@ -280,7 +280,11 @@ def test_sampler_philox_statistics():
     tests agree")."""
     from oracle import stretch_move_oracle
     from oracle.sampler_oracle import gpll_batch
-    theta, y = rosenbrock_training(50)
+    theta, _ = rosenbrock_training(50)
+    # a unimodal target (the Rosenbrock surrogate at these hyper-parameters is multi-modal with tau > 100: two CPU
+    # oracle runs with different seeds already disagree at this chain length, which is why the first version of this
+    # test could only afford a KS statistic < 0.2)
+    y = -0.5 * ((theta[:, 0] - 1.0) ** 2 / 1.5 ** 2 + (theta[:, 1] + 0.5) ** 2 / 0.8 ** 2)
     logM = np.array([0.5, 1.2])
     gp, orc = make_pair(theta, y, logM)
     lo, hi = np.array([-5.0, -5.0]), np.array([5.0, 5.0])
