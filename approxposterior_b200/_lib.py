@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("APGP_LIB") or os.path.join(_HERE, "libapgp.so")     # APGP_LIB: debug/profiling builds
 
-APGP_OK, APGP_NOT_POSDEF, APGP_NOT_COMPUTED, APGP_NEEDS_REFACTOR = 0, 1, 2, 3
+APGP_OK, APGP_NOT_POSDEF, APGP_NOT_COMPUTED, APGP_NEEDS_REFACTOR, APGP_NEEDS_HOST = 0, 1, 2, 3, 4
 MAX_DIM = 32
 UTIL_KINDS = {None: 0, "none": 0, "agp": 1, "bape": 2, "jones": 3, "negmean": 4}
 OPT_METHODS = {"nelder-mead": 0, "powell": 1}
@@ -58,6 +58,8 @@ _SIGNATURES = {
                                     C.c_void_p]),
     "apgp_sampler_run": (C.c_int, [C.c_void_p, C.POINTER(SamplerOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int]),
+    "apgp_integrated_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_longlong, C.c_int,
+                                       C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "apgp_minimize_utility": (C.c_int, [C.c_void_p, C.POINTER(PredictOpts), C.POINTER(OptOpts), C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "apgp_minimize_nll": (C.c_int, [C.c_void_p, C.POINTER(OptOpts), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,

@@ -1,7 +1,8 @@
 """``ApproxPosterior``: mirror of reference ``approxposterior/approx.py`` on the B200 engine.
 
 Same constructor, ``run`` / ``findNextPoint`` / ``runMCMC`` / ``findMAP`` / ``bayesOpt`` / ``optGP``
-methods, keyword names, defaults, cache files and RNG consumption order as the reference class
+methods, keyword names, defaults, cache files and (as long as no utility restart is retried, see
+``utility.minimizeObjective``) RNG consumption order as the reference class
 (approx.py:30-1151); george.GP becomes ``approxposterior_b200.GP`` and emcee.EnsembleSampler becomes
 ``approxposterior_b200.sampler.EnsembleSampler``.  What changes is *how* the three hot loops run:
 
@@ -258,9 +259,7 @@ class ApproxPosterior(object):
                     if not hasattr(self, "gpPar"):
                         self.gpPar = list()
                     self.gpPar.append(currentHype)
-                if hasattr(self.gp, "rebuild"):          # foreign george-like GP (tests inject the CPU oracle)
-                    self.gp = self.gp.rebuild(currentHype, self.theta, self.y)
-                elif isinstance(self.gp, GP):
+                if isinstance(self.gp, GP):
                     # the reference builds a fresh george.GP around the same kernel (approx.py:712-717);
                     # re-computing in place is equivalent and keeps the device handle and its buffers
                     # ... and, with unchanged hyper-parameters, a bordered O(N^2) update replaces the refactor
@@ -268,10 +267,11 @@ class ApproxPosterior(object):
                     self.gp.set_parameter_vector(currentHype)
                     self.gp.append_point(thetaT, yT)
                 else:
-                    self.gp = GP(kernel=self.gp.kernel, fit_mean=True, mean=self.gp.mean,
-                                 white_noise=self.gp.white_noise, fit_white_noise=False)
+                    # any other george-like object: rebuild it the way the reference does (approx.py:712-717)
+                    self.gp = type(self.gp)(kernel=self.gp.kernel, fit_mean=True, mean=self.gp.mean,
+                                            white_noise=self.gp.white_noise, fit_white_noise=False)
                     self.gp.set_parameter_vector(currentHype)
-                    self.gp.compute(self.theta, y=self.y)
+                    self.gp.compute(self.theta)
                 if ii % optGPEveryN == 0:
                     self.optGP(seed=seed, method=gpMethod, options=gpOptions, p0=gpP0, nGPRestarts=nGPRestarts,
                                gpHyperPrior=gpHyperPrior)

@@ -64,6 +64,7 @@ struct apgp_handle {
   double* pin = nullptr;               // pinned host staging for small calls (latency path)
   static constexpr size_t PIN_DOUBLES = 32768;   // 256 KB: [0, PIN/2) inputs, [PIN/2, PIN) outputs
   DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
+  DevBuf ac_part, ac_f, ac_stage;                            // autocorrelation partial sums, f(t), host-chain staging
   DevBuf gws;                                                // fused cluster-per-restart workspace (chol_group.cuh)
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
   DevBuf o_in, o_x, o_f, o_stats;      // device optimiser staging
@@ -126,7 +127,7 @@ int apgp_destroy(apgp_handle* h) {
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
                     &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->ap_k, &h->ap_l, &h->ap_u, &h->ap_x, &h->bK,
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
-                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->gws};
+                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->gws, &h->ac_part, &h->ac_f, &h->ac_stage};
   for (DevBuf* b : bufs) b->release();
   if (h->pin) cudaFreeHost(h->pin);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -574,6 +575,64 @@ int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* o, const double* p
     CU(cudaStreamSynchronize(h->stream));
   }
   return APGP_OK;
+}
+
+// ---- integrated autocorrelation time (emcee's estimator) of a chain, on the device -----------------------------
+int apgp_integrated_time(apgp_handle* h, const double* chain, long long n_total, int W, int d, long long discard, int thin,
+                         double c, int on_host, double* tau_out, int* window_out) {
+  if (!h || !chain || !tau_out) return fail(APGP_ERR_ARG, "apgp_integrated_time: null argument");
+  if (n_total < 1 || W < 1 || d < 1 || thin < 1 || discard < 0) return fail(APGP_ERR_ARG, "apgp_integrated_time: bad shape");
+  const long long off = discard + thin - 1;                 // emcee: chain[discard + thin - 1 :: thin]
+  if (off >= n_total) return fail(APGP_ERR_ARG, "apgp_integrated_time: nothing left after discard/thin");
+  const long long nll = (n_total - off + thin - 1) / thin;
+  if (nll > (1ll << 30)) return fail(APGP_ERR_ARG, "apgp_integrated_time: chain too long");
+  const int n = (int)nll;
+  Guard g(h->device);
+  if (!autocorr_fits(n, 1)) return APGP_NEEDS_HOST;          // series does not fit one CTA's shared memory
+  const double* src = chain;
+  if (on_host) {
+    const size_t bytes = (size_t)n_total * W * d * 8;
+    CUI(h->ac_stage.reserve(bytes));
+    CU(cudaMemcpyAsync(h->ac_stage.p, chain, bytes, cudaMemcpyHostToDevice, h->stream));
+    src = h->ac_stage.as<double>();
+  }
+  std::vector<double> f;
+  int T = 256;
+  for (int k = 0; k < d; ++k) { tau_out[k] = NAN; if (window_out) window_out[k] = -1; }
+  std::vector<char> found(d, 0);
+  for (;;) {
+    if (T > n) T = n;
+    if (!autocorr_fits(n, T)) return APGP_NEEDS_HOST;
+    int G, nchunk;
+    const size_t pb = autocorr_partial_bytes(W, d, T, h->num_sms, &G, &nchunk);
+    CUI(h->ac_part.reserve(pb));
+    CUI(h->ac_f.reserve((size_t)d * T * 8));
+    int nl = 0;
+    CUI(launch_autocorr(src, off, thin, n, W, d, T, h->num_sms, h->ac_part.as<double>(), h->ac_f.as<double>(), h->stream, &nl));
+    h->launches += nl;
+    f.resize((size_t)d * T);
+    CU(cudaMemcpyAsync(f.data(), h->ac_f.p, (size_t)d * T * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    bool all = true;
+    for (int k = 0; k < d; ++k) {
+      if (found[k]) continue;
+      double cum = 0.0;
+      int win = -1;
+      double tw = NAN;
+      for (int M = 0; M < T; ++M) {
+        cum += f[(size_t)k * T + M];
+        const double taus = 2.0 * cum - 1.0;
+        if (!((double)M < c * taus)) { win = M; tw = taus; break; }      // first M where (M < c tau(M)) is false
+        if (M == n - 1) { win = M; tw = taus; }                          // no such M: emcee takes the last lag
+      }
+      if (win >= 0) { found[k] = 1; tau_out[k] = tw; if (window_out) window_out[k] = win; }
+      else all = false;
+    }
+    if (all) return APGP_OK;
+    if (T == n) return APGP_OK;
+    if (T >= 4096) return APGP_NEEDS_HOST;                    // window beyond 4096 lags: let the caller use its FFT path
+    T *= 4;
+  }
 }
 
 // ---- device-resident optimisers ---------------------------------------------------------------------

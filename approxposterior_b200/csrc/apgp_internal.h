@@ -163,4 +163,10 @@ struct SamplerParams {
 };
 int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches);
 
+// ---- integrated autocorrelation time of a device-resident chain (autocorr.cu) -------
+bool autocorr_fits(int n, int T);
+size_t autocorr_partial_bytes(int W, int d, int T, int num_sms, int* G_out, int* nchunk_out);
+int launch_autocorr(const double* chain, long long off, int thin, int n, int W, int d, int T, int num_sms, double* partial,
+                    double* f_dev, cudaStream_t st, int* launches);
+
 }  // namespace apgp

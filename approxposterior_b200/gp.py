@@ -130,7 +130,14 @@ class GP(object):
 
     def compute(self, x, yerr=None, y=None, **kwargs):
         """george.GP.compute(x).  ``y`` is an optional hint (george only sees y at predict time);
-        when it is omitted the factorisation is finished on the first call that supplies y."""
+        when it is omitted the factorisation is finished on the first call that supplies y.
+        ``yerr``: approxposterior never passes one (gpUtils.py:178, approx.py:717), so only george's default
+        (1.25e-12, whose square is added to the diagonal next to exp(white_noise)) is accepted; anything else raises
+        instead of being dropped.  Note the constructor's ``white_noise`` default is -12 (what gpUtils.defaultGP
+        passes), not george's None = log(1.25e-12 ** 2)."""
+        if yerr is not None and np.any(np.asarray(yerr, dtype=np.float64) != 1.25e-12):
+            raise NotImplementedError("per-point observational errors (yerr) are outside the engine's scope: "
+                                      "the diagonal carries exp(white_noise) + (1.25e-12)^2 only")
         self._x = self._parse(x)
         self._y = None if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
         if self._y is not None and self._y.size != self._x.shape[0]:
@@ -406,12 +413,17 @@ class GP(object):
         return p, f, stats[:, 0].copy()
 
     # ------------------------------------------------------------------ sampler
-    def run_ensembles(self, y, p0, nsteps, bounds, nens=1, a=2.0, seed=0, thin=1, lnprior_const=0.0, replay=None):
+    def run_ensembles(self, y, p0, nsteps, bounds, nens=1, a=2.0, seed=0, thin=1, lnprior_const=0.0, replay=None,
+                      device_out=False):
         """Device-resident stretch-move sampling of the surrogate posterior mean (emcee as driven
         from approx.py:839-847).  ``p0`` is (nens*nwalkers, ndim); returns dict(chain, log_prob,
-        blobs, naccepted) with chain shaped (nsteps//thin, nens*nwalkers, ndim)."""
+        blobs, naccepted) with chain shaped (nsteps//thin, nens*nwalkers, ndim).
+        ``device_out=True`` (or a torch CUDA ``p0``): the results stay on the GPU as torch tensors -- the chain of
+        65 536 walkers is never copied to the host unless asked for (``integrated_time`` works on it in place)."""
         self._sync_y(y)
         self.recompute()
+        if device_out or _is_torch(p0):
+            return self._run_ensembles_device(p0, nsteps, bounds, nens, a, seed, thin, lnprior_const, replay)
         p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, self.ndim))
         W = p0.shape[0]
         if W % nens:
@@ -439,6 +451,65 @@ class GP(object):
                                               _lib.ptr(blob), _lib.ptr(nacc), 1), "apgp_sampler_run")
         del keep
         return dict(chain=chain, log_prob=logp, blobs=blob, naccepted=nacc)
+
+    def _torch_stream(self, dev):
+        """Run the engine on torch's current stream of ``dev`` (so torch sees the results in stream order)."""
+        import torch
+        sh = torch.cuda.current_stream(dev).cuda_stream or 1
+        _lib.check(self._lib.apgp_set_stream(self._h, C.c_void_p(sh)), "apgp_set_stream")
+
+    def _run_ensembles_device(self, p0, nsteps, bounds, nens, a, seed, thin, lnprior_const, replay):
+        import torch
+        if replay is not None:
+            raise ValueError("replayed draws are a host-side test facility: use device_out=False")
+        dev = torch.device("cuda", self._device)
+        if _is_torch(p0):
+            p0 = p0.to(device=dev, dtype=torch.float64).reshape(-1, self.ndim).contiguous()
+        else:
+            p0 = torch.from_numpy(np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, self.ndim))).to(dev)
+        W = p0.shape[0]
+        if W % nens:
+            raise ValueError("p0 rows must be a multiple of nens")
+        o = _lib.SamplerOpts()
+        o.nens, o.nwalkers, o.nsteps, o.thin = int(nens), int(W // nens), int(nsteps), int(thin)
+        o.a, o.seed, o.lnprior_const = float(a), int(seed) & (2**64 - 1), float(lnprior_const)
+        _lib.fill_bounds(o.lo, o.hi, bounds, self.ndim)
+        ns = nsteps // thin
+        chain = torch.empty((ns, W, self.ndim), dtype=torch.float64, device=dev)
+        logp = torch.empty((ns, W), dtype=torch.float64, device=dev)
+        blob = torch.empty((ns, W), dtype=torch.float64, device=dev)
+        nacc = torch.zeros(W, dtype=torch.int32, device=dev)
+        self._torch_stream(dev)
+        _lib.check(self._lib.apgp_sampler_run(self._h, C.byref(o), _lib.ptr(p0), _lib.ptr(chain), _lib.ptr(logp),
+                                              _lib.ptr(blob), _lib.ptr(nacc), 0), "apgp_sampler_run")
+        return dict(chain=chain, log_prob=logp, blobs=blob, naccepted=nacc)
+
+    def integrated_time(self, chain, discard=0, thin=1, c=5.0):
+        """emcee's integrated autocorrelation time (per dimension) of ``chain`` (n_t, n_walkers, ndim) restricted to
+        ``chain[discard + thin - 1::thin]`` -- NOT multiplied by ``thin`` -- computed on the device by direct lagged sums
+        over just the lags Sokal's window needs (reference mcmcUtils.py:198 via emcee's get_autocorr_time).  ``chain``
+        may be a torch CUDA tensor (used in place) or a NumPy array (uploaded).  Returns (tau [ndim], window [ndim]), or
+        None when the series is too long for the device kernel (callers then use the host FFT estimator)."""
+        on_host = 0 if _is_torch(chain) else 1
+        if on_host:
+            chain = np.ascontiguousarray(np.asarray(chain, dtype=np.float64))
+            if chain.ndim == 2:
+                chain = chain[:, :, None]
+        else:
+            import torch
+            if not chain.is_cuda or chain.dtype != torch.float64 or chain.dim() != 3:
+                raise ValueError("device chains must be float64 CUDA tensors of shape (n_t, n_walkers, ndim)")
+            chain = chain.contiguous()
+            self._torch_stream(chain.device)
+        n_t, W, d = chain.shape
+        tau = np.empty(d)
+        win = np.empty(d, dtype=np.int32)
+        st = _lib.check(self._lib.apgp_integrated_time(self._h, _lib.ptr(chain), int(n_t), int(W), int(d), int(discard),
+                                                       int(thin), float(c), on_host, _lib.ptr(tau), _lib.ptr(win)),
+                        "apgp_integrated_time")
+        if st == _lib.APGP_NEEDS_HOST:
+            return None
+        return tau, win
 
     # ------------------------------------------------------------------ diagnostics (tests)
     def _alpha(self):

@@ -76,6 +76,11 @@ def integrated_time(x, c=5, tol=50, quiet=False):
     return tau_est
 
 
+def _host(a):
+    """NumPy view/copy of a NumPy array or torch tensor."""
+    return a if isinstance(a, np.ndarray) else a.detach().cpu().numpy()
+
+
 class _State(object):
     def __init__(self, coords, log_prob, blobs):
         self.coords, self.log_prob, self.blobs = coords, log_prob, blobs
@@ -108,10 +113,12 @@ class EnsembleSampler(object):
 
     # ------------------------------------------------------------------ running
     def _run_device(self, p0, nsteps):
+        """The chain, log-probabilities and blobs stay on the GPU (torch tensors); ``get_chain`` & co. copy what they
+        are asked for, ``get_autocorr_time`` works on the device copy in place."""
         seed = self._seed if self._seed is not None else int(self._random.randint(0, 2 ** 31 - 1))
         out = self.gp.run_ensembles(self.y, p0, nsteps, self.bounds, nens=self.nens, a=self.a, seed=seed,
-                                    lnprior_const=self.lnprior_const)
-        return out["chain"], out["log_prob"], out["blobs"], out["naccepted"].astype(np.int64)
+                                    lnprior_const=self.lnprior_const, device_out=True)
+        return out["chain"], out["log_prob"], out["blobs"], out["naccepted"].cpu().numpy().astype(np.int64)
 
     def _run_host(self, p0, nsteps):
         rng, a = self._random, self.a
@@ -157,17 +164,31 @@ class EnsembleSampler(object):
         if self._chain is None:
             self._chain, self._logp, self._blobs, self.naccepted = chain, lp, blobs, nacc
         else:
-            self._chain = np.concatenate([self._chain, chain]); self._logp = np.concatenate([self._logp, lp])
-            self._blobs = np.concatenate([self._blobs, blobs]); self.naccepted = self.naccepted + nacc
+            cat = np.concatenate
+            if not isinstance(chain, np.ndarray):
+                import torch
+                cat = torch.cat
+            self._chain = cat([self._chain, chain]); self._logp = cat([self._logp, lp])
+            self._blobs = cat([self._blobs, blobs]); self.naccepted = self.naccepted + nacc
         self.iteration += int(nsteps)
         if self.backend is not None:
-            np.savez(str(self.backend), chain=self._chain, log_prob=self._logp, blobs=self._blobs,
+            np.savez(str(self.backend), chain=_host(self._chain), log_prob=_host(self._logp), blobs=_host(self._blobs),
                      accepted=self.naccepted)
-        return _State(self._chain[-1], self._logp[-1], self._blobs[-1])
+        return _State(_host(self._chain[-1]), _host(self._logp[-1]), _host(self._blobs[-1]))
 
     def sample(self, initial_state, iterations=1, **kwargs):
-        """Generator form used at approx.py:846 (``for _ in sampler.sample(**mcmcKwargs): pass``).  The
-        chain is produced in one go on first advance; one (final-state) item is yielded per iteration."""
+        """Generator form used at approx.py:846 (``for _ in sampler.sample(**mcmcKwargs): pass``).
+
+        Limitation (deliberate): the whole chain is produced on the first advance -- on the device engine it is ONE
+        kernel launch -- and the same FINAL state is then yielded ``iterations`` times.  Breaking out of the loop
+        early does not shorten the run and no intermediate states are exposed; callers that need either should call
+        ``run_mcmc`` in chunks.  emcee options that would change what is stored (``thin_by``, ``store=False``,
+        ``tune``, ``skip_initial_state_check``) are rejected rather than silently ignored."""
+        if kwargs.get("thin_by", 1) not in (None, 1) or kwargs.get("store", True) is not True:
+            raise NotImplementedError("sample(thin_by=..., store=False) are not supported; thin with get_chain(thin=)")
+        unknown = set(kwargs) - {"thin_by", "store", "progress", "tune", "skip_initial_state_check", "log_prob0", "rstate0", "blobs0"}
+        if unknown:
+            raise TypeError("sample() got unexpected keyword arguments: %s" % sorted(unknown))
         state = self.run_mcmc(initial_state, iterations)
         for _ in range(int(iterations)):
             yield state
@@ -178,8 +199,8 @@ class EnsembleSampler(object):
             raise AttributeError("you must run the sampler before accessing the results")
         v = arr[discard + thin - 1::thin]
         if flat:
-            v = v.reshape((-1,) + v.shape[2:])
-        return v
+            v = v.reshape((-1,) + tuple(v.shape[2:]))
+        return _host(v)                      # device-resident results: only the requested slice is copied
 
     def get_chain(self, discard=0, flat=False, thin=1):
         return self._get(self._chain, discard, flat, thin)
@@ -203,5 +224,18 @@ class EnsembleSampler(object):
     def acceptance_fraction(self):
         return self.naccepted / float(self.iteration)
 
-    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
-        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
+    def get_autocorr_time(self, discard=0, thin=1, c=5, tol=50, quiet=False, **kwargs):
+        """emcee's ``get_autocorr_time``.  A device-resident chain (engine="device") is analysed where it is by the
+        engine's direct-sum kernel (GP.integrated_time); host chains, and series too long for that kernel, take the
+        FFT estimator above."""
+        tau = None
+        if self._chain is not None and not isinstance(self._chain, np.ndarray) and self.gp is not None:
+            res = self.gp.integrated_time(self._chain, discard=discard, thin=thin, c=c)
+            if res is not None:
+                tau = res[0]
+                n_t = len(range(discard + thin - 1, self._chain.shape[0], thin))
+                if np.any(tol * tau > n_t) and not quiet and tol > 0:
+                    raise AutocorrError(tau, "The chain is shorter than %d times the integrated autocorrelation time" % tol)
+        if tau is None:
+            tau = integrated_time(self.get_chain(discard=discard, thin=thin), c=c, tol=tol, quiet=quiet)
+        return thin * tau

@@ -169,6 +169,11 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
       Nelder-Mead / Powell restated on the device, the whole multistart in a single launch;
     * ``engine="lockstep"``: the restarts advance in lock step on the host (coroutine restatements of the
       same SciPy algorithms) and each round of objective calls is one fused predict+utility launch.
+
+    RNG consumption: all ``nRestarts`` start points are drawn up front (the restarts run side by side), retries draw
+    afterwards.  The reference draws start r, optimises, redraws on rejection, and only then draws start r+1
+    (utility.py:336,364): the two orders consume ``np.random`` identically as long as NO restart is retried; a seeded
+    run in which a retry happens picks different later starts than the reference would.
     """
     if str(method).lower() == "nelder-mead" and options is None:
         options = {"adaptive": True}

@@ -28,6 +28,7 @@ extern "C" {
 #define APGP_NOT_POSDEF 1        /* covariance not positive definite (george: LinAlgError) */
 #define APGP_NOT_COMPUTED 2      /* predict/log-likelihood before a successful factorisation */
 #define APGP_NEEDS_REFACTOR 3    /* apgp_append_point: padded buffers are full, call set_training + factorize */
+#define APGP_NEEDS_HOST 4        /* apgp_integrated_time: chain longer than one CTA's shared memory / window beyond 4096 lags */
 #define APGP_ERR_ARG (-1)
 #define APGP_ERR_CUDA (-2)
 #define APGP_ERR_NOMEM (-3)
@@ -103,6 +104,8 @@ int apgp_grad_log_likelihood(apgp_handle* h, int fit_amp, double* grad);
  * grad_host [R][P] or NULL: gradient of the log-likelihood in the same parameter order (what gpUtils._grad_nll,
  * gpUtils.py:83-111, evaluates one vector at a time); zeros where ll is -inf.  Batched gradients use the
  * one-restart-per-CTA shared-memory kernel and need N(N+1)/2 + N(d+2) doubles <= 220 KB (N <= ~224).
+ * Larger N (log-likelihood only): ONE launch of the fused cluster-per-vector kernel (covariance build, look-ahead
+ * blocked Cholesky, reductions; csrc/chol_group.cuh).
  * Does not disturb the handle's current factorisation. */
 int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fit_amp, double white_noise,
                       double* ll_host, double* grad_host);
@@ -133,6 +136,15 @@ typedef struct apgp_sampler_opts {
 int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double* p0, double* chain, double* logp,
                      double* blob, int* naccept, int on_host);
 
+/* emcee.EnsembleSampler.get_autocorr_time(discard, thin, c, tol=0) / thin, as mcmcUtils.estimateBurnin calls it
+ * (mcmcUtils.py:198; approx.py:853): integrated autocorrelation time per dimension of chain [n_total][W][d] restricted to
+ * chain[discard + thin - 1 :: thin] -- walker-averaged normalised autocorrelation, Sokal window with constant c
+ * (emcee: 5).  The chain may stay where apgp_sampler_run(on_host=0) left it: nothing but d x T doubles crosses PCIe.
+ * tau_out [d] (host), window_out [d] (host, may be NULL).  Returns APGP_NEEDS_HOST when the series does not fit one
+ * CTA's shared memory (n > ~27 000 samples) or the window lies beyond 4096 lags. */
+int apgp_integrated_time(apgp_handle* h, const double* chain, long long n_total, int W, int d, long long discard, int thin,
+                         double c, int on_host, double* tau_out, int* window_out);
+
 /* ---- device-resident local optimisers: one CTA per start, the whole multistart in ONE launch ----------------- */
 #define APGP_OPT_NELDER_MEAD 0
 #define APGP_OPT_POWELL 1
@@ -156,9 +168,10 @@ int apgp_minimize_utility(apgp_handle* h, const apgp_predict_opts* obj, const ap
 /* gpUtils.optimizeGP's inner loop (gpUtils.py:223-247): scipy.optimize.minimize(_nll, p0[r], method=...)["x"] for
  * R restarts at once; _nll as gpUtils.py:46-80 (+inf when default_prior and any |p[1:]| > 20 -- gpUtils.py:22-43 --,
  * when the covariance is not positive definite or the likelihood is not finite).  Rows in george order
- * [mean, (log_constant), log M_0..], P = 1 + fit_amp + d.  Needs the one-restart-per-CTA shared-memory path
- * (apgp_minimize_nll_fits() == 1, N <= ~220); otherwise drive apgp_loglik_batch from a host optimiser.
- * Does not disturb the handle's current factorisation. */
+ * [mean, (log_constant), log M_0..], P = 1 + fit_amp + d.  apgp_minimize_nll_fits() says which kernel runs: 1 = one
+ * restart per CTA with everything in shared memory (N <= ~220), 2 = one thread-block CLUSTER per restart with the
+ * matrix in L2-resident global memory (N <= 4096; optimiser state replicated in every CTA of the cluster), 0 = too
+ * large: drive apgp_loglik_batch from a host optimiser.  Does not disturb the handle's current factorisation. */
 int apgp_minimize_nll(apgp_handle* h, const apgp_opt_opts* opt, const double* p0, int R, int P, int fit_amp,
                       double white_noise, int default_prior, double* p_out, double* f_out, long long* stats,
                       int evaluate_only);

@@ -214,20 +214,15 @@ def test_shard_bounds_cover_exactly():
 
 
 class _OracleGP(object):
-    """Factory for an oracle GP carrying the batched entry points + rebuild hook, so the whole
-    ApproxPosterior driver (lock-step restarts, design-point loop, host-rng MCMC) runs on CPU."""
+    """Factory for an oracle GP with george's constructor signature (oracle.refshim.GP) carrying the batched entry
+    points, so the whole ApproxPosterior driver (lock-step restarts, design-point loop with the reference's
+    rebuild-per-point, host-rng MCMC) runs on CPU."""
 
     @staticmethod
     def make(ndim, metric, mean, white_noise=-12.0):
-        from oracle import GPOracle, UTILITY_BY_NAME
+        from oracle import UTILITY_BY_NAME, refshim
 
-        class G(GPOracle):
-            def rebuild(self, hype, theta, y):
-                g = G(self.ndim, np.exp(self.log_M), mean=self.mean, white_noise=self.white_noise)
-                g.set_parameter_vector(hype)
-                g.compute(theta)
-                return g
-
+        class G(refshim.GP):
             def predict_utility(self, y, t, kind, bounds=None, zeta=0.01):
                 mu, var = self.predict(y, t, return_var=True)
                 fn = UTILITY_BY_NAME[kind]
@@ -243,7 +238,7 @@ class _OracleGP(object):
                 self.recompute(quiet=True)
                 return np.array(out)
 
-        return G(ndim, metric, mean=mean, white_noise=white_noise)
+        return G(kernel=refshim._ExpSquared(metric, ndim), fit_mean=True, mean=mean, white_noise=white_noise)
 
 
 def test_approx_posterior_driver_on_oracle_gp(tmp_path):

@@ -157,13 +157,10 @@ if "cfg1" in which:
     # README configuration: m0=50, m=20, nmax=2, 20 walkers x 2e4 steps, nGPRestarts=3
     from oracle import UTILITY_BY_NAME, default_gp_oracle
 
-    class OracleGP(GPOracle):
-        """CPU oracle behind the same drivers (lock-step entry points + rebuild hook)."""
-        def rebuild(self, hype, theta, y):
-            g = OracleGP(self.ndim, np.exp(self.log_M), mean=self.mean, white_noise=self.white_noise)
-            g.set_parameter_vector(hype); g.compute(theta)
-            return g
+    from oracle import refshim
 
+    class OracleGP(refshim.GP):
+        """CPU oracle behind the same drivers (george constructor signature + lock-step entry points)."""
         def predict_utility(self, y, t, kind, bounds=None, zeta=0.01):
             mu, var = self.predict(y, t, return_var=True)
             fn = UTILITY_BY_NAME[kind]
@@ -208,7 +205,7 @@ if "cfg1" in which:
     # the same drivers on the CPU oracle (one BAPE iteration + a 2000-step per-half-step-batched MCMC)
     theta, y = readme_problem()
     g0 = default_gp_oracle(theta, y)
-    gp = OracleGP(2, np.exp(g0.log_M), mean=g0.mean, white_noise=-12); gp.compute(theta)
+    gp = OracleGP(kernel=refshim._ExpSquared(np.exp(g0.log_M), 2), fit_mean=True, mean=g0.mean, white_noise=-12); gp.compute(theta)
     ap = approx.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lh.rosenbrockLnprior, lnlike=lh.rosenbrockLnlike,
                                 priorSample=lh.rosenbrockSample, bounds=bounds, algorithm="bape")
     ap.run(m=20, nmax=1, estBurnin=True, nGPRestarts=3, mcmcKwargs={"iterations": 2000},
