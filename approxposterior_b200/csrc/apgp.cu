@@ -49,6 +49,8 @@ struct DevBuf {
 struct apgp_handle {
   int device = 0, num_sms = 0;
   cudaStream_t stream = nullptr; bool own_stream = false;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the pipelined host-buffer predict
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int N = 0, d = 0, Np = 0, Npad = 0;
   int variant = 2;       // requested tiling: 2 = 256x64 (fastest measured, profiles/), 1 = 128x128, 0 = 64x256
   int variant_eff = 2;   // tiling the current factorisation was packed for
@@ -130,6 +132,13 @@ int apgp_destroy(apgp_handle* h) {
                     &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->gws, &h->ac_part, &h->ac_f, &h->ac_stage};
   for (DevBuf* b : bufs) b->release();
   if (h->pin) cudaFreeHost(h->pin);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
+    if (h->ev_k[b]) cudaEventDestroy(h->ev_k[b]);
+    if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
+  }
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return APGP_OK;
@@ -319,6 +328,56 @@ static void fill_predict_params(apgp_handle* h, PredictParams& p) {
   p.mean = h->mean; p.amp = h->amp;
 }
 
+// one launch of the predict kernels for the queries described by p (device pointers), on stream st
+static int predict_launch(apgp_handle* h, PredictParams& p, int want_var, cudaStream_t st, int* nl) {
+  const int d = h->d;
+  if (!want_var) { CUI(launch_predict_mean(p, h->num_sms, st, nl)); return APGP_OK; }
+  const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d, p.Q);
+  if (G > 1) {
+    CUI(h->scratch.reserve(predict_group_scratch_bytes(h->Npad, h->num_sms, G)));
+    CUI(h->g_arrive.reserve(sizeof(int) * ((h->num_sms + G - 1) / G)));
+    CUI(h->g_part.reserve(predict_group_part_bytes(h->Npad, h->num_sms, G)));
+    CUI(h->g_plan.reserve(4 * 128 * sizeof(int)));
+    p.scratch = h->scratch.as<double>();
+    p.grp_arrive = h->g_arrive.as<int>(); p.grp_part = h->g_part.as<double>(); p.grp_plan = h->g_plan.as<int>();
+    if (h->plan_Npad != h->Npad || h->plan_G != G || h->plan_d != d) {      // re-plan only when the shape changes
+      int tab[4 * 128];
+      predict_group_plan(h->Npad, h->num_sms, G, d, tab);
+      CU(cudaMemcpyAsync(h->g_plan.p, tab, sizeof(tab), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+      h->plan_Npad = h->Npad; h->plan_G = G; h->plan_d = d;
+    }
+    const int ge = launch_predict_var_grouped(p, h->num_sms, G, st, nl);
+    if (ge == (int)cudaErrorCooperativeLaunchTooLarge) {
+      // the GPU is shared (fewer SMs free than the grid needs for its spin barriers): one tile per CTA instead
+      (void)cudaGetLastError();
+      --*nl;
+      CUI(h->scratch.reserve(predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff)));
+      p.scratch = h->scratch.as<double>();
+      CUI(launch_predict_var(p, h->num_sms, st, h->variant_eff, nl));
+    } else {
+      CUI(ge);
+    }
+  } else {
+    CUI(h->scratch.reserve(predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff)));
+    p.scratch = h->scratch.as<double>();
+    CUI(launch_predict_var(p, h->num_sms, st, h->variant_eff, nl));
+  }
+  return APGP_OK;
+}
+
+static int ensure_pipeline(apgp_handle* h) {
+  if (h->copy_in) return APGP_OK;
+  CU(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CU(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_k[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming));
+  }
+  return APGP_OK;
+}
+
 int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, double* var, double* util,
                  const apgp_predict_opts* o, int on_host) {
   if (!h || !o) return fail(APGP_ERR_ARG, "apgp_predict: null argument");
@@ -336,11 +395,23 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
   p.has_box = o->has_box; p.utility_kind = o->utility; p.ybest = o->ybest; p.zeta = o->zeta;
   for (int i = 0; i < d; ++i) { p.lo[i] = o->lo[i]; p.hi[i] = o->hi[i]; }
   const int nout = (mu ? 1 : 0) + (var ? 1 : 0) + (util ? 1 : 0);
+  int nl = 0;
+  if (!on_host) {
+    p.Xq = Xq; p.mu = mu; p.var = var; p.util = util;
+    { int st_ = predict_launch(h, p, o->want_var, h->stream, &nl); if (st_ != APGP_OK) return st_; }
+    h->launches += nl;
+    return APGP_OK;
+  }
   // small host calls (optimiser rounds: a handful of queries) go through pinned staging: one async H2D,
   // one async D2H, no pageable-memory bounce -- this path is pure latency
   const size_t half = apgp_handle::PIN_DOUBLES / 2;
-  const bool small_call = on_host && (size_t)Q * d <= half && (size_t)Q * (nout ? nout : 1) <= half;
-  if (on_host) {
+  const bool small_call = (size_t)Q * d <= half && (size_t)Q * (nout ? nout : 1) <= half;
+  // large host calls are cut into slices whose H2D copy, kernel and D2H copies overlap on three streams
+  // (double-buffered device staging): end to end the call costs max(kernel, copies) instead of their sum.
+  // Slices are whole multiples of one wave of 256-query tiles (num_sms tiles) so no slice ends in a partial wave.
+  const long long wave = (long long)h->num_sms * 256;
+  const bool pipelined = !small_call && Q >= 4 * wave && !getenv("APGP_NO_PIPELINE");
+  if (!pipelined) {
     CUI(h->stage_in.reserve((size_t)Q * d * 8));
     CUI(h->stage_out.reserve((size_t)Q * 8 * (nout ? nout : 1)));
     const double* src = Xq;
@@ -351,60 +422,60 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
     if (mu) { p.mu = o0; o0 += Q; }
     if (var) { p.var = o0; o0 += Q; }
     if (util) { p.util = o0; o0 += Q; }
-  } else {
-    p.Xq = Xq; p.mu = mu; p.var = var; p.util = util;
-  }
-  int nl = 0;
-  if (o->want_var) {
-    const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d, Q);
-    if (G > 1) {
-      CUI(h->scratch.reserve(predict_group_scratch_bytes(h->Npad, h->num_sms, G)));
-      CUI(h->g_arrive.reserve(sizeof(int) * ((h->num_sms + G - 1) / G)));
-      CUI(h->g_part.reserve(predict_group_part_bytes(h->Npad, h->num_sms, G)));
-      CUI(h->g_plan.reserve(4 * 128 * sizeof(int)));
-      p.scratch = h->scratch.as<double>();
-      p.grp_arrive = h->g_arrive.as<int>(); p.grp_part = h->g_part.as<double>(); p.grp_plan = h->g_plan.as<int>();
-      if (h->plan_Npad != h->Npad || h->plan_G != G || h->plan_d != d) {      // re-plan only when the shape changes
-        int tab[4 * 128];
-        predict_group_plan(h->Npad, h->num_sms, G, d, tab);
-        CU(cudaMemcpyAsync(h->g_plan.p, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->plan_Npad = h->Npad; h->plan_G = G; h->plan_d = d;
-      }
-      const int ge = launch_predict_var_grouped(p, h->num_sms, G, h->stream, &nl);
-      if (ge == (int)cudaErrorCooperativeLaunchTooLarge) {
-        // the GPU is shared (fewer SMs free than the grid needs for its spin barriers): one tile per CTA instead
-        (void)cudaGetLastError();
-        --nl;
-        CUI(h->scratch.reserve(predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff)));
-        p.scratch = h->scratch.as<double>();
-        CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant_eff, &nl));
-      } else {
-        CUI(ge);
-      }
+    { int st_ = predict_launch(h, p, o->want_var, h->stream, &nl); if (st_ != APGP_OK) return st_; }
+    h->launches += nl;
+    if (small_call) {
+      double* hp = h->pin + half;
+      CU(cudaMemcpyAsync(hp, h->stage_out.p, (size_t)Q * 8 * nout, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      if (mu) { memcpy(mu, hp, (size_t)Q * 8); hp += Q; }
+      if (var) { memcpy(var, hp, (size_t)Q * 8); hp += Q; }
+      if (util) { memcpy(util, hp, (size_t)Q * 8); hp += Q; }
     } else {
-      const size_t sb = predict_scratch_bytes(h->Npad, h->num_sms, h->variant_eff);
-      CUI(h->scratch.reserve(sb));
-      p.scratch = h->scratch.as<double>();
-      CUI(launch_predict_var(p, h->num_sms, h->stream, h->variant_eff, &nl));
+      if (mu) CU(cudaMemcpyAsync(mu, p.mu, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
+      if (var) CU(cudaMemcpyAsync(var, p.var, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
+      if (util) CU(cudaMemcpyAsync(util, p.util, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
     }
-  } else {
-    CUI(launch_predict_mean(p, h->num_sms, h->stream, &nl));
+    return APGP_OK;
+  }
+  { int st_ = ensure_pipeline(h); if (st_ != APGP_OK) return st_; }
+  long long per = (Q / 8) / wave * wave;
+  if (per < wave) per = wave;
+  const int no = nout ? nout : 1;
+  CUI(h->stage_in.reserve((size_t)2 * per * d * 8));
+  CUI(h->stage_out.reserve((size_t)2 * per * 8 * no));
+  // the copy streams start after everything already queued on the compute stream (e.g. a pending factorisation)
+  CU(cudaEventRecord(h->ev_k[0], h->stream)); CU(cudaEventRecord(h->ev_k[1], h->stream));
+  CU(cudaEventRecord(h->ev_out[0], h->stream)); CU(cudaEventRecord(h->ev_out[1], h->stream));
+  int slice = 0;
+  for (long long q0 = 0; q0 < Q; q0 += per, ++slice) {
+    const long long qn = (Q - q0 < per) ? (Q - q0) : per;
+    const int b = slice & 1;
+    double* din = h->stage_in.as<double>() + (size_t)b * per * d;
+    double* dout = h->stage_out.as<double>() + (size_t)b * per * no;
+    CU(cudaStreamWaitEvent(h->copy_in, h->ev_k[b], 0));                 // the kernel of slice - 2 has read this buffer
+    CU(cudaMemcpyAsync(din, Xq + (size_t)q0 * d, (size_t)qn * d * 8, cudaMemcpyHostToDevice, h->copy_in));
+    CU(cudaEventRecord(h->ev_in[b], h->copy_in));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));                // the D2H of slice - 2 has drained this buffer
+    PredictParams ps = p;
+    ps.Q = qn; ps.Xq = din;
+    double* o0 = dout;
+    if (mu) { ps.mu = o0; o0 += qn; }
+    if (var) { ps.var = o0; o0 += qn; }
+    if (util) { ps.util = o0; o0 += qn; }
+    { int st_ = predict_launch(h, ps, o->want_var, h->stream, &nl); if (st_ != APGP_OK) return st_; }
+    CU(cudaEventRecord(h->ev_k[b], h->stream));
+    CU(cudaStreamWaitEvent(h->copy_out, h->ev_k[b], 0));
+    if (mu) CU(cudaMemcpyAsync(mu + q0, ps.mu, (size_t)qn * 8, cudaMemcpyDeviceToHost, h->copy_out));
+    if (var) CU(cudaMemcpyAsync(var + q0, ps.var, (size_t)qn * 8, cudaMemcpyDeviceToHost, h->copy_out));
+    if (util) CU(cudaMemcpyAsync(util + q0, ps.util, (size_t)qn * 8, cudaMemcpyDeviceToHost, h->copy_out));
+    CU(cudaEventRecord(h->ev_out[b], h->copy_out));
   }
   h->launches += nl;
-  if (on_host && small_call) {
-    double* hp = h->pin + half;
-    CU(cudaMemcpyAsync(hp, h->stage_out.p, (size_t)Q * 8 * nout, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    if (mu) { memcpy(mu, hp, (size_t)Q * 8); hp += Q; }
-    if (var) { memcpy(var, hp, (size_t)Q * 8); hp += Q; }
-    if (util) { memcpy(util, hp, (size_t)Q * 8); hp += Q; }
-  } else if (on_host) {
-    if (mu) CU(cudaMemcpyAsync(mu, p.mu, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (var) CU(cudaMemcpyAsync(var, p.var, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (util) CU(cudaMemcpyAsync(util, p.util, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-  }
+  CU(cudaStreamSynchronize(h->copy_out));
+  CU(cudaStreamSynchronize(h->stream));
   return APGP_OK;
 }
 
@@ -616,15 +687,20 @@ int apgp_integrated_time(apgp_handle* h, const double* chain, long long n_total,
     bool all = true;
     for (int k = 0; k < d; ++k) {
       if (found[k]) continue;
-      double cum = 0.0;
+      // emcee.autocorr.auto_window: m = arange(n) < c * taus; window = argmin(m) if any(m) else n - 1.
+      // argmin(m) is the FIRST M where the condition fails -- and 0 when it never fails (argmin of an all-True
+      // array), in which case emcee reports tau(0) = 2 f(0) - 1 = 1; kept.  (All-False needs taus[0] <= 0 or NaN:
+      // the first failure is then M = 0 and the reported value is the same NaN.)
+      double cum = 0.0, tau0 = NAN;
       int win = -1;
       double tw = NAN;
       for (int M = 0; M < T; ++M) {
         cum += f[(size_t)k * T + M];
         const double taus = 2.0 * cum - 1.0;
-        if (!((double)M < c * taus)) { win = M; tw = taus; break; }      // first M where (M < c tau(M)) is false
-        if (M == n - 1) { win = M; tw = taus; }                          // no such M: emcee takes the last lag
+        if (M == 0) tau0 = taus;
+        if (!((double)M < c * taus)) { win = M; tw = taus; break; }
       }
+      if (win < 0 && T == n) { win = 0; tw = tau0; }
       if (win >= 0) { found[k] = 1; tau_out[k] = tw; if (window_out) window_out[k] = win; }
       else all = false;
     }

@@ -8,7 +8,7 @@ plumbing (NCCL on GPUs, gloo in the CPU tests); there is no per-step communicati
 import numpy as np
 
 __all__ = ["world", "shard_bounds", "gather_best", "gather_concat", "scan_utility_sharded",
-           "run_ensembles_sharded", "best_restart_sharded"]
+           "run_ensembles_sharded", "best_restart_sharded", "predict_sharded", "optimize_gp_sharded"]
 
 
 def world():
@@ -97,3 +97,57 @@ def best_restart_sharded(params, mll):
     m = np.where(np.isfinite(allr[:, 0]), allr[:, 0], -np.inf)
     i = int(np.argmax(m))
     return allr[i, 1:], float(allr[i, 0])
+
+
+def predict_sharded(gp, y, n_queries_total, make_queries, chunk=1 << 22, want_var=True, utility=None, bounds=None):
+    """BASELINE config 5: ``n_queries_total`` query points split over the ranks as contiguous blocks; rank r
+    produces its block chunk by chunk with ``make_queries(first_index, count) -> torch CUDA tensor [count, d]``
+    (e.g. a counter-based generator, so the points do not depend on the number of ranks), evaluates the fused predict
+    kernel on each chunk and keeps running sums; ONE all-gather of (count, sum mu, sum var, min utility) per call
+    closes it.  Returns dict(count, sum_mu, sum_var, min_util) over ALL ranks."""
+    import torch
+    rank, ws = world()
+    lo, hi = shard_bounds(n_queries_total, rank, ws)
+    gp._sync_y(y)
+    gp.recompute()
+    ybest = float(np.max(gp._y))
+    acc = torch.zeros(3, dtype=torch.float64, device=torch.device("cuda", gp._device))
+    umin = float("inf")
+    for s in range(lo, hi, chunk):
+        c = min(chunk, hi - s)
+        q = make_queries(s, c)
+        mu, var, u = gp._predict_raw(q, want_var, utility=utility, bounds=bounds, ybest=ybest)
+        acc[0] += c
+        acc[1] += mu.sum()
+        if var is not None:
+            acc[2] += var.sum()
+        if u is not None:
+            umin = min(umin, float(torch.nan_to_num(u, nan=float("inf")).min()))
+    pack = np.concatenate([acc.cpu().numpy(), [umin]])
+    allp = gather_concat(pack[None, :], axis=0)
+    return dict(count=int(allp[:, 0].sum()), sum_mu=float(allp[:, 1].sum()), sum_var=float(allp[:, 2].sum()),
+                min_util=float(allp[:, 3].min()))
+
+
+def optimize_gp_sharded(gp, y, x0s, method="powell", options=None, default_prior=True):
+    """gpUtils.optimizeGP's restarts (reference gpUtils.py:223-254) split over the ranks: every rank holds the same
+    ``x0s`` [R, P] (same seed), minimises its contiguous block on its GPU with ONE ``apgp_minimize_nll`` launch, and
+    one all-gather of (mll, p) rows picks the best restart on every rank.  Returns (p_best, mll_best, nfev_total)."""
+    rank, ws = world()
+    x0s = np.atleast_2d(np.asarray(x0s, dtype=np.float64))
+    lo, hi = shard_bounds(x0s.shape[0], rank, ws)
+    P = x0s.shape[1]
+    if hi > lo:
+        p, f, nfev = gp.minimize_nll(x0s[lo:hi], y, method=method, options=options, default_prior=default_prior)
+        rows = np.hstack([np.where(np.isfinite(f), -f, -np.inf)[:, None], p, nfev[:, None].astype(np.float64)])
+    else:
+        rows = np.empty((0, P + 2))
+    # equal-shape gather: pad every rank's block to the largest block
+    width = -(-x0s.shape[0] // ws)
+    pad = np.full((width, P + 2), -np.inf)
+    pad[:, -1] = 0.0
+    pad[:rows.shape[0]] = rows
+    allr = gather_concat(pad, axis=0)
+    m = np.where(np.isfinite(allr[:, 0]), allr[:, 0], -np.inf)
+    i = int(np.argmax(m))
+    return allr[i, 1:1 + P], float(allr[i, 0]), int(allr[:, -1].sum())

@@ -124,7 +124,14 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
                  and (gpHyperPrior is defaultHyperPrior or gpHyperPrior is None)
                  and hasattr(gp, "minimize_nll") and gp.can_minimize_nll())
 
-    if on_device:
+    from . import dist as _dist
+    if on_device and _dist.world()[1] > 1:
+        # one process per GPU (torchrun): the restarts are sharded over the ranks, one all-gather picks the winner
+        pbest, mbest, nfev = _dist.optimize_gp_sharded(gp, y, np.array(x0s), method=method, options=options,
+                                                       default_prior=gpHyperPrior is not None)
+        res, mll = [pbest], [mbest]
+        optimizeGP.last_stats = dict(batches=1, evals=int(nfev), scheduler="device-sharded", world=_dist.world()[1])
+    elif on_device:
         res, fres, nfev = gp.minimize_nll(np.array(x0s), y, method=method, options=options,
                                           default_prior=gpHyperPrior is not None)
         res = list(res)

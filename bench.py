@@ -23,6 +23,11 @@ import sys
 import threading
 import time
 
+# The CPU arms (cpu_baseline, --impl reference) use every host core whatever the launcher left in the environment:
+# torch.distributed.run exports OMP_NUM_THREADS=1, which pinned the round-1 reference arm to one BLAS thread at N > 1.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -32,7 +37,17 @@ N_TRAIN, DIM, Q_PER_GPU = 2048, 5, 1 << 20
 METRIC = "GP-surrogate lnprob evals/s (fp64 mean+var, N=2048, d=5)"
 UNIT = "evals/s"
 BOUNDS = [(-5.0, 5.0)] * DIM
-NCU_TRAFFIC_BYTES = 36.5e9       # dram__bytes_read.sum + dram__bytes_write.sum of one predict_var_group launch (profiles/)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, read from the committed ncu
+    summary (profiles/ncu_traffic.json: {"bytes": ..., "kernel": ..., "source": <profile file>, "git": <commit the
+    capture was taken at>}); None when the file is missing, so a stale constant cannot linger in the source."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def flops_per_eval(N, d):
@@ -133,7 +148,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"sample_per_step": nq}),
+            "config": workload_config({"sample_per_step": nq, "blas_threads": blas_threads(),
+                                       "host_cores": os.cpu_count()}),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                              "sample": "%d candidates per step (bounded sample of 2^20), oracle port of "
                                        "george predict+BAPE, all BLAS threads" % nq},
@@ -370,9 +386,10 @@ def run_gpu(args):
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
-                             "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture "
-                                             "profiles/r01_predict_var_grouped_ncu_summary.txt): every K* panel is written "
+                             "frac": achieved / peak, "traffic": (ncu_traffic() or {}).get("bytes"),
+                             "traffic_source": ncu_traffic(),
+                             "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture named in "
+                                             "traffic_source): every K* panel is written "
                                              "once (17 GB per 2^20 queries) and re-read from L2 (84% hit) because 8 CTAs "
                                              "share one query tile; the one-tile-per-CTA kernel of the same round moved "
                                              "294 GB.  Algorithmic I/O is 67 MB -- the kernel is FP64-tensor-pipe bound "
@@ -412,9 +429,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configuration; cfg3 (default) is the one the headline metric is quoted on")
+    ap.add_argument("--N", type=int, default=512, help="cfg5: training-set size of the sweep point")
+    ap.add_argument("--d", type=int, default=5, help="cfg5: input dimension of the sweep point")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-bape", action="store_true", help="skip the secondary BAPE-iteration-time measurement")
     args = ap.parse_args()
+    if args.config != "cfg3":
+        import bench_configs
+        me = sys.modules[__name__]
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                bench_configs.REFERENCE[args.config](args, me)
+        else:
+            args.warmup = max(args.warmup, 3 if args.config in ("cfg2", "cfg5") else 1)
+            bench_configs.GPU[args.config](args, me)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -42,7 +42,17 @@ def _worker(rank, ws, port, q):
         mll = np.array([-10.0 + rank, np.nan if rank == 0 else -np.inf])
         pbest, mbest = apd.best_restart_sharded(p_loc, mll)
         ok3 = mbest == -10.0 + (ws - 1) and pbest[0] == ws - 1 and pbest[1] == 1.0
-        q.put((rank, bool(ok1), bool(ok2), bool(ok3)))
+        # optimizeGP restarts sharded over ranks (uneven split: 5 restarts on 2 ranks), fake engine on CPU
+        class FakeGP(object):
+            def minimize_nll(self, x0s, y, method="powell", options=None, default_prior=True):
+                x0s = np.atleast_2d(x0s)
+                f = np.sum((x0s - 0.3) ** 2, axis=1)
+                f[np.any(x0s > 1.9, axis=1)] = np.inf           # a failed restart never wins
+                return x0s * 0.5, f, np.full(len(x0s), 7, dtype=np.int64)
+        x0s = np.array([[2.0, 0.0], [1.0, 1.0], [0.5, 0.25], [0.3, 0.31], [-1.0, 0.0]])
+        pb, mb, nfev = apd.optimize_gp_sharded(FakeGP(), None, x0s)
+        ok4 = np.array_equal(pb, x0s[3] * 0.5) and np.isclose(mb, -np.sum((x0s[3] - 0.3) ** 2)) and nfev == 35
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3 and ok4)))
     finally:
         dist.destroy_process_group()
 
