@@ -564,3 +564,34 @@ def test_sampler_cluster_replicas_give_the_same_chain(cluster, monkeypatch):
     out = gp.run_ensembles(y, q0, 40, bounds, nens=1, replay={k: ref[k][None] for k in ("inds", "zz", "rint", "logu")})
     np.testing.assert_allclose(out["chain"], ref["chain"], rtol=1e-9, atol=1e-9)
     assert np.array_equal(out["naccepted"], ref["naccepted"])
+
+
+@pytest.mark.parametrize("N,d,Q,kind", [(300, 3, 200000, "bape"), (1100, 5, 170001, None), (256, 2, 600000, "agp")])
+def test_pipelined_host_predict_equals_device_resident(N, d, Q, kind, monkeypatch):
+    """apgp_predict(on_host=1) cuts large calls into slices whose H2D copy, kernel and D2H copies overlap on three
+    streams (double-buffered staging).  Results must be bit-identical to the device-resident call and to the serial
+    host path, for pageable and for pinned host buffers, mean-only and fused utility alike."""
+    import torch
+    X, y, logM, _ = synthetic_gp_problem(N, d, seed=N + 1)
+    gp, _ = make_pair(X, y, logM)
+    g = torch.Generator(device="cuda"); g.manual_seed(N)
+    q = -5.5 + 11.0 * torch.rand((Q, d), dtype=torch.float64, device="cuda", generator=g)
+    bounds = [(-5.0, 5.0)] * d
+    ref = gp._predict_raw(q, True, utility=kind, bounds=bounds)
+    qh = q.cpu().numpy()
+    pinned_q = torch.empty((Q, d), dtype=torch.float64).pin_memory(); pinned_q.copy_(q.cpu())
+    for host_q in (qh, pinned_q.numpy()):
+        for serial in (False, True):
+            if serial:
+                monkeypatch.setenv("APGP_NO_PIPELINE", "1")
+            else:
+                monkeypatch.delenv("APGP_NO_PIPELINE", raising=False)
+            out = gp._predict_raw(host_q, True, utility=kind, bounds=bounds)
+            for a, b in zip(out, ref):
+                if b is None:
+                    assert a is None
+                else:
+                    assert np.array_equal(a, b.cpu().numpy(), equal_nan=True)
+    monkeypatch.delenv("APGP_NO_PIPELINE", raising=False)
+    m_only = gp._predict_raw(qh, False)[0]
+    assert np.array_equal(m_only, gp._predict_raw(q, False)[0].cpu().numpy(), equal_nan=True)
