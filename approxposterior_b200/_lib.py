@@ -58,6 +58,13 @@ _SIGNATURES = {
                                     C.c_void_p]),
     "apgp_sampler_run": (C.c_int, [C.c_void_p, C.POINTER(SamplerOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int]),
+    "apgp_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "apgp_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "apgp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "apgp_comm_group_start": (C.c_int, []),
+    "apgp_comm_group_end": (C.c_int, []),
+    "apgp_comm_broadcast_factor": (C.c_int, [C.c_void_p, C.c_int]),
+    "apgp_comm_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
     "apgp_integrated_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_longlong, C.c_int,
                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "apgp_minimize_utility": (C.c_int, [C.c_void_p, C.POINTER(PredictOpts), C.POINTER(OptOpts), C.c_void_p, C.c_int,

@@ -67,6 +67,8 @@ struct apgp_handle {
   static constexpr size_t PIN_DOUBLES = 32768;   // 256 KB: [0, PIN/2) inputs, [PIN/2, PIN) outputs
   DevBuf bK, bDinv, br, bscal, binfo, bhyper, bll, bgrad;   // batched log-likelihood workspace
   DevBuf ac_part, ac_f, ac_stage;                            // autocorrelation partial sums, f(t), host-chain staging
+  void* comm = nullptr; int comm_rank = 0, comm_world = 1;  // NCCL communicator (apgp_comm_init)
+  DevBuf c_hdr, c_send, c_recv;                               // collective staging
   DevBuf gws;                                                // fused cluster-per-restart workspace (chol_group.cuh)
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
   DevBuf o_in, o_x, o_f, o_stats;      // device optimiser staging
@@ -129,8 +131,9 @@ int apgp_destroy(apgp_handle* h) {
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
                     &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->ap_k, &h->ap_l, &h->ap_u, &h->ap_x, &h->bK,
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
-                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->gws, &h->ac_part, &h->ac_f, &h->ac_stage};
+                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->gws, &h->ac_part, &h->ac_f, &h->ac_stage, &h->c_hdr, &h->c_send, &h->c_recv};
   for (DevBuf* b : bufs) b->release();
+  if (h->comm) comm_destroy(h->comm);
   if (h->pin) cudaFreeHost(h->pin);
   for (int b = 0; b < 2; ++b) {
     if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
@@ -643,6 +646,105 @@ int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* o, const double* p
     CU(cudaMemcpyAsync(logp, p.logp, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(blob, p.blob, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(naccept, p.naccept, W * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return APGP_OK;
+}
+
+// ---- multi-GPU: one handle per GPU, NCCL over NVLink (comm.cu) ------------------------------------------------------
+int apgp_comm_unique_id(char id_out[128]) {
+  if (!id_out) return fail(APGP_ERR_ARG, "apgp_comm_unique_id: null argument");
+  if (comm_unique_id(id_out)) return fail(APGP_ERR_COMM, comm_last_error());
+  return APGP_OK;
+}
+int apgp_comm_group_start(void) { if (comm_group_start()) return fail(APGP_ERR_COMM, comm_last_error()); return APGP_OK; }
+int apgp_comm_group_end(void) { if (comm_group_end()) return fail(APGP_ERR_COMM, comm_last_error()); return APGP_OK; }
+
+int apgp_comm_init(apgp_handle* h, const char id[128], int rank, int world) {
+  if (!h || !id || world < 1 || rank < 0 || rank >= world) return fail(APGP_ERR_ARG, "apgp_comm_init: bad argument");
+  Guard g(h->device);
+  if (h->comm) { comm_destroy(h->comm); h->comm = nullptr; }
+  if (comm_init(&h->comm, id, rank, world)) return fail(APGP_ERR_COMM, comm_last_error());
+  h->comm_rank = rank; h->comm_world = world;
+  return APGP_OK;
+}
+int apgp_comm_destroy(apgp_handle* h) {
+  if (!h) return APGP_OK;
+  Guard g(h->device);
+  if (h->comm) { cudaStreamSynchronize(h->stream); comm_destroy(h->comm); h->comm = nullptr; }
+  h->comm_rank = 0; h->comm_world = 1;
+  return APGP_OK;
+}
+
+// header of a broadcast factorisation: everything host-side that apgp_factorize leaves in the handle
+struct FactorHeader {
+  int N, d, Np, Npad, variant_eff, factored;
+  double mean, amp, white_noise, logdet, loglik;
+  double log_metric[APGP_MAX_DIM];
+};
+
+int apgp_comm_broadcast_factor(apgp_handle* h, int root) {
+  if (!h || !h->comm) return fail(APGP_ERR_ARG, "apgp_comm_broadcast_factor: apgp_comm_init first");
+  if (root < 0 || root >= h->comm_world) return fail(APGP_ERR_ARG, "apgp_comm_broadcast_factor: bad root");
+  Guard g(h->device);
+  const bool is_root = h->comm_rank == root;
+  if (is_root && !h->factored) return fail(APGP_NOT_COMPUTED, "apgp_comm_broadcast_factor: the root's GP is not computed");
+  FactorHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  if (is_root) {
+    hd.N = h->N; hd.d = h->d; hd.Np = h->Np; hd.Npad = h->Npad; hd.variant_eff = h->variant_eff; hd.factored = 1;
+    hd.mean = h->mean; hd.amp = h->amp; hd.white_noise = h->white_noise; hd.logdet = h->logdet; hd.loglik = h->loglik;
+    for (int i = 0; i < h->d; ++i) hd.log_metric[i] = h->log_metric[i];
+  }
+  CUI(h->c_hdr.reserve(sizeof(hd)));
+  if (is_root) CU(cudaMemcpyAsync(h->c_hdr.p, &hd, sizeof(hd), cudaMemcpyHostToDevice, h->stream));
+  if (comm_broadcast_bytes(h->comm, h->c_hdr.p, sizeof(hd), root, h->stream)) return fail(APGP_ERR_COMM, comm_last_error());
+  CU(cudaMemcpyAsync(&hd, h->c_hdr.p, sizeof(hd), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (!hd.factored || hd.N < 1 || hd.d < 1 || hd.d > APGP_MAX_DIM) return fail(APGP_ERR_COMM, "apgp_comm_broadcast_factor: bad header");
+  const int N = hd.N, d = hd.d, Np = hd.Np;
+  if (!is_root) {
+    h->N = N; h->d = d; h->Np = Np; h->Npad = hd.Npad; h->variant_eff = hd.variant_eff;
+    h->mean = hd.mean; h->amp = hd.amp; h->white_noise = hd.white_noise; h->logdet = hd.logdet; h->loglik = hd.loglik;
+    for (int i = 0; i < d; ++i) h->log_metric[i] = hd.log_metric[i];
+    h->has_training = true; h->has_hyper = true; h->factored = false;
+    CUI(h->X.reserve((size_t)N * d * 8)); CUI(h->y.reserve((size_t)N * 8));
+    CUI(h->K.reserve((size_t)Np * Np * 8)); CUI(h->Dinv.reserve((size_t)Np * 64 * 8)); CUI(h->r.reserve((size_t)Np * 8));
+    CUI(h->Linv.reserve((size_t)Np * Np * 8)); CUI(h->work.reserve((size_t)Np * Np * 8));
+    CUI(h->alpha.reserve((size_t)Np * 8)); CUI(h->alphaA.reserve((size_t)h->Npad * 8)); CUI(h->Xs.reserve((size_t)d * h->Npad * 8));
+    CUI(h->scal.reserve(4 * 8)); CUI(h->info.reserve(4)); CUI(h->hyper.reserve((3 + APGP_MAX_DIM) * 8)); CUI(h->qscale.reserve(APGP_MAX_DIM * 8));
+    const int BN = predict_variant_bn(h->variant_eff);
+    CUI(h->LinvF.reserve((size_t)linvf_total_tiles(h->Npad, BN) * BN * 16 * 8));
+  }
+  struct { DevBuf* b; size_t bytes; } parts[] = {
+      {&h->X, (size_t)N * d * 8}, {&h->y, (size_t)N * 8}, {&h->K, (size_t)Np * Np * 8}, {&h->Dinv, (size_t)Np * 64 * 8},
+      {&h->r, (size_t)Np * 8}, {&h->Linv, (size_t)Np * Np * 8}, {&h->alpha, (size_t)Np * 8}, {&h->hyper, (size_t)(3 + d) * 8},
+      {&h->scal, 16}};
+  for (auto& pt : parts)
+    if (comm_broadcast_bytes(h->comm, pt.b->p, pt.bytes, root, h->stream)) return fail(APGP_ERR_COMM, comm_last_error());
+  if (!is_root) {
+    int nl = 0;
+    { int st_ = pack_predict_operands(h, &nl); if (st_ != APGP_OK) return st_; }
+    h->launches += nl;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  h->factored = true;
+  return APGP_OK;
+}
+
+int apgp_comm_allgather(apgp_handle* h, const double* send, double* recv, long long count, int on_host) {
+  if (!h || !h->comm || !send || !recv || count < 0) return fail(APGP_ERR_ARG, "apgp_comm_allgather: bad argument");
+  if (count == 0) return APGP_OK;
+  Guard g(h->device);
+  const double* s = send; double* r = recv;
+  if (on_host) {
+    CUI(h->c_send.reserve((size_t)count * 8)); CUI(h->c_recv.reserve((size_t)count * 8 * h->comm_world));
+    CU(cudaMemcpyAsync(h->c_send.p, send, (size_t)count * 8, cudaMemcpyHostToDevice, h->stream));
+    s = h->c_send.as<double>(); r = h->c_recv.as<double>();
+  }
+  if (comm_allgather_doubles(h->comm, s, r, (size_t)count, h->stream)) return fail(APGP_ERR_COMM, comm_last_error());
+  if (on_host) {
+    CU(cudaMemcpyAsync(recv, r, (size_t)count * 8 * h->comm_world, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
   return APGP_OK;

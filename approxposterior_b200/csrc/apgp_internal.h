@@ -169,4 +169,14 @@ size_t autocorr_partial_bytes(int W, int d, int T, int num_sms, int* G_out, int*
 int launch_autocorr(const double* chain, long long off, int thin, int n, int W, int d, int T, int num_sms, double* partial,
                     double* f_dev, cudaStream_t st, int* launches);
 
+// ---- NCCL plumbing (comm.cu; NCCL bound at run time with dlopen) ---------------------
+int comm_unique_id(char out[128]);
+int comm_init(void** comm_out, const char id_bytes[128], int rank, int world);
+int comm_destroy(void* comm);
+int comm_broadcast_bytes(void* comm, void* buf_dev, size_t bytes, int root, cudaStream_t st);
+int comm_allgather_doubles(void* comm, const double* send_dev, double* recv_dev, size_t count, cudaStream_t st);
+int comm_group_start();
+int comm_group_end();
+const char* comm_last_error();
+
 }  // namespace apgp

@@ -32,6 +32,7 @@ extern "C" {
 #define APGP_ERR_ARG (-1)
 #define APGP_ERR_CUDA (-2)
 #define APGP_ERR_NOMEM (-3)
+#define APGP_ERR_COMM (-4)       /* NCCL could not be loaded / a collective failed */
 
 #define APGP_MAX_DIM 32
 
@@ -135,6 +136,25 @@ typedef struct apgp_sampler_opts {
  * per ensemble (same chains bit for bit).  nwalkers * (24 ndim + 72) bytes must fit one CTA's shared memory. */
 int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double* p0, double* chain, double* logp,
                      double* blob, int* naccept, int on_host);
+
+/* ---- multi-GPU: one handle per GPU, NCCL over NVLink / NVSwitch (bound at run time: dlopen libnccl.so.2) ----------
+ * The path shards by independent units (queries / ensembles / restarts: SURVEY 8e), so the only exchanges are the
+ * replication of a factorised GP and the concatenation of per-rank results -- what a multi-process driver around
+ * approx.py:664-672 (candidate scores), :839-847 (chains) and gpUtils.py:223-254 (restart results) needs.
+ *   apgp_comm_unique_id      rank 0 creates the 128-byte NCCL id; the caller distributes it (file, MPI, TCP store)
+ *   apgp_comm_init           ncclCommInitRank on the handle's device (collective over all `world` handles; several
+ *                            handles of ONE process must be initialised between apgp_comm_group_start/_end)
+ *   apgp_comm_broadcast_factor  replicate the root's factorisation (training set, hyper-parameters, L, L^-1, alpha,
+ *                            log-likelihood) into every other handle, which then predicts / samples without having
+ *                            factorised: <= 2 Np^2 doubles over NVLink instead of an O(N^3) refactorisation per GPU
+ *   apgp_comm_allgather      recv[world][count] <- every rank's send[count] (rank order); host or device buffers */
+int apgp_comm_unique_id(char id_out[128]);
+int apgp_comm_init(apgp_handle* h, const char id[128], int rank, int world);
+int apgp_comm_destroy(apgp_handle* h);
+int apgp_comm_group_start(void);
+int apgp_comm_group_end(void);
+int apgp_comm_broadcast_factor(apgp_handle* h, int root);
+int apgp_comm_allgather(apgp_handle* h, const double* send, double* recv, long long count, int on_host);
 
 /* emcee.EnsembleSampler.get_autocorr_time(discard, thin, c, tol=0) / thin, as mcmcUtils.estimateBurnin calls it
  * (mcmcUtils.py:198; approx.py:853): integrated autocorrelation time per dimension of chain [n_total][W][d] restricted to

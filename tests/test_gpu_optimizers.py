@@ -167,9 +167,11 @@ def test_device_optimizer_large_training_set_reads_linv_from_global():
     xh, fh, _ = _run_host(lambda t0: opt.nelder_mead_gen(t0, adaptive=True, _stable=True), starts,
                           lambda P: gp.minimize_utility(y, np.array(P), "agp", bounds=bounds, evaluate_only=True)[1])
     assert np.array_equal(xd, xh) and np.array_equal(fd, fh)
-    assert not gp.can_minimize_nll() or True       # informational: N=400 is beyond the shared-memory nll path
-    with pytest.raises(Exception):
-        gp.minimize_nll(gp.get_parameter_vector()[None, :], y)
+    # N = 400 is beyond the one-CTA shared-memory nll objective: the cluster-per-restart objective takes over
+    # (tests/test_gpu_chol_group.py); only training sets beyond 4096 points are refused
+    assert gp.can_minimize_nll()
+    p, f, nfev = gp.minimize_nll(gp.get_parameter_vector()[None, :], y, options={"maxiter": 1})
+    assert np.isfinite(f[0]) and nfev[0] > 3
 
 
 def test_find_map_on_device():

@@ -65,7 +65,7 @@ for N in [int(v) for v in which]:
                 dt = (time.perf_counter() - t0) / reps
                 print(json.dumps(dict(config="cfg4-loglik", N=N, d=d, R=R, path=path, cluster=C, ms_per_batch=dt * 1e3,
                                       nll_evals_per_s=R / dt, tflops_algorithmic=R * F / dt * 1e-12,
-                                      frac_of_dgemm=R * F / dt * 1e-12 / (PEAK * 1e-3), dgemm_tflops=PEAK * 1e-3,
+                                      frac_of_dgemm=R * F / dt * 1e-12 / PEAK, dgemm_tflops=PEAK,
                                       finite=int(np.isfinite(ll).sum()))), flush=True)
     os.environ.pop("APGP_CHOL_CLUSTER", None)
     os.environ.pop("APGP_LOGLIK_PATH", None)
