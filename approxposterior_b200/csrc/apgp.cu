@@ -332,10 +332,12 @@ static void fill_predict_params(apgp_handle* h, PredictParams& p) {
 }
 
 // one launch of the predict kernels for the queries described by p (device pointers), on stream st
-static int predict_launch(apgp_handle* h, PredictParams& p, int want_var, cudaStream_t st, int* nl) {
+// Qplan: the size of the WHOLE call this launch is a slice of -- the group size (hence the summation order of the mean)
+// must not depend on how a host call was sliced
+static int predict_launch(apgp_handle* h, PredictParams& p, int want_var, cudaStream_t st, int* nl, long long Qplan) {
   const int d = h->d;
   if (!want_var) { CUI(launch_predict_mean(p, h->num_sms, st, nl)); return APGP_OK; }
-  const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d, p.Q);
+  const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d, Qplan);
   if (G > 1) {
     CUI(h->scratch.reserve(predict_group_scratch_bytes(h->Npad, h->num_sms, G)));
     CUI(h->g_arrive.reserve(sizeof(int) * ((h->num_sms + G - 1) / G)));
@@ -401,7 +403,7 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
   int nl = 0;
   if (!on_host) {
     p.Xq = Xq; p.mu = mu; p.var = var; p.util = util;
-    { int st_ = predict_launch(h, p, o->want_var, h->stream, &nl); if (st_ != APGP_OK) return st_; }
+    { int st_ = predict_launch(h, p, o->want_var, h->stream, &nl, Q); if (st_ != APGP_OK) return st_; }
     h->launches += nl;
     return APGP_OK;
   }
@@ -425,7 +427,7 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
     if (mu) { p.mu = o0; o0 += Q; }
     if (var) { p.var = o0; o0 += Q; }
     if (util) { p.util = o0; o0 += Q; }
-    { int st_ = predict_launch(h, p, o->want_var, h->stream, &nl); if (st_ != APGP_OK) return st_; }
+    { int st_ = predict_launch(h, p, o->want_var, h->stream, &nl, Q); if (st_ != APGP_OK) return st_; }
     h->launches += nl;
     if (small_call) {
       double* hp = h->pin + half;
@@ -468,7 +470,7 @@ int apgp_predict(apgp_handle* h, const double* Xq, long long Q, double* mu, doub
     if (mu) { ps.mu = o0; o0 += qn; }
     if (var) { ps.var = o0; o0 += qn; }
     if (util) { ps.util = o0; o0 += qn; }
-    { int st_ = predict_launch(h, ps, o->want_var, h->stream, &nl); if (st_ != APGP_OK) return st_; }
+    { int st_ = predict_launch(h, ps, o->want_var, h->stream, &nl, Q); if (st_ != APGP_OK) return st_; }
     CU(cudaEventRecord(h->ev_k[b], h->stream));
     CU(cudaStreamWaitEvent(h->copy_out, h->ev_k[b], 0));
     if (mu) CU(cudaMemcpyAsync(mu + q0, ps.mu, (size_t)qn * 8, cudaMemcpyDeviceToHost, h->copy_out));

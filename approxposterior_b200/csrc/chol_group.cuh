@@ -41,7 +41,7 @@ constexpr int CG_TILE = CG_T * CG_LD;    // doubles per staged tile
 constexpr size_t CG_SMEM_DOUBLES = (size_t)4 * CG_TILE;          // 2 workers x (A, B)
 constexpr int CG_DIAG_LDR = CG_T + 1;
 // the diagonal factorisation aliases the tile buffers: packed block + (1 + 64) right-hand sides + pivots
-static_assert((size_t)(CG_T * (CG_T + 1) / 2 + (CG_T + 1) * CG_DIAG_LDR + CG_T) <= CG_SMEM_DOUBLES, "diag scratch fits");
+static_assert((size_t)(CG_T * (CG_T + 1) / 2 + (CG_T + 1) * CG_DIAG_LDR + CG_T) <= (size_t)2 * CG_TILE, "diag scratch fits in ONE worker's buffers");
 
 struct CholGroup {
   int N, Np, nb, d;
@@ -141,10 +141,86 @@ __device__ __forceinline__ void cg_tile_mma(const double* As, const double* Bs, 
   }
 }
 
+// ---- helpers of the v2 schedule ---------------------------------------------------------------------------------
+// worker-scope publication: the 128 threads of one worker have finished their global writes
+__device__ __forceinline__ void cg_publish_store_w(unsigned long long* p, unsigned long long v, int bar, int wtid) {
+  named_bar_sync(bar, CG_WT);
+  if (wtid == 0) { __threadfence(); asm volatile("st.release.gpu.global.u64 [%0], %1;\n" :: "l"(p), "l"(v) : "memory"); }
+}
+
+// tile (i, j) from its row-major index in the lower triangle, L = i (i + 1) / 2 + j
+__device__ __forceinline__ void cg_unrank(int L, int& i, int& j) {
+  int r = (int)((sqrtf(8.0f * (float)L + 1.0f) - 1.0f) * 0.5f);
+  while ((r + 1) * (r + 2) / 2 <= L) ++r;
+  while (r * (r + 1) / 2 > L) --r;
+  i = r; j = L - r * (r + 1) / 2;
+}
+
+// C(i, j) -= A(i, kcol) * A(j, kcol)^T for one 64x64 tile, by one worker.  The C fragments are fetched into registers
+// while the cp.async operand copies are in flight, so the read-modify-write adds no exposed latency after the MMAs.
+__device__ __forceinline__ void cg_update_tile(const CholGroup& g, int i, int j, int kcol, double* As, double* Bs, int w,
+                                               int wtid, int wm, int wn, int lane) {
+  const int Np = g.Np;
+  cg_stage_tile(As, g.K + (size_t)i * CG_T * Np + (size_t)kcol * CG_T, Np, wtid);
+  cg_stage_tile(Bs, g.K + (size_t)j * CG_T * Np + (size_t)kcol * CG_T, Np, wtid);
+  double* Ct = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
+  double2 c[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int rr = wm * 32 + a * 8 + (lane >> 2), cc = wn * 32 + b * 8 + 2 * (lane & 3);
+      c[a][b] = *reinterpret_cast<const double2*>(Ct + (size_t)rr * Np + cc);
+    }
+  cg_stage_wait();
+  named_bar_sync(1 + w, CG_WT);
+  CgAcc acc;
+  cg_tile_mma(As, Bs, acc, wm, wn, lane);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int rr = wm * 32 + a * 8 + (lane >> 2), cc = wn * 32 + b * 8 + 2 * (lane & 3);
+      double2 o = c[a][b];
+      o.x -= acc.v[a][b][0]; o.y -= acc.v[a][b][1];
+      *reinterpret_cast<double2*>(Ct + (size_t)rr * Np + cc) = o;
+    }
+  named_bar_sync(1 + w, CG_WT);                            // the worker's buffers are free again
+}
+
+// Explicit inverse of a 64x64 lower-triangular factor held packed in shared memory, by the 128 threads of worker 0
+// (named barrier `bar`): column j of the inverse is the forward substitution of e_j, carried by the thread pair
+// (2 j, 2 j + 1) which splits every dot product.  Xc: [64][CG_DIAG_LDR] scratch, column j of the inverse in row j.
+__device__ __forceinline__ void cg_tri_inverse64(const double* __restrict__ S, const double* __restrict__ dg,
+                                                 double* __restrict__ Xc, int wtid, int bar) {
+  const int j = wtid >> 1, h = wtid & 1;
+  double* x = Xc + j * CG_DIAG_LDR;
+  for (int i = j; i < CG_T; ++i) {
+    const double* Li = S + i * (i + 1) / 2;
+    double s0 = 0.0, s1 = 0.0;
+    int c = j + h;
+    for (; c + 2 < i; c += 4) { s0 = fma(Li[c], x[c], s0); s1 = fma(Li[c + 2], x[c + 2], s1); }
+    for (; c < i; c += 2) s0 = fma(Li[c], x[c], s0);
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    const double v = (((i == j) ? 1.0 : 0.0) - s) / dg[i];
+    if (h == 0) x[i] = v;
+    __syncwarp();                                          // the pair shares x through shared memory
+  }
+  named_bar_sync(bar, CG_WT);
+}
+
 // One evaluation.  hyp (shared or global, [3 + d]): mean, amplitude, noise variance, 1/M_0 .. 1/M_{d-1}.
 // sm: CG_SMEM_DOUBLES doubles of dynamic shared memory (16-byte aligned).  epoch: number of evaluations this cluster
 // has completed on these flags (identical in every CTA).  Returns the log-likelihood (-inf when not positive definite
 // or not finite) to every thread of every CTA of the cluster.  Ends with a CTA barrier.
+//
+// Schedule of iteration k inside a CTA (two workers of 128 threads, w0 and w1):
+//   (1+2) the owner's w0 factors diagonal block k (nrhs = 1: z_k rides along), inverts it (cg_tri_inverse64) and
+//         raises A_k, while w1 -- and w0 as soon as it is done, and both workers of every other CTA -- pull the
+//         DEFERRED trailing tiles of step k-1 (columns >= k+1) from a shared-memory task counter;
+//   (3)   panel k after A_k;  B_k;
+//   (4)   urgent tiles of step k: column k+1 only (so that block k+1 can be factored first thing in iteration k+1).
 template <bool FAST_PIVOT>
 __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, double* sm, unsigned long long epoch) {
   const int tid = threadIdx.x, w = tid >> 7, wtid = tid & 127, warp = (tid >> 5) & 3, lane = tid & 31;
@@ -156,106 +232,114 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
   const unsigned long long baseB = epoch * (unsigned long long)(nb - 1) * C;       // one increment per CTA per panel
   double* part = g.part + (size_t)(epoch & 1ull) * nb * 4;
   const double mean = hyp[0], amp = hyp[1], noise = hyp[2];
-  __shared__ int s_bad;
+  const int ntiles = nb * (nb + 1) / 2;
+  __shared__ int s_bad, s_next, s_task[2];
 
   // ---- build: every CTA forms its own tiles; the owner of (i, 0) also initialises r_i = y_i - mean --------------
   {
     int t = 0;
-    for (int i = 0; i < nb; ++i)
-      for (int j = 0; j <= i; ++j) {
-        if (cg_owner(i, j, C) != me) continue;
-        if ((t++ & 1) != w) continue;
-        // stage the two row blocks of X in the worker's buffers: rows i*64.. in As, rows j*64.. in Bs ([row][d])
-        for (int e = wtid; e < CG_T * d; e += CG_WT) {
-          const int rr = e / d, c = e - rr * d;
-          const int gi = i * CG_T + rr, gj = j * CG_T + rr;
-          As[e] = (gi < g.N) ? g.X[(size_t)gi * d + c] : 0.0;
-          Bs[e] = (gj < g.N) ? g.X[(size_t)gj * d + c] : 0.0;
-        }
-        named_bar_sync(1 + w, CG_WT);
-        double* Kt = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
-        for (int e = wtid; e < CG_T * CG_T; e += CG_WT) {
-          const int rr = e >> 6, cc = e & 63;
-          const int gi = i * CG_T + rr, gj = j * CG_T + cc;
-          double v;
-          if (gi < g.N && gj < g.N) {
-            double s = 0.0;
-            for (int c = 0; c < d; ++c) { const double df = As[rr * d + c] - Bs[cc * d + c]; s += df * df * hyp[3 + c]; }
-            v = amp * exp(-0.5 * s);
-            if (gi == gj) v += noise;
-          } else {
-            v = (gi == gj) ? 1.0 : 0.0;
-          }
-          Kt[(size_t)rr * Np + cc] = v;
-        }
-        if (j == 0 && wtid < CG_T) {
-          const int gi = i * CG_T + wtid;
-          g.r[gi] = (gi < g.N) ? (g.y[gi] - mean) : 0.0;
-        }
-        named_bar_sync(1 + w, CG_WT);
+    for (int L = me; L < ntiles; L += C, ++t) {
+      if ((t & 1) != w) continue;
+      int i, j;
+      cg_unrank(L, i, j);
+      // stage the two row blocks of X in the worker's buffers: rows i*64.. in As, rows j*64.. in Bs ([row][d])
+      for (int e = wtid; e < CG_T * d; e += CG_WT) {
+        const int rr = e / d, c = e - rr * d;
+        const int gi = i * CG_T + rr, gj = j * CG_T + rr;
+        As[e] = (gi < g.N) ? g.X[(size_t)gi * d + c] : 0.0;
+        Bs[e] = (gj < g.N) ? g.X[(size_t)gj * d + c] : 0.0;
       }
+      named_bar_sync(1 + w, CG_WT);
+      double* Kt = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
+      for (int e = wtid; e < CG_T * CG_T; e += CG_WT) {
+        const int rr = e >> 6, cc = e & 63;
+        const int gi = i * CG_T + rr, gj = j * CG_T + cc;
+        double v;
+        if (gi < g.N && gj < g.N) {
+          double s = 0.0;
+          for (int c = 0; c < d; ++c) { const double df = As[rr * d + c] - Bs[cc * d + c]; s += df * df * hyp[3 + c]; }
+          v = amp * exp(-0.5 * s);
+          if (gi == gj) v += noise;
+        } else {
+          v = (gi == gj) ? 1.0 : 0.0;
+        }
+        Kt[(size_t)rr * Np + cc] = v;
+      }
+      if (j == 0 && wtid < CG_T) {
+        const int gi = i * CG_T + wtid;
+        g.r[gi] = (gi < g.N) ? (g.y[gi] - mean) : 0.0;
+      }
+      named_bar_sync(1 + w, CG_WT);
+    }
   }
   __syncthreads();
 
   for (int k = 0; k < nb; ++k) {
-    // ---- (1) diagonal block k: factor, invert, z_k, partial sums -- by its owner, all 256 threads -------------------
-    if (cg_owner(k, k, C) == me) {
-      double* S = sm;                                   // packed lower triangle
-      double* R = S + CG_T * (CG_T + 1) / 2;            // [1 + 64][CG_DIAG_LDR]: row 0 = r_k, row 1 + c = e_c
-      double* dg = R + (CG_T + 1) * CG_DIAG_LDR;        // [64] pivots
+    const bool own_diag = cg_owner(k, k, C) == me;
+    // task counter of the deferred phase: first tile index of row k+1 that belongs to this CTA
+    if (tid == 0) {
+      const int L0 = (k + 1) * (k + 2) / 2;
+      s_next = (L0 <= me) ? 0 : (L0 - me + C - 1) / C;
+    }
+    __syncthreads();
+    // ---- (1) diagonal block k on worker 0 of its owner ----------------------------------------------------------------
+    if (own_diag && w == 0) {
+      double* S = sm;                                   // packed lower triangle (worker 0's buffers)
+      double* R = S + CG_T * (CG_T + 1) / 2;            // [CG_DIAG_LDR] r_k -> z_k
+      double* dg = R + CG_DIAG_LDR;                     // [64] pivots
+      double* Xc = dg + CG_T;                           // [64][CG_DIAG_LDR] columns of the inverse
       double* A = g.K + (size_t)k * CG_T * Np + (size_t)k * CG_T;
       double* rk = g.r + k * CG_T;
-      if (tid == 0) s_bad = 0;
-      for (int e = tid; e < CG_T * CG_T; e += CG_THREADS) {
+      if (wtid == 0) s_bad = 0;
+      for (int e = wtid; e < CG_T * CG_T; e += CG_WT) {
         const int i = e >> 6, j = e & 63;
         if (j <= i) S[i * (i + 1) / 2 + j] = A[(size_t)i * Np + j];          // own tile: written by this CTA only
-        R[(1 + i) * CG_DIAG_LDR + j] = (i == j) ? 1.0 : 0.0;
       }
-      if (tid < CG_T) R[tid] = __ldcg(rk + tid);                              // r_k was updated by other CTAs' panels
-      __syncthreads();
-      chol_packed_blocked<CG_THREADS, FAST_PIVOT>(S, R, dg, CG_T, &s_bad, true, CG_T + 1, CG_DIAG_LDR);
+      if (wtid < CG_T) R[wtid] = __ldcg(rk + wtid);                           // r_k was updated by other CTAs' panels
+      named_bar_sync(3, CG_WT);
+      chol_packed_blocked_sub<CG_WT, FAST_PIVOT, 3>(S, R, dg, CG_T, &s_bad, true, 1, CG_DIAG_LDR);
+      cg_tri_inverse64(S, dg, Xc, wtid, 3);
       double* Dg = g.Dinv + (size_t)k * CG_T * CG_T;
-      for (int e = tid; e < CG_T * CG_T; e += CG_THREADS) {
+      for (int e = wtid; e < CG_T * CG_T; e += CG_WT) {
         const int i = e >> 6, j = e & 63;
         A[(size_t)i * Np + j] = (j <= i) ? S[i * (i + 1) / 2 + j] : 0.0;
-        Dg[e] = (j <= i) ? R[(1 + j) * CG_DIAG_LDR + i] : 0.0;               // D^{-1}[i][j] = (solution for e_j)[i]
+        Dg[e] = (j <= i) ? Xc[j * CG_DIAG_LDR + i] : 0.0;                     // D^{-1}[i][j] = (column j)[i]
       }
-      if (tid < CG_T) rk[tid] = R[tid];
-      if (tid < 32) {                                                          // block partials, fixed order
-        double zz = R[tid] * R[tid] + R[tid + 32] * R[tid + 32];
-        double lg = log(dg[tid]) + log(dg[tid + 32]);
+      if (wtid < CG_T) rk[wtid] = R[wtid];
+      if (wtid < 32) {                                                         // block partials, fixed order
+        double zz = R[wtid] * R[wtid] + R[wtid + 32] * R[wtid + 32];
+        double lg = log(dg[wtid]) + log(dg[wtid + 32]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { zz += __shfl_xor_sync(0xffffffffu, zz, o); lg += __shfl_xor_sync(0xffffffffu, lg, o); }
-        if (tid == 0) { part[k * 4 + 0] = zz; part[k * 4 + 1] = lg; part[k * 4 + 2] = s_bad ? 1.0 : 0.0; }
+        if (wtid == 0) { part[k * 4 + 0] = zz; part[k * 4 + 1] = lg; part[k * 4 + 2] = s_bad ? 1.0 : 0.0; }
       }
-      if (C > 1) cg_publish_store(g.flagA, baseA + k + 1); else __syncthreads();
+      if (C > 1) cg_publish_store_w(g.flagA, baseA + k + 1, 3, wtid); else named_bar_sync(3, CG_WT);
     }
-    // ---- (2) deferred trailing work of step k-1 (columns >= k+1) overlaps the owner's pivot chain ------------------
+    // ---- (2) deferred trailing tiles of step k-1 (columns >= k+1), pulled from the task counter ----------------------
     if (k > 0) {
-      int t = 0;
-      for (int j = k + 1; j < nb; ++j)
-        for (int i = j; i < nb; ++i) {
-          if (cg_owner(i, j, C) != me) continue;
-          if ((t++ & 1) != w) continue;
-          cg_stage_tile(As, g.K + (size_t)i * CG_T * Np + (size_t)(k - 1) * CG_T, Np, wtid);
-          cg_stage_tile(Bs, g.K + (size_t)j * CG_T * Np + (size_t)(k - 1) * CG_T, Np, wtid);
-          cg_stage_wait();
-          named_bar_sync(1 + w, CG_WT);
-          CgAcc acc;
-          cg_tile_mma(As, Bs, acc, wm, wn, lane);
-          double* Ct = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int rr = wm * 32 + a * 8 + (lane >> 2), cc = wn * 32 + b * 8 + 2 * (lane & 3);
-              double2* p = reinterpret_cast<double2*>(Ct + (size_t)rr * Np + cc);
-              double2 o = *p; o.x -= acc.v[a][b][0]; o.y -= acc.v[a][b][1]; *p = o;
-            }
-          named_bar_sync(1 + w, CG_WT);
+      for (;;) {
+        if (wtid == 0) {
+          int L = -1;
+          for (;;) {
+            const int t = atomicAdd(&s_next, 1);
+            const int cand = me + t * C;
+            if (cand >= ntiles) break;
+            int i, j;
+            cg_unrank(cand, i, j);
+            if (j >= k + 1) { L = cand; break; }
+          }
+          s_task[w] = L;
         }
-      __syncthreads();
+        named_bar_sync(1 + w, CG_WT);
+        const int L = s_task[w];
+        named_bar_sync(1 + w, CG_WT);                      // everyone has read the slot before the leader reuses it
+        if (L < 0) break;
+        int i, j;
+        cg_unrank(L, i, j);
+        cg_update_tile(g, i, j, k - 1, As, Bs, w, wtid, wm, wn, lane);
+      }
     }
+    __syncthreads();
     if (k == nb - 1) break;
     // ---- (3) panel k: L_ik = A_ik D_k^{-T}, r_i -= L_ik z_k -----------------------------------------------------------
     if (C > 1) cg_wait_ge(g.flagA, baseA + k + 1);
@@ -301,22 +385,7 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
       for (int i = j; i < nb; ++i) {
         if (cg_owner(i, j, C) != me) continue;
         if ((t++ & 1) != w) continue;
-        cg_stage_tile(As, g.K + (size_t)i * CG_T * Np + (size_t)k * CG_T, Np, wtid);
-        cg_stage_tile(Bs, g.K + (size_t)j * CG_T * Np + (size_t)k * CG_T, Np, wtid);
-        cg_stage_wait();
-        named_bar_sync(1 + w, CG_WT);
-        CgAcc acc;
-        cg_tile_mma(As, Bs, acc, wm, wn, lane);
-        double* Ct = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int rr = wm * 32 + a * 8 + (lane >> 2), cc = wn * 32 + b * 8 + 2 * (lane & 3);
-            double2* p = reinterpret_cast<double2*>(Ct + (size_t)rr * Np + cc);
-            double2 o = *p; o.x -= acc.v[a][b][0]; o.y -= acc.v[a][b][1]; *p = o;
-          }
-        named_bar_sync(1 + w, CG_WT);
+        cg_update_tile(g, i, j, k, As, Bs, w, wtid, wm, wn, lane);
       }
     }
     __syncthreads();

@@ -42,7 +42,13 @@ __device__ long long g_prof[16];
 //    FAST_PIVOT: pivots by rsqrt (<= 1 ulp, ~75 cycles) instead of IEEE sqrt + divide (~190 cycles): used by the
 //    optimiser objectives, where the pivot chain is the critical path; the factorisation behind predict keeps the
 //    correctly rounded pair (its errors are amplified by cond(K) into alpha and L^{-1}).
-template <int NT, bool FAST_PIVOT>
+template <int NT, int BAR>
+__device__ __forceinline__ void chol_sync() {
+  if (BAR == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;\n" :: "r"(BAR), "r"(NT) : "memory");
+}
+
+template <int NT, bool FAST_PIVOT, int BAR = 0>
 __device__ __forceinline__ void chol_packed_blocked_classic(double* __restrict__ K, double* __restrict__ r,
                                                     double* __restrict__ diag, int N, int* badflag, bool store_diag,
                                                     int nrhs, int ldr) {
@@ -69,7 +75,7 @@ __device__ __forceinline__ void chol_packed_blocked_classic(double* __restrict__
         *dst -= ((s0 + s1) + (s2 + s3));
       }
       PROF_ADD(4, t_p1);
-      __syncthreads();
+      chol_sync<NT, BAR>();
     }
     PROF_ADD(0, t_p1);
     PROF_T(t_p2);
@@ -125,7 +131,7 @@ __device__ __forceinline__ void chol_packed_blocked_classic(double* __restrict__
       }
     }
     PROF_ADD(5, t_p2);
-    __syncthreads();
+    chol_sync<NT, BAR>();
     PROF_ADD(1, t_p2);
     if (store_diag && tid == nbelow) {                           // everyone has read the unfactored block: write L back
 #pragma unroll
@@ -135,7 +141,7 @@ __device__ __forceinline__ void chol_packed_blocked_classic(double* __restrict__
           if (c < bw) K[(size_t)(J0 + c) * (J0 + c + 1) / 2 + J0 + c2] = D[c][c2];
     }
   }
-  if (store_diag) __syncthreads();
+  if (store_diag) chol_sync<NT, BAR>();
 }
 
 
@@ -258,6 +264,16 @@ __device__ __forceinline__ void chol_packed_blocked(double* __restrict__ K, doub
                                                     int nrhs = 1, int ldr = 0) {
   if (N + nrhs <= NT - 160) chol_packed_blocked_lookahead<NT, FAST_PIVOT>(K, r, diag, N, badflag, store_diag, nrhs, ldr);
   else chol_packed_blocked_classic<NT, FAST_PIVOT>(K, r, diag, N, badflag, store_diag, nrhs, ldr);
+}
+
+// The classic form run by the first NT threads of a larger CTA (threadIdx.x < NT), meeting at named barrier BAR: the
+// rest of the CTA keeps working (chol_group.cuh factors a 64x64 diagonal block on one half of the CTA while the other
+// half runs trailing updates).
+template <int NT, bool FAST_PIVOT, int BAR>
+__device__ __forceinline__ void chol_packed_blocked_sub(double* __restrict__ K, double* __restrict__ r,
+                                                        double* __restrict__ diag, int N, int* badflag, bool store_diag,
+                                                        int nrhs = 1, int ldr = 0) {
+  chol_packed_blocked_classic<NT, FAST_PIVOT, BAR>(K, r, diag, N, badflag, store_diag, nrhs, ldr);
 }
 
 }  // namespace apgp

@@ -64,6 +64,7 @@ class GP(object):
         self._h = h
         self._logdet = np.nan
         self._loglik = -np.inf
+        self._ll_cache = None              # (parameter vector, log-likelihood) of the last deferred evaluation
         self._training_uploaded = False
 
     def __del__(self):
@@ -144,6 +145,7 @@ class GP(object):
             raise ValueError("dimension mismatch")
         self._training_uploaded = False
         self._dirty = True
+        self._ll_cache = None
         self.computed = False
         self.recompute()
 
@@ -211,6 +213,7 @@ class GP(object):
             self._y = y.copy()
             self._training_uploaded = False
             self._dirty = True
+            self._ll_cache = None
 
     # ------------------------------------------------------------------ predict
     def _predict_raw(self, t, want_var, utility=None, bounds=None, ybest=0.0, zeta=0.01, want_mu=True, out=None):
@@ -277,7 +280,19 @@ class GP(object):
 
     # ------------------------------------------------------------------ likelihood
     def log_likelihood(self, y, quiet=False):
+        """george.GP.log_likelihood.  With ``quiet=True`` and changed hyper-parameters -- the call gpUtils._nll makes
+        once per optimiser evaluation (gpUtils.py:74-78) -- only the log-likelihood kernel runs (covariance build +
+        Cholesky + reductions, one launch); the full factorisation behind predict (explicit inverse, alpha, packed
+        operands) is deferred until something needs it (recompute / predict)."""
         self._sync_y(y)
+        if quiet and self._dirty and self._x is not None:
+            p = self.get_parameter_vector()
+            if self._ll_cache is not None and np.array_equal(self._ll_cache[0], p):
+                return self._ll_cache[1]
+            ll = float(self.log_likelihood_batch(p[None, :], self._y)[0])
+            ll = ll if np.isfinite(ll) else -np.inf
+            self._ll_cache = (p.copy(), ll)
+            return ll
         if not self.recompute(quiet=quiet):
             return -np.inf
         ll = self._loglik

@@ -200,7 +200,7 @@ def run_cfg1(args, bench):
     if H.rank == 0 and ref is not None:
         from approxposterior_b200 import compat
         from oracle.refshim import scipy_x0_compat
-        compat.install()
+        compat.install(box_prior_sampler=True)      # rosenbrockLnprior IS the box over ap.bounds: device sampler
         sys.path.insert(0, ref)
         try:
             import approxposterior.approx as rap, approxposterior.gpUtils as rgu, approxposterior.likelihood as rlh, approxposterior.utility as rut
@@ -211,7 +211,7 @@ def run_cfg1(args, bench):
                    "bytes_note": "approximate: one training-set upload per hyper-parameter evaluation and one scalar back, "
                                  "~400 evaluations per refit through the reference's scalar SciPy loop",
                    "api": "the reference's own approxposterior.ApproxPosterior.run (baseline/_ref, unmodified) with george/"
-                          "emcee resolved to the engine by approxposterior_b200.compat.install()"}
+                          "emcee resolved to the engine by approxposterior_b200.compat.install(box_prior_sampler=True)"}
         finally:
             sys.path.remove(ref); compat.uninstall()
     H.finish()
@@ -439,7 +439,9 @@ def run_cfg4(args, bench):
     orig = gpUtils.optimizeGP
 
     def timed_opt(*a, **k):
-        t0 = time.perf_counter(); r = orig(*a, **k); evals.append((time.perf_counter() - t0, orig.last_stats["evals"], len(ap.y)))
+        t0 = time.perf_counter(); r = orig(*a, **k)
+        st = getattr(gpUtils.optimizeGP, "last_stats", None) or getattr(orig, "last_stats", None) or {"evals": 0}
+        evals.append((time.perf_counter() - t0, st["evals"], len(ap.y)))
         return r
     gpUtils.optimizeGP = timed_opt
     approx.gpUtils.optimizeGP = timed_opt
