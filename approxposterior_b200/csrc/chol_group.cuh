@@ -195,16 +195,19 @@ __device__ __forceinline__ void cg_tri_inverse64(const double* __restrict__ S, c
                                                  double* __restrict__ Xc, int wtid, int bar) {
   const int j = wtid >> 1, h = wtid & 1;
   double* x = Xc + j * CG_DIAG_LDR;
-  for (int i = j; i < CG_T; ++i) {
+  // every lane runs all 64 steps (the pair shuffle and the warp barrier need the whole warp): lanes whose column
+  // starts below row i just idle through the early steps
+  for (int i = 0; i < CG_T; ++i) {
     const double* Li = S + i * (i + 1) / 2;
     double s0 = 0.0, s1 = 0.0;
-    int c = j + h;
-    for (; c + 2 < i; c += 4) { s0 = fma(Li[c], x[c], s0); s1 = fma(Li[c + 2], x[c + 2], s1); }
-    for (; c < i; c += 2) s0 = fma(Li[c], x[c], s0);
+    if (i > j) {
+      int c = j + h;
+      for (; c + 2 < i; c += 4) { s0 = fma(Li[c], x[c], s0); s1 = fma(Li[c + 2], x[c + 2], s1); }
+      for (; c < i; c += 2) s0 = fma(Li[c], x[c], s0);
+    }
     double s = s0 + s1;
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    const double v = (((i == j) ? 1.0 : 0.0) - s) / dg[i];
-    if (h == 0) x[i] = v;
+    if (i >= j && h == 0) x[i] = (((i == j) ? 1.0 : 0.0) - s) / dg[i];
     __syncwarp();                                          // the pair shares x through shared memory
   }
   named_bar_sync(bar, CG_WT);

@@ -112,3 +112,55 @@ def test_two_handles_on_two_devices_in_one_process():
         outs.append((mu, var, u, m2, ch, ll, g, xs, fs, ps, fn, gl))
     for a, b in zip(*outs):
         assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def _comm_worker(rank, ws, idq, outq):
+    """C-ABI multi-GPU entry points (include/apgp.h: apgp_comm_*), no torch.distributed involved."""
+    import ctypes as C
+    from approxposterior_b200 import GP, kernels, _lib
+    lib = _lib.load()
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        _lib.check(lib.apgp_comm_unique_id(buf), "apgp_comm_unique_id")
+        for _ in range(ws - 1):
+            idq.put(buf.raw)
+        idb = buf.raw
+    else:
+        idb = idq.get(timeout=120)
+    if rank == 0:
+        gp, y = _make_gp(0)
+    else:                                    # same model shape, never computed: the factorisation arrives by broadcast
+        gp = GP(kernel=kernels.ExpSquaredKernel([1.0, 1.0, 1.0], ndim=3), fit_mean=True, mean=0.0, white_noise=-12.0,
+                device=rank)
+    _lib.check(lib.apgp_comm_init(gp._h, idb, rank, ws), "apgp_comm_init")
+    _lib.check(lib.apgp_comm_broadcast_factor(gp._h, 0), "apgp_comm_broadcast_factor")
+    q = np.random.default_rng(7).uniform(-5, 5, size=(5000, 3))
+    lo, hi = (len(q) * rank) // ws, (len(q) * (rank + 1)) // ws
+    mu, var, u = gp._predict_raw(q[lo:hi], True, utility="bape", bounds=[(-5.0, 5.0)] * 3, ybest=1.0)
+    send = np.ascontiguousarray(np.stack([mu, var, u], axis=1).ravel())
+    recv = np.empty(send.size * ws)
+    _lib.check(lib.apgp_comm_allgather(gp._h, _lib.ptr(send), _lib.ptr(recv), send.size, 1), "apgp_comm_allgather")
+    _lib.check(lib.apgp_comm_destroy(gp._h), "apgp_comm_destroy")
+    outq.put((rank, recv))
+
+
+@pytest.mark.timeout(300)
+def test_c_abi_comm_broadcast_factor_and_allgather():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    idq, outq = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_comm_worker, args=(r, 2, idq, outq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([outq.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(30)
+    assert np.array_equal(res[0][1], res[1][1], equal_nan=True)              # every rank holds the same gathered result
+    gp, y = _make_gp(0)                                                        # single-GPU oracle: the whole batch at once
+    q = np.random.default_rng(7).uniform(-5, 5, size=(5000, 3))
+    mu, var, u = gp._predict_raw(q, True, utility="bape", bounds=[(-5.0, 5.0)] * 3, ybest=1.0)
+    ref = np.stack([mu, var, u], axis=1).ravel()
+    assert np.array_equal(res[0][1], ref, equal_nan=True)                     # rank 1 never factorised: broadcast state is exact
