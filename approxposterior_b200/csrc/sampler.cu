@@ -81,9 +81,12 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
 }
 
 // rows [r0, np) of sm.q (r0 even)
-__device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np, int r0 = 0) {
+// nslice > 0: "split training set" mode -- sm.xs holds only this CTA's slice ([d+1][slice_pad], nslice points) and the
+// raw partial sums (no mean, no finiteness gate) go to sm.nlp for the cluster-wide reduction that follows.
+__device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np, int r0 = 0, int nslice = 0, int slice_pad = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int d = p.d, Npad = p.Npad;
+  const int d = p.d, Npad = nslice ? slice_pad : p.Npad;
+  const int Neff = nslice ? nslice : p.N;
   for (int i0 = r0 + 2 * warp; i0 < np; i0 += 2 * nwarps) {
     const int i1 = (i0 + 1 < np) ? i0 + 1 : i0;
     const int ok0 = sm.ok[i0], ok1 = sm.ok[i1];
@@ -92,7 +95,7 @@ __device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np, int r0
     if (ok0 | ok1) {
       const double* q0 = sm.sq + i0 * d;
       const double* q1 = sm.sq + i1 * d;
-      if (sm.xs) eval_pair(sm.xs, sm.xs + d * Npad, q0, q1, sm.etab, p.N, Npad, d, lane, acc0, acc1);
+      if (sm.xs) eval_pair(sm.xs, sm.xs + d * Npad, q0, q1, sm.etab, Neff, Npad, d, lane, acc0, acc1);
       else eval_pair(p.Xs, p.alphaA, q0, q1, sm.etab, p.N, Npad, d, lane, acc0, acc1);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -103,9 +106,13 @@ __device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np, int r0
     if (lane < 2) {
       const int i = lane ? i1 : i0;
       const int oki = lane ? ok1 : ok0;
-      const double mu = p.mean + (lane ? acc1 : acc0);
-      const bool fin = oki && (mu == mu) && (fabs(mu) < INFINITY);
-      if (lane == 0 || i1 != i0) { sm.nlp[i] = fin ? mu : -INFINITY; sm.ok[i] = fin ? 1 : 0; }
+      if (nslice) {
+        if (lane == 0 || i1 != i0) sm.nlp[i] = lane ? acc1 : acc0;          // partial sum over this CTA's slice
+      } else {
+        const double mu = p.mean + (lane ? acc1 : acc0);
+        const bool fin = oki && (mu == mu) && (fabs(mu) < INFINITY);
+        if (lane == 0 || i1 != i0) { sm.nlp[i] = fin ? mu : -INFINITY; sm.ok[i] = fin ? 1 : 0; }
+      }
     }
   }
 }
@@ -127,8 +134,12 @@ __device__ __forceinline__ int stage_row(const SamplerParams& p, const Smem& sm,
 // accepts its slice of each half-step's walkers, writes the accepted moves into every replica through distributed
 // shared memory, and the cluster meets at one hardware cluster barrier per half-step.  Same draws, same arithmetic
 // per walker: chains are bit-identical to C = 1.
+// tsplit > 0: the scaled training set does not fit one CTA's shared memory, so it is PARTITIONED over the cluster instead
+// (tsplit = points per CTA, padded): every CTA keeps its slice resident, evaluates ALL proposals of a half-step against
+// it, the partial sums meet in every CTA through distributed shared memory (one cluster barrier per half-step) and are
+// added in rank order -- every replica then takes the same accept decisions locally, with no remote state writes.
 __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ SamplerParams p, int xs_in_smem, int SB,
-                                                       int C) {
+                                                       int C, int tsplit) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int e = blockIdx.x / C, rank = blockIdx.x % C, tid = threadIdx.x;
   cg::cluster_group cluster = cg::this_cluster();
@@ -140,7 +151,11 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
   sm.etab = etab_s;
   double* f = reinterpret_cast<double*>(raw);
   sm.xs = nullptr;
+  double* parts = nullptr;                   // split mode: [2][C][nw] partial sums from every CTA of the cluster
+  const int n_lo = tsplit * rank;
+  const int nslice = tsplit ? max(0, min(tsplit, p.N - n_lo)) : 0;
   if (xs_in_smem) { sm.xs = f; f += (size_t)(d + 1) * Npad; }
+  if (tsplit) { sm.xs = f; f += (size_t)(d + 1) * tsplit; parts = f; f += (size_t)2 * C * nw; }
   sm.coords = f; f += nw * d;
   sm.lp = f; f += nw;
   sm.blob = f; f += nw;
@@ -161,6 +176,32 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
     for (int idx = tid; idx < (d + 1) * Npad; idx += blockDim.x)
       sm.xs[idx] = (idx < d * Npad) ? p.Xs[idx] : p.alphaA[idx - d * Npad];
   }
+  if (tsplit) {
+    for (int idx = tid; idx < (d + 1) * tsplit; idx += blockDim.x) {
+      const int c = idx / tsplit, t = idx - c * tsplit;
+      double v = 0.0;
+      if (t < nslice) v = (c < d) ? p.Xs[(size_t)c * Npad + n_lo + t] : p.alphaA[n_lo + t];
+      sm.xs[idx] = v;
+    }
+  }
+  int hs = 0;                                // exchanges done so far (parity selects the parts buffer)
+  // split mode: publish my partial sums of rows [0, np) to every CTA, meet, add in rank order, gate
+  auto combine = [&](int np) {
+    double* mine = parts + (size_t)(hs & 1) * C * nw;
+    for (int i = tid; i < np; i += blockDim.x) {
+      const double v = sm.nlp[i];
+      for (int r = 0; r < C; ++r) cluster.map_shared_rank(mine, r)[rank * nw + i] = v;
+    }
+    cluster.sync();
+    for (int i = tid; i < np; i += blockDim.x) {
+      double mu = p.mean;
+      for (int r = 0; r < C; ++r) mu += mine[r * nw + i];
+      const bool fin = sm.ok[i] && (mu == mu) && (fabs(mu) < INFINITY);
+      sm.nlp[i] = fin ? mu : -INFINITY; sm.ok[i] = fin ? 1 : 0;
+    }
+    ++hs;
+    __syncthreads();
+  };
   for (int idx = tid; idx < nw * d; idx += blockDim.x) {
     double v = p.p0[(size_t)e * nw * d + idx];
     sm.coords[idx] = v; sm.q[idx] = v;
@@ -168,14 +209,17 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
   __syncthreads();
   for (int w = tid; w < nw; w += blockDim.x) sm.ok[w] = stage_row(p, sm, w);
   __syncthreads();
-  eval_rows(p, sm, nw);
+  if (tsplit) cluster.sync();                // every CTA's parts buffers exist before anyone writes into a peer
+  eval_rows(p, sm, nw, 0, tsplit ? (nslice ? nslice : -1) : 0, tsplit);
   __syncthreads();
+  if (tsplit) combine(nw);
   for (int w = tid; w < nw; w += blockDim.x) { sm.lp[w] = sm.nlp[w]; sm.blob[w] = sm.ok[w] ? p.lnprior_const : NAN; }
   __syncthreads();
   if (C > 1) cluster.sync();                 // every replica initialised before anyone writes into a peer
   // my slice of each half-step's Ns proposals (even boundaries: a warp evaluates rows in pairs) and of the walkers
   // whose chain entries I store
-  const int i_lo = ((Ns * rank) / C) & ~1, i_hi = (rank == C - 1) ? Ns : (((Ns * (rank + 1)) / C) & ~1);
+  const int i_lo = tsplit ? 0 : ((Ns * rank) / C) & ~1;
+  const int i_hi = tsplit ? Ns : ((rank == C - 1) ? Ns : (((Ns * (rank + 1)) / C) & ~1));
   const int w_lo = (nw * rank) / C, w_hi = (nw * (rank + 1)) / C;
 
   Philox rng; rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
@@ -252,14 +296,15 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
           sm.ok[i] = stage_row(p, sm, i);
         }
         __syncthreads();
-        eval_rows(p, sm, i_hi, i_lo);
+        eval_rows(p, sm, i_hi, i_lo, tsplit ? (nslice ? nslice : -1) : 0, tsplit);
         __syncthreads();
+        if (tsplit) combine(Ns);
         for (int i = i_lo + tid; i < i_hi; i += blockDim.x) {
           const int j = sidx[i];
           const double diff = sm.fac[boff + i] + sm.nlp[i] - sm.lp[j];
           if (diff > sm.logu[boff + i]) {
             const double nl = sm.nlp[i], bl = sm.ok[i] ? p.lnprior_const : NAN;
-            if (C > 1) {
+            if (C > 1 && !tsplit) {
               for (int r = 0; r < C; ++r) {                    // the move goes into every replica of the state
                 double* rc = cluster.map_shared_rank(sm.coords, r);
                 for (int c = 0; c < d; ++c) rc[j * d + c] = sm.q[i * d + c];
@@ -271,10 +316,10 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
               sm.lp[j] = nl;
               sm.blob[j] = bl;
             }
-            atomicAdd(&p.naccept[(size_t)e * nw + j], 1);
+            if (!tsplit || rank == 0) atomicAdd(&p.naccept[(size_t)e * nw + j], 1);
           }
         }
-        if (C > 1) cluster.sync(); else __syncthreads();
+        if (C > 1 && !tsplit) cluster.sync(); else __syncthreads();
       }
       if ((step + 1) % p.thin == 0) {
         const long srow = (step + 1) / p.thin - 1;
@@ -284,7 +329,7 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
           p.logp[srow * W + (size_t)e * nw + w] = sm.lp[w];
           p.blob[srow * W + (size_t)e * nw + w] = sm.blob[w];
         }
-        if (C > 1) cluster.sync();           // my reads of the replica finish before a peer's next accepted move lands
+        if (C > 1 && !tsplit) cluster.sync(); // my reads of the replica finish before a peer's next accepted move lands
       }
       // no sync needed: the next writes to coords/lp/blob happen after two more __syncthreads
     }
@@ -308,12 +353,30 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   const size_t xs_bytes = (size_t)(p.d + 1) * p.Npad * 8;
   if (state + per_step > cap) return (int)cudaErrorInvalidValue;
   int xs_in_smem = (state + per_step + xs_bytes <= cap) ? 1 : 0;
-  const size_t room = cap - state - (xs_in_smem ? xs_bytes : 0);
+  // the training set does not fit one CTA: partition it over a cluster of Cs CTAs (each keeps N / Cs points resident and
+  // the partial sums meet through distributed shared memory) -- unless even 8 slices do not fit, or the caller forbids it
+  int split = 0, Cs = 1;
+  if (!xs_in_smem && !getenv("APGP_SAMPLER_NO_SPLIT")) {
+    for (int c = 2; c <= 8; c <<= 1) {
+      const int per = (((p.N + c - 1) / c) + 1) & ~1;
+      const size_t need = state + per_step + (size_t)(p.d + 1) * per * 8 + (size_t)2 * c * p.nwalk * 8;
+      if (need <= cap) { split = per; Cs = c; break; }
+    }
+    if (const char* sv = getenv("APGP_SAMPLER_SPLIT")) {          // A/B runs: force the number of slices
+      const int c = atoi(sv);
+      if (c == 2 || c == 4 || c == 8) {
+        const int per = (((p.N + c - 1) / c) + 1) & ~1;
+        if (state + per_step + (size_t)(p.d + 1) * per * 8 + (size_t)2 * c * p.nwalk * 8 <= cap) { split = per; Cs = c; }
+      }
+    }
+  }
+  const size_t resident = xs_in_smem ? xs_bytes : (split ? (size_t)(p.d + 1) * split * 8 + (size_t)2 * Cs * p.nwalk * 8 : 0);
+  const size_t room = cap - state - resident;
   int SB = (int)(room / per_step);
   if (SB > 32) SB = 32;
   if (SB > p.nsteps) SB = p.nsteps;
   if (SB < 1) SB = 1;
-  const size_t smem = state + (size_t)SB * per_step + (xs_in_smem ? xs_bytes : 0);
+  const size_t smem = state + (size_t)SB * per_step + resident;
   static PerDeviceOnce attr;
   if (attr.needed()) {
     cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -326,15 +389,19 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   // evaluations per CTA per half-step (measured, tools/bench_single_ensemble.py: 100 walkers at N = 500 / 1000 gain
   // 1.3x / 1.45x with C = 4, 40 walkers at N = 90 lose 20 %).  APGP_SAMPLER_CLUSTER overrides (1, 2, 4, 8) for A/B runs.
   int C = 1;
-  if (p.nens <= 32) {
-    for (int c = 8; c >= 2; c >>= 1)
-      if (Ns / c >= 8 && (long long)Ns * p.N / c >= 6000) { C = c; break; }
+  if (split) {
+    C = Cs;                                   // the slices ARE the cluster
+  } else {
+    if (p.nens <= 32) {
+      for (int c = 8; c >= 2; c >>= 1)
+        if (Ns / c >= 8 && (long long)Ns * p.N / c >= 6000) { C = c; break; }
+    }
+    if (const char* cv = getenv("APGP_SAMPLER_CLUSTER")) { int c = atoi(cv); if (c == 1 || c == 2 || c == 4 || c == 8) C = c; }
+    while (C > 1 && Ns / C < 2) C >>= 1;
   }
-  if (const char* cv = getenv("APGP_SAMPLER_CLUSTER")) { int c = atoi(cv); if (c == 1 || c == 2 || c == 4 || c == 8) C = c; }
-  while (C > 1 && Ns / C < 2) C >>= 1;
   // one warp per pair of proposals of a CTA's slice (a warp evaluates two rows per pass), 8..32 warps: a single large
   // ensemble lives on few SMs, so its parallelism is warps (APGP_SAMPLER_WARPS overrides, for A/B runs)
-  const int pairs = ((Ns + C - 1) / C + 1) / 2;
+  const int pairs = split ? (Ns + 1) / 2 : ((Ns + C - 1) / C + 1) / 2;      // split mode: every CTA evaluates all proposals
   int nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : (pairs < 8 ? 8 : (pairs > 32 ? 32 : pairs));
   if (const char* wv = getenv("APGP_SAMPLER_WARPS")) { int w = atoi(wv); if (w >= 1 && w <= 32) nwarps = w; }
   cudaMemsetAsync(p.naccept, 0, sizeof(int) * (size_t)p.nens * p.nwalk, st);
@@ -345,7 +412,7 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = (unsigned)C; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, sampler_kernel, p, xs_in_smem, SB, C);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, sampler_kernel, p, xs_in_smem, SB, C, split);
   if (le != cudaSuccess && C > 1) {
     // the cluster could not be scheduled (e.g. a partitioned GPU): one CTA per ensemble gives the same chains
     (void)cudaGetLastError();
@@ -354,7 +421,8 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
     nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : (pairs1 < 8 ? 8 : (pairs1 > 32 ? 32 : pairs1));
     cfg.gridDim = dim3((unsigned)p.nens); cfg.blockDim = dim3((unsigned)(nwarps * 32));
     attrs[0].val.clusterDim.x = 1;
-    le = cudaLaunchKernelEx(&cfg, sampler_kernel, p, xs_in_smem, SB, C);
+    // (a split launch falls back to streaming the training set from L2; SB was sized for the smaller footprint)
+    le = cudaLaunchKernelEx(&cfg, sampler_kernel, p, xs_in_smem, SB, C, 0);
   }
   if (le != cudaSuccess) return (int)le;
   if (launches) ++*launches;

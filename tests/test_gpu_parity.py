@@ -595,3 +595,45 @@ def test_pipelined_host_predict_equals_device_resident(N, d, Q, kind, monkeypatc
     monkeypatch.delenv("APGP_NO_PIPELINE", raising=False)
     m_only = gp._predict_raw(qh, False)[0]
     assert np.array_equal(m_only, gp._predict_raw(q, False)[0].cpu().numpy(), equal_nan=True)
+
+
+@pytest.mark.parametrize("N,d,nw,nens", [(2000, 10, 60, 1), (1300, 20, 44, 3), (3000, 5, 24, 2)])
+def test_sampler_training_set_partitioned_over_the_cluster(N, d, nw, nens, monkeypatch):
+    """Training sets too large for one CTA's shared memory are partitioned over the cluster (every CTA keeps a slice
+    resident, partial means meet through distributed shared memory and are added in rank order).  Against the
+    stream-from-L2 path (APGP_SAMPLER_NO_SPLIT) the log-probabilities differ by summation order only, so short chains
+    agree to rounding and accept the same moves; every slice count gives a valid, deterministic chain; and the replayed
+    oracle draws are reproduced to 1e-9."""
+    from oracle import stretch_move_oracle
+    from oracle.sampler_oracle import gpll_batch
+    X, y, logM, _ = synthetic_gp_problem(N, d, seed=N + d)
+    gp, orc = make_pair(X, y, logM)
+    lo, hi = np.full(d, -5.0), np.full(d, 5.0)
+    bounds = list(zip(lo, hi))
+    rng = np.random.default_rng(3)
+    p0 = rng.uniform(-1, 1, size=(nens * nw, d))
+    monkeypatch.setenv("APGP_SAMPLER_NO_SPLIT", "1")
+    ref = gp.run_ensembles(y, p0, 12, bounds, nens=nens, seed=4)
+    monkeypatch.delenv("APGP_SAMPLER_NO_SPLIT")
+    outs = []
+    for slices in (None, "2", "4", "8"):
+        if slices is None:
+            monkeypatch.delenv("APGP_SAMPLER_SPLIT", raising=False)
+        else:
+            monkeypatch.setenv("APGP_SAMPLER_SPLIT", slices)
+        a = gp.run_ensembles(y, p0, 12, bounds, nens=nens, seed=4)
+        b = gp.run_ensembles(y, p0, 12, bounds, nens=nens, seed=4)
+        assert np.array_equal(a["chain"], b["chain"]) and np.array_equal(a["naccepted"], b["naccepted"])
+        np.testing.assert_allclose(a["log_prob"], ref["log_prob"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(a["chain"], ref["chain"], rtol=1e-10, atol=1e-12)
+        assert np.array_equal(a["naccepted"], ref["naccepted"])
+        outs.append(a)
+    monkeypatch.delenv("APGP_SAMPLER_SPLIT", raising=False)
+    rs = np.random.RandomState(4)
+    q0 = rs.uniform(-1, 1, size=(nw, d))
+    yo = y.copy(); yo.setflags(write=False)
+    orc_run = stretch_move_oracle(lambda q: gpll_batch(orc, yo, q, lo, hi), q0, 10, rng=rs, record=True)
+    out = gp.run_ensembles(y, q0, 10, bounds, nens=1, replay={k: orc_run[k][None] for k in ("inds", "zz", "rint", "logu")})
+    np.testing.assert_allclose(out["chain"], orc_run["chain"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out["log_prob"], orc_run["log_prob"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(out["naccepted"], orc_run["naccepted"])
