@@ -357,10 +357,16 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   // the partial sums meet through distributed shared memory) -- unless even 8 slices do not fit, or the caller forbids it
   int split = 0, Cs = 1;
   if (!xs_in_smem && !getenv("APGP_SAMPLER_NO_SPLIT")) {
+    // the smallest slice count that fits, then -- while the grid stays within half the GPU (a cluster barrier per
+    // half-step costs more when the SMs are oversubscribed) -- as many slices as possible: measured at N = 2000, d = 10,
+    // 200 walkers (tools/bench_sampler_split.py): 1 ensemble 100 us per step streamed from L2, 88 / 51 / 33 us with
+    // 2 / 4 / 8 slices; 16 ensembles 202 us streamed, 90 / 52 / 66 us
     for (int c = 2; c <= 8; c <<= 1) {
       const int per = (((p.N + c - 1) / c) + 1) & ~1;
       const size_t need = state + per_step + (size_t)(p.d + 1) * per * 8 + (size_t)2 * c * p.nwalk * 8;
-      if (need <= cap) { split = per; Cs = c; break; }
+      if (need > cap) continue;
+      if (split && (long long)p.nens * c > 74) break;
+      split = per; Cs = c;
     }
     if (const char* sv = getenv("APGP_SAMPLER_SPLIT")) {          // A/B runs: force the number of slices
       const int c = atoi(sv);
