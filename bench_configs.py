@@ -234,7 +234,7 @@ def run_cfg1(args, bench):
                                              "fraction of the FP64 peak is not the figure of merit here, the 18 us per "
                                              "evaluation is (profiles/r01_optimizers.md)",
                                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"},
-                           cpu_baseline=cfg1_reference(bounded=True)))
+                           cpu_baseline=None if args.no_cpu else cfg1_reference(bounded=True)))
 
 
 def cfg1_reference(bounded=True):
@@ -359,7 +359,7 @@ def run_cfg2(args, bench):
                                              "share of the walkers over this rank's kernel time",
                                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (the FP64 pipe; DFMA issue peak is "
                                                     "half the DMMA flop rate)"},
-                           cpu_baseline=cfg2_reference(bounded_s=10.0)))
+                           cpu_baseline=None if args.no_cpu else cfg2_reference(bounded_s=10.0)))
 
 
 def cfg2_reference(bounded_s=10.0):
@@ -492,7 +492,7 @@ def run_cfg4(args, bench):
                                      "flops_per_eval": F_ll(Nmid, 10), "N": Nmid,
                                      "note": "latency-bound serial Cholesky chains on 64 of 148 SMs",
                                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"},
-                           cpu_baseline=cfg4_reference(restarts=2)))
+                           cpu_baseline=None if args.no_cpu else cfg4_reference(restarts=2)))
 
 
 def cfg4_reference(restarts=2):
@@ -610,7 +610,7 @@ def run_cfg5(args, bench):
                                      "note": "FP64-pipe bound at every N of the sweep (SURVEY 8d): compulsory HBM traffic is 8d+16 bytes "
                                              "per evaluation; algorithmic_hbm_gbs is that figure over the kernel time",
                                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"},
-                           cpu_baseline=cfg5_reference(N, d, target_s=10.0)))
+                           cpu_baseline=None if args.no_cpu else cfg5_reference(N, d, target_s=10.0)))
 
 
 def cfg5_reference(N, d, target_s=10.0):
