@@ -141,6 +141,34 @@ __device__ __forceinline__ void cg_tile_mma(const double* As, const double* Bs, 
   }
 }
 
+// Panel solve by substitution: one thread owns one row of a 64x64 panel tile and overwrites it with
+//   x = a L^{-T}   (L: the factored diagonal block, row-major in shared memory with leading dimension CG_LD;
+//                   inv: reciprocal pivots 1 / L_cc)
+// in 8-wide column blocks, exactly the structure of chol_small.cuh: the contribution of the finished columns goes into 8
+// independent accumulators (no dependent chain), the 8x8 triangular remainder is solved in registers.  The row lives in
+// registers for the whole solve (64 doubles); L is read as warp-wide broadcasts.  ~2000 FMAs per row.
+__device__ __forceinline__ void cg_trsm_row(double (&x)[CG_T], const double* __restrict__ Ls, const double* __restrict__ inv) {
+#pragma unroll
+  for (int J = 0; J < CG_T / 8; ++J) {
+    double u[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) u[cc] = x[8 * J + cc];
+#pragma unroll
+    for (int c2 = 0; c2 < 8 * J; ++c2) {
+      const double xv = x[c2];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) u[cc] = fma(-xv, Ls[(8 * J + cc) * CG_LD + c2], u[cc]);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      double v = u[cc];
+#pragma unroll
+      for (int c3 = 0; c3 < cc; ++c3) v = fma(-x[8 * J + c3], Ls[(8 * J + cc) * CG_LD + 8 * J + c3], v);
+      x[8 * J + cc] = v * inv[8 * J + cc];
+    }
+  }
+}
+
 // One evaluation.  hyp (shared or global, [3 + d]): mean, amplitude, noise variance, 1/M_0 .. 1/M_{d-1}.
 // sm: CG_SMEM_DOUBLES doubles of dynamic shared memory (16-byte aligned).  epoch: number of evaluations this cluster
 // has completed on these flags (identical in every CTA).  Returns the log-likelihood (-inf when not positive definite
@@ -201,26 +229,26 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
     // ---- (1) diagonal block k: factor, invert, z_k, partial sums -- by its owner, all 256 threads -------------------
     if (cg_owner(k, k, C) == me) {
       double* S = sm;                                   // packed lower triangle
-      double* R = S + CG_T * (CG_T + 1) / 2;            // [1 + 64][CG_DIAG_LDR]: row 0 = r_k, row 1 + c = e_c
-      double* dg = R + (CG_T + 1) * CG_DIAG_LDR;        // [64] pivots
+      double* R = S + CG_T * (CG_T + 1) / 2;            // [CG_DIAG_LDR]: r_k -> z_k
+      double* dg = R + CG_DIAG_LDR;                     // [64] pivots
       double* A = g.K + (size_t)k * CG_T * Np + (size_t)k * CG_T;
       double* rk = g.r + k * CG_T;
       if (tid == 0) s_bad = 0;
       for (int e = tid; e < CG_T * CG_T; e += CG_THREADS) {
         const int i = e >> 6, j = e & 63;
         if (j <= i) S[i * (i + 1) / 2 + j] = A[(size_t)i * Np + j];          // own tile: written by this CTA only
-        R[(1 + i) * CG_DIAG_LDR + j] = (i == j) ? 1.0 : 0.0;
       }
       if (tid < CG_T) R[tid] = __ldcg(rk + tid);                              // r_k was updated by other CTAs' panels
       __syncthreads();
-      chol_packed_blocked<CG_THREADS, FAST_PIVOT>(S, R, dg, CG_T, &s_bad, true, CG_T + 1, CG_DIAG_LDR);
+      chol_packed_blocked<CG_THREADS, FAST_PIVOT>(S, R, dg, CG_T, &s_bad, true, 1, CG_DIAG_LDR);
+      // the factored block goes back row-major (the panel solves read it), its reciprocal pivots into the block's
+      // slot of Dinv -- no explicit inverse: the panels are solved by substitution (cg_trsm_row)
       double* Dg = g.Dinv + (size_t)k * CG_T * CG_T;
       for (int e = tid; e < CG_T * CG_T; e += CG_THREADS) {
         const int i = e >> 6, j = e & 63;
         A[(size_t)i * Np + j] = (j <= i) ? S[i * (i + 1) / 2 + j] : 0.0;
-        Dg[e] = (j <= i) ? R[(1 + j) * CG_DIAG_LDR + i] : 0.0;               // D^{-1}[i][j] = (solution for e_j)[i]
       }
-      if (tid < CG_T) rk[tid] = R[tid];
+      if (tid < CG_T) { Dg[tid] = 1.0 / dg[tid]; rk[tid] = R[tid]; }
       if (tid < 32) {                                                          // block partials, fixed order
         double zz = R[tid] * R[tid] + R[tid + 32] * R[tid + 32];
         double lg = log(dg[tid]) + log(dg[tid + 32]);
@@ -257,40 +285,43 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
       __syncthreads();
     }
     if (k == nb - 1) break;
-    // ---- (3) panel k: L_ik = A_ik D_k^{-T}, r_i -= L_ik z_k -----------------------------------------------------------
+    // ---- (3) panel k: L_ik = A_ik L_kk^{-T} by substitution (one thread per row), r_i -= L_ik z_k --------------------
     if (C > 1) cg_wait_ge(g.flagA, baseA + k + 1);
     {
-      int t = 0;
-      for (int i = k + 1; i < nb; ++i) {
-        if (cg_owner(i, k, C) != me) continue;
-        if ((t++ & 1) != w) continue;
-        double* Aik = g.K + (size_t)i * CG_T * Np + (size_t)k * CG_T;
-        cg_stage_tile(As, Aik, Np, wtid);
-        cg_stage_tile(Bs, g.Dinv + (size_t)k * CG_T * CG_T, CG_T, wtid);
+      // every worker keeps its own copy of L_kk (row-major, ld CG_LD) in its first buffer; reciprocal pivots and z_k
+      // in its second
+      int mine = 0;
+      for (int i = k + 1; i < nb; ++i) mine += (cg_owner(i, k, C) == me);
+      if (mine > 0) {
+        cg_stage_tile(As, g.K + (size_t)k * CG_T * Np + (size_t)k * CG_T, Np, wtid);
+        if (wtid < CG_T) { Bs[wtid] = __ldcg(g.Dinv + (size_t)k * CG_T * CG_T + wtid); Bs[CG_T + wtid] = __ldcg(g.r + k * CG_T + wtid); }
         cg_stage_wait();
         named_bar_sync(1 + w, CG_WT);
-        CgAcc acc;
-        cg_tile_mma(As, Bs, acc, wm, wn, lane);
-        named_bar_sync(1 + w, CG_WT);                                          // everyone has read As/Bs
+        // the worker's two halves (64 threads each) take alternate tiles of the CTA's share
+        const int half = wtid >> 6, row = wtid & 63;
+        int t = 0;
+        for (int i = k + 1; i < nb; ++i) {
+          if (cg_owner(i, k, C) != me) continue;
+          if ((t++ & 3) != 2 * w + half) continue;
+          double* Arow = g.K + (size_t)(i * CG_T + row) * Np + (size_t)k * CG_T;
+          double x[CG_T];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int rr = wm * 32 + a * 8 + (lane >> 2), cc = wn * 32 + b * 8 + 2 * (lane & 3);
-            double2 o; o.x = acc.v[a][b][0]; o.y = acc.v[a][b][1];
-            *reinterpret_cast<double2*>(Aik + (size_t)rr * Np + cc) = o;
-            As[rr * CG_LD + cc] = o.x; As[rr * CG_LD + cc + 1] = o.y;          // keep L_ik for the rhs update
+          for (int m = 0; m < CG_T / 2; ++m) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(Arow) + m);
+            x[2 * m] = v.x; x[2 * m + 1] = v.y;
           }
-        if (wtid < CG_T) Bs[wtid] = __ldcg(g.r + k * CG_T + wtid);             // z_k
-        named_bar_sync(1 + w, CG_WT);
-        if (wtid < CG_T) {
-          double s = 0.0;
-#pragma unroll 8
-          for (int c = 0; c < CG_T; ++c) s = fma(As[wtid * CG_LD + c], Bs[c], s);
-          double* ri = g.r + i * CG_T + wtid;
-          *ri = __ldcg(ri) - s;
+          cg_trsm_row(x, As, Bs);
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int m = 0; m < CG_T / 2; ++m) {
+            double2 v; v.x = x[2 * m]; v.y = x[2 * m + 1];
+            reinterpret_cast<double2*>(Arow)[m] = v;
+            s0 = fma(v.x, Bs[CG_T + 2 * m], s0); s1 = fma(v.y, Bs[CG_T + 2 * m + 1], s1);
+          }
+          double* ri = g.r + i * CG_T + row;
+          *ri = __ldcg(ri) - (s0 + s1);
         }
-        named_bar_sync(1 + w, CG_WT);
+        named_bar_sync(1 + w, CG_WT);                      // the worker's buffers are free again
       }
     }
     if (C > 1) { cg_publish_add(g.cntB); cg_wait_ge(g.cntB, baseB + (unsigned long long)(k + 1) * C); } else __syncthreads();
