@@ -692,7 +692,10 @@ int launch_loglik_small(const double* X, const double* y, int N, int d, const do
 int chol_group_cluster(int Np, int R, int num_sms) {
   const int nb = Np / T;
   int C = 1;
-  while (C * 2 <= 16 && (long)R * C * 2 <= num_sms && C * 2 <= (nb > 1 ? nb - 1 : 1) * 2) C *= 2;
+  // 16-CTA clusters (non-portable size) only pay for a handful of vectors: measured at R = 8, N = 1024 a batch takes
+  // 0.91 ms with C = 8 and 1.31 ms with C = 16 (few GPCs can host a 16-CTA cluster at a time); R = 1: 0.90 vs 0.67 ms
+  const int maxC = (R <= 4) ? 16 : 8;
+  while (C * 2 <= maxC && (long)R * C * 2 <= num_sms && C * 2 <= (nb > 1 ? nb - 1 : 1) * 2) C *= 2;
   if (const char* v = getenv("APGP_CHOL_CLUSTER")) { const int c = atoi(v); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) C = c; }
   return C;
 }

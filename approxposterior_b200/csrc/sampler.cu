@@ -50,6 +50,32 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
                                           const double* __restrict__ etab, int N, int Npad, int d, int lane,
                                           double& acc0, double& acc1) {
   int j = lane;
+  // four training points per trip: eight independent exponential chains per thread (the loop is bound by the dependent
+  // latency of the chain, ~10 FP64 operations deep, not by issue slots or the FP64 pipe: ncu 50 % / 71 % with two
+  // points per trip).  The per-lane summation order is unchanged (j, j+32, j+64, j+96, ...), so results are
+  // bit-identical to the two-point loop.
+  for (; j + 96 < N; j += 128) {
+    double s00 = 0.0, s01 = 0.0, s02 = 0.0, s03 = 0.0, s10 = 0.0, s11 = 0.0, s12 = 0.0, s13 = 0.0;
+    int off = j;
+    for (int c = 0; c < d; ++c, off += Npad) {
+      const double xa = xs[off], xb = xs[off + 32], xc = xs[off + 64], xd = xs[off + 96];
+      const double qa = q0[c], qb = q1[c];
+      double t;
+      t = xa - qa; s00 = fma(t, t, s00);
+      t = xb - qa; s01 = fma(t, t, s01);
+      t = xc - qa; s02 = fma(t, t, s02);
+      t = xd - qa; s03 = fma(t, t, s03);
+      t = xa - qb; s10 = fma(t, t, s10);
+      t = xb - qb; s11 = fma(t, t, s11);
+      t = xc - qb; s12 = fma(t, t, s12);
+      t = xd - qb; s13 = fma(t, t, s13);
+    }
+    const double a0 = al[j], a1 = al[j + 32], a2 = al[j + 64], a3 = al[j + 96];
+    const double e00 = exp_neg(s00, etab), e01 = exp_neg(s01, etab), e02 = exp_neg(s02, etab), e03 = exp_neg(s03, etab);
+    const double e10 = exp_neg(s10, etab), e11 = exp_neg(s11, etab), e12 = exp_neg(s12, etab), e13 = exp_neg(s13, etab);
+    acc0 = fma(e00, a0, acc0); acc0 = fma(e01, a1, acc0); acc0 = fma(e02, a2, acc0); acc0 = fma(e03, a3, acc0);
+    acc1 = fma(e10, a0, acc1); acc1 = fma(e11, a1, acc1); acc1 = fma(e12, a2, acc1); acc1 = fma(e13, a3, acc1);
+  }
   for (; j + 32 < N; j += 64) {
     double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;      // s[row][point]
     int off = j;
