@@ -78,6 +78,7 @@ _SIGNATURES = {
     "apgp_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "apgp_set_group": (C.c_int, [C.c_void_p, C.c_int]),
     "apgp_debug_exp_neg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "apgp_debug_exp_neg256": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "apgp_debug_read_prof": (C.c_int, [C.c_void_p]),
     "apgp_debug_group_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -939,16 +939,21 @@ static int get_square(apgp_handle* h, const DevBuf& b, double* out) {
     for (int j = i + 1; j < h->N; ++j) out[(size_t)i * h->N + j] = 0.0;
   return APGP_OK;
 }
-int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out) {
+static int debug_exp(apgp_handle* h, const double* s, int n, double* out, int variant);
+int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out) { return debug_exp(h, s, n, out, 0); }
+int apgp_debug_exp_neg256(apgp_handle* h, const double* s, int n, double* out) { return debug_exp(h, s, n, out, 1); }
+}  // extern "C"
+static int debug_exp(apgp_handle* h, const double* s, int n, double* out, int variant) {
   if (!h || !s || !out || n < 1) return fail(APGP_ERR_ARG, "apgp_debug_exp_neg");
   Guard g(h->device);
   CUI(h->stage_in.reserve((size_t)n * 8)); CUI(h->stage_out.reserve((size_t)n * 8));
   CU(cudaMemcpyAsync(h->stage_in.p, s, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-  CUI(launch_exp_neg_test(h->stage_in.as<double>(), n, h->stage_out.as<double>(), h->stream));
+  CUI(launch_exp_neg_test(h->stage_in.as<double>(), n, h->stage_out.as<double>(), h->stream, variant));
   CU(cudaMemcpyAsync(out, h->stage_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return APGP_OK;
 }
+extern "C" {
 int apgp_debug_group_plan(int N, int num_sms, int d, long long Q, int requested, int* G_out, int* tab512) {
   // host-only: the work split the grouped variance kernel would use (no device needed; exercised by the CPU tests)
   if (!G_out || N < 1 || num_sms < 1 || d < 1) return fail(APGP_ERR_ARG, "apgp_debug_group_plan");

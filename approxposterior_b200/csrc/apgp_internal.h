@@ -50,7 +50,7 @@ int predict_variant_bn(int variant);   // block-row height BN of the LinvF tilin
 
 // returns cudaError_t as int; *launches incremented by the number of kernel launches issued
 int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches);
-int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st);
+int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st, int variant = 0);
 int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, int* launches);
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant);
 // grouped 256x64 kernel: G CTAs share one query tile so the K* panels in flight stay in L2 (predict.cu).

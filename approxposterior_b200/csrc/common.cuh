@@ -125,6 +125,28 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ t
   return (s >= 700.0) ? 0.0 : res;                            // exp(-700) ~ 1e-304: flush (keeps 2^k normal); NaN propagates
 }
 
+// exp(-s) for s >= 0 with a 256-entry table 2^(j/256) and a degree-4 polynomial: 9 FP64 operations (the 64-entry form
+// above needs 10 plus an FP64 compare for the range check, done here on the integer pipe), <= 2 ulp.  Used where the
+// exponential IS the work and the kernel is bound by instruction issue next to the FP64 pipe (sampler, mean-only
+// predict); |r| <= ln2/512, so the first dropped term r^5/120 is below 4e-17.
+__device__ __forceinline__ double exp_neg256(double s, const double* __restrict__ tab) {
+  const double x = -s;
+  const double t = fma(x, 369.32993046757464 /*256/ln2*/, 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -0.0027076061740622863 /*ln2/256 hi*/, x);
+  r = fma(nf, -9.0587766165871075e-20 /*ln2/256 lo*/, r);
+  double q = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
+  q = fma(r, q, 0.5);
+  const double pm1 = fma(r * r, q, r);                      // e^r - 1
+  const double T = tab[n & 255];
+  double res = fma(T, pm1, T);
+  res = __hiloint2double(__double2hiint(res) + ((n >> 8) << 20), __double2loint(res));
+  // s in [700, +inf] -> 0 (keeps 2^k normal); NaN has a larger high word and falls through to propagate
+  const unsigned hs = (unsigned)__double2hiint(s);
+  return (hs - 0x4085E000u <= 0x7FF00000u - 0x4085E000u) ? 0.0 : res;
+}
+
 // Philox4x32-10 counter-based RNG (Salmon et al. 2011), for the device sampler.
 struct Philox {
   uint32_t k0, k1;

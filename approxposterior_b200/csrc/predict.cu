@@ -578,8 +578,8 @@ predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
   const int d = (D > 0) ? D : p.d, Npad = p.Npad;
   double* xs = sm;                                // [d+1][JCH]
   double* qs = sm + (size_t)(d + 1) * JCH;        // [d][MEAN_QPT*MEAN_THREADS]
-  __shared__ double etab[64];
-  if (threadIdx.x < 64) etab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));
+  __shared__ double etab[256];
+  for (int j = threadIdx.x; j < 256; j += blockDim.x) etab[j] = exp2((double)j * (1.0 / 256.0));
   constexpr int QB = MEAN_THREADS * MEAN_QPT;
   const int tid = threadIdx.x;
   const long long ntiles = (p.Q + QB - 1) / QB;
@@ -641,10 +641,10 @@ predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
         const double2 ab = *reinterpret_cast<const double2*>(al + j + 2);
 #pragma unroll
         for (int u = 0; u < MEAN_QPT; ++u) {
-          acc[u] = fma(exp_neg(s[u][0], etab), aa.x, acc[u]);
-          acc[u] = fma(exp_neg(s[u][1], etab), aa.y, acc[u]);
-          acc[u] = fma(exp_neg(s[u][2], etab), ab.x, acc[u]);
-          acc[u] = fma(exp_neg(s[u][3], etab), ab.y, acc[u]);
+          acc[u] = fma(exp_neg256(s[u][0], etab), aa.x, acc[u]);
+          acc[u] = fma(exp_neg256(s[u][1], etab), aa.y, acc[u]);
+          acc[u] = fma(exp_neg256(s[u][2], etab), ab.x, acc[u]);
+          acc[u] = fma(exp_neg256(s[u][3], etab), ab.y, acc[u]);
         }
       }
     }
@@ -691,11 +691,13 @@ __global__ void pack_xs_kernel(const double* __restrict__ X, int N, int d, int N
   }
 }
 
-__global__ void exp_neg_test_kernel(const double* __restrict__ s, int n, double* __restrict__ out) {
-  __shared__ double tab[64];
-  if (threadIdx.x < 64) tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / 64.0));
+__global__ void exp_neg_test_kernel(const double* __restrict__ s, int n, double* __restrict__ out, int variant) {
+  __shared__ double tab[256];
+  const int m = variant ? 256 : 64;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) tab[j] = exp2((double)j / (double)m);
   __syncthreads();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = exp_neg(s[i], tab);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = variant ? exp_neg256(s[i], tab) : exp_neg(s[i], tab);
 }
 
 template <int BM, int BN, int NSTAGE, int NCW = 8>
@@ -895,8 +897,8 @@ int launch_pack_linv(const double* Linv, int ld, int N, int Npad, int BN, double
   return (int)cudaGetLastError();
 }
 
-int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st) {
-  exp_neg_test_kernel<<<64, 256, 0, st>>>(s, n, out);
+int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st, int variant) {
+  exp_neg_test_kernel<<<64, 256, 0, st>>>(s, n, out, variant);
   return (int)cudaGetLastError();
 }
 

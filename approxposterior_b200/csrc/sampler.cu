@@ -27,7 +27,7 @@ struct Smem {
   double* q;       // [nw][d]   proposals (initial pass evaluates all nw walkers)
   double* sq;      // [nw][d]   the same rows scaled for the kernel distance
   double* nlp;     // [nw]
-  const double* etab;  // [64] 2^(j/64) for exp_neg
+  const double* etab;  // [256] 2^(j/256) for exp_neg256
   int* ok;         // [nw]
   // everything random about a step is independent of the chain's state, so it is drawn for SB steps at a time by
   // all threads in parallel (the per-step critical path is then: propose, evaluate, accept)
@@ -71,8 +71,8 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
       t = xd - qb; s13 = fma(t, t, s13);
     }
     const double a0 = al[j], a1 = al[j + 32], a2 = al[j + 64], a3 = al[j + 96];
-    const double e00 = exp_neg(s00, etab), e01 = exp_neg(s01, etab), e02 = exp_neg(s02, etab), e03 = exp_neg(s03, etab);
-    const double e10 = exp_neg(s10, etab), e11 = exp_neg(s11, etab), e12 = exp_neg(s12, etab), e13 = exp_neg(s13, etab);
+    const double e00 = exp_neg256(s00, etab), e01 = exp_neg256(s01, etab), e02 = exp_neg256(s02, etab), e03 = exp_neg256(s03, etab);
+    const double e10 = exp_neg256(s10, etab), e11 = exp_neg256(s11, etab), e12 = exp_neg256(s12, etab), e13 = exp_neg256(s13, etab);
     acc0 = fma(e00, a0, acc0); acc0 = fma(e01, a1, acc0); acc0 = fma(e02, a2, acc0); acc0 = fma(e03, a3, acc0);
     acc1 = fma(e10, a0, acc1); acc1 = fma(e11, a1, acc1); acc1 = fma(e12, a2, acc1); acc1 = fma(e13, a3, acc1);
   }
@@ -89,8 +89,8 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
       t = xb - qb; s11 = fma(t, t, s11);
     }
     const double a0 = al[j], a1 = al[j + 32];
-    acc0 = fma(exp_neg(s00, etab), a0, acc0); acc0 = fma(exp_neg(s01, etab), a1, acc0);
-    acc1 = fma(exp_neg(s10, etab), a0, acc1); acc1 = fma(exp_neg(s11, etab), a1, acc1);
+    acc0 = fma(exp_neg256(s00, etab), a0, acc0); acc0 = fma(exp_neg256(s01, etab), a1, acc0);
+    acc1 = fma(exp_neg256(s10, etab), a0, acc1); acc1 = fma(exp_neg256(s11, etab), a1, acc1);
   }
   for (; j < N; j += 32) {
     double s0 = 0.0, s1 = 0.0;
@@ -101,8 +101,8 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
       s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
     }
     const double a = al[j];
-    acc0 = fma(exp_neg(s0, etab), a, acc0);
-    acc1 = fma(exp_neg(s1, etab), a, acc1);
+    acc0 = fma(exp_neg256(s0, etab), a, acc0);
+    acc1 = fma(exp_neg256(s1, etab), a, acc1);
   }
 }
 
@@ -172,8 +172,9 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
   const int nw = p.nwalk, d = p.d, Ns = nw / 2, Npad = p.Npad;
   const long W = (long)p.nens * nw;
   Smem sm;
-  __shared__ double etab_s[64];
-  if (tid < 64) etab_s[tid] = exp2((double)tid * (1.0 / 64.0));
+  __shared__ double etab_s[256];
+  if (tid < 256) etab_s[tid] = exp2((double)tid * (1.0 / 256.0));
+  if (blockDim.x < 256) for (int j = blockDim.x + tid; j < 256; j += blockDim.x) etab_s[j] = exp2((double)j * (1.0 / 256.0));
   sm.etab = etab_s;
   double* f = reinterpret_cast<double*>(raw);
   sm.xs = nullptr;

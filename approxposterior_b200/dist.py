@@ -62,14 +62,15 @@ def gather_best(score, theta):
     return allp[i, 1:], float(allp[i, 0]), i
 
 
-def scan_utility_sharded(gp, y, kind, bounds, nCandidates, seed=0, zeta=0.01):
+def scan_utility_sharded(gp, y, kind, bounds, nCandidates, seed=0, zeta=0.01, candidates=None):
     """Utility scan of ``nCandidates`` uniform candidates split over the ranks (BASELINE config 3):
-    rank r draws and scores its own block on its GPU, then one all-gather picks the winner."""
+    rank r draws and scores its own block on its GPU, then one all-gather picks the winner.
+    ``candidates``: this rank's block as a torch CUDA tensor, when the caller already holds it on the device."""
     from .utility import scanUtility
     rank, ws = world()
     lo, hi = shard_bounds(nCandidates, rank, ws)
     best, ubest, _, _ = scanUtility(gp, y, kind, bounds, nCandidates=hi - lo, seed=int(seed) * 1000003 + rank,
-                                    zeta=zeta, device_out=True)
+                                    zeta=zeta, device_out=True, candidates=candidates)
     return gather_best(ubest, best)[:2]
 
 

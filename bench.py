@@ -286,8 +286,7 @@ def run_gpu(args):
     gen = torch.Generator(device=dev); gen.manual_seed(1 + rank)
     nbuf = 4
     cands = [(-5.0 + 10.0 * torch.rand((Q, DIM), dtype=torch.float64, device=dev, generator=gen)) for _ in range(nbuf)]
-    best_pack = torch.zeros(1 + DIM, dtype=torch.float64, device=dev)
-    gathered = [torch.zeros_like(best_pack) for _ in range(world)] if world > 1 else None
+    from approxposterior_b200 import dist as apd
 
     kev = []
 
@@ -296,19 +295,25 @@ def run_gpu(args):
         tensors die with the call, so the caching allocator hands the same blocks to the next step (keeping them
         alive across iterations forced a cudaMalloc -- an implicit device sync of 3-100 ms -- inside timed step 1)."""
         c = cands[i % nbuf]
-        if timed:
-            k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
-            k0.record()
-        mu, var, u = gp._predict_raw(c, True, utility="bape", bounds=BOUNDS, ybest=ybest)
-        if timed:
-            k1.record()
-            kev.append((k0, k1))
-        u2 = torch.nan_to_num(u, nan=float("inf"))
-        ib = torch.argmin(u2)
-        best_pack[0] = u2[ib]; best_pack[1:] = c[ib]
-        if world > 1:
-            dist.all_gather(gathered, best_pack)     # the single exchange: candidate scores
-        return None
+        # the package's own sharded scan (dist.py): fused predict + utility on this rank's block, arg-min, then the
+        # single exchange -- one all-gather of every rank's best (score, candidate)
+        hook["on"] = timed
+        theta_best, u_best = apd.scan_utility_sharded(gp, y, "bape", BOUNDS, nCandidates=Q * world, candidates=c)
+        hook["on"] = False
+        return theta_best, u_best
+
+    # CUDA events around the predict launch itself (on the stream the kernel is launched on = torch's current stream)
+    hook = {"on": False}
+    raw = gp._predict_raw
+
+    def timed_raw(*a, **k):
+        if not hook["on"]:
+            return raw(*a, **k)
+        k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+        k0.record(); out = raw(*a, **k); k1.record()
+        kev.append((k0, k1))
+        return out
+    gp._predict_raw = timed_raw
 
     def barrier():
         if world > 1:
@@ -362,6 +367,26 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
+    # N > 1: NCCL sharding parity inside the bench itself -- every rank scores the SAME small candidate block on its own
+    # GPU and the gathered results must be bit-identical across ranks; and a sharded scan of one common list must pick
+    # the candidate a single rank finds in the whole list
+    parity = None
+    if world > 1:
+        gc = torch.Generator(device=dev); gc.manual_seed(4242)
+        common = -5.0 + 10.0 * torch.rand((1 << 16, DIM), dtype=torch.float64, device=dev, generator=gc)
+        mu_c, var_c, u_c = raw(common, True, utility="bape", bounds=BOUNDS, ybest=ybest)
+        mine = torch.stack([mu_c, var_c, torch.nan_to_num(u_c, nan=0.0, posinf=1e300)]).cpu().numpy()
+        allr = apd.gather_concat(mine[None], axis=0)
+        same = all(np.array_equal(allr[0], allr[r]) for r in range(1, world))
+        lo_c, hi_c = apd.shard_bounds(common.shape[0], rank, world)
+        th_s, u_s = apd.scan_utility_sharded(gp, y, "bape", BOUNDS, nCandidates=common.shape[0], candidates=common[lo_c:hi_c])
+        u_all = np.where(np.isnan(u_c.cpu().numpy()), np.inf, u_c.cpu().numpy())
+        i_all = int(np.argmin(u_all))
+        picked = bool(u_s == u_all[i_all] and np.array_equal(th_s, common[i_all].cpu().numpy()))
+        parity = {"identical_across_ranks": bool(same), "sharded_scan_equals_single_rank_scan": picked, "queries": int(common.shape[0])}
+        if not (same and picked):
+            raise SystemExit("bench.py: multi-GPU parity check failed: %r" % (parity,))
+    gp._predict_raw = raw
     if world > 1:                     # all collectives are done: release the other ranks before rank 0's CPU legs
         dist.barrier()
         dist.destroy_process_group()
@@ -377,13 +402,15 @@ def run_gpu(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": workload_config({"parallelism": "candidates sharded over %d GPU(s), one all-gather of "
+                "config": workload_config({"parallelism": "candidates sharded over %d GPU(s) through "
+                                                          "approxposterior_b200.dist.scan_utility_sharded, one all-gather of "
                                                           "per-rank best" % world,
                                            "factor_s": t_factor}),
                 "e2e": {"value": Q * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 8,
                         "d2h_bytes_per_step": 3 * Q * 8, "steps": e2e_steps,
                         "api": "GP.predict_utility(y, pinned host ndarray, 'bape', bounds, out=pinned) -> (mu, var, util) + argmin"},
                 "gpu_launches": int(launches),
+                "multi_gpu_parity": parity,
                 "clocks": clk,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": (ncu_traffic() or {}).get("bytes"),

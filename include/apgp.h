@@ -203,6 +203,8 @@ int apgp_get_linv(apgp_handle* h, double* linv);
 int apgp_get_chol(apgp_handle* h, double* L);
 /* exp(-s), s >= 0, as evaluated inside the fused predict kernel (table + degree-5 polynomial); host buffers */
 int apgp_debug_exp_neg(apgp_handle* h, const double* s, int n, double* out);
+/* the 256-entry-table / degree-4 form used by the sampler and the mean-only predict kernel */
+int apgp_debug_exp_neg256(apgp_handle* h, const double* s, int n, double* out);
 /* host-only planning of the grouped variance kernel for a training set of N points on a GPU with num_sms SMs and a
  * call of Q queries: *G_out = CTAs per query tile (requested: -1 automatic, else as apgp_set_group); tab512 (may be NULL)
  * receives [full group | last group] x [owner of block-row ib | owner of panel column block cb] x 128 ints. */

@@ -369,22 +369,25 @@ def test_posterior_cfg2_many_ensembles_vs_single_ensemble():
     _assert_same_posterior(a, c)
 
 
-def test_kernel_exp_matches_libm():
-    """The table+polynomial exp(-s) used inside the fused predict kernel: <= 2 ulp against numpy."""
+@pytest.mark.parametrize("entry", ["apgp_debug_exp_neg", "apgp_debug_exp_neg256"])
+def test_kernel_exp_matches_libm(entry):
+    """The table+polynomial exp(-s) used inside the kernels (64-entry table + degree 5 in the fused predict kernel,
+    256-entry table + degree 4 in the sampler and the mean-only predict): <= 2 ulp against numpy."""
     import ctypes as C
     from approxposterior_b200 import GP, kernels, _lib
     gp = GP(kernel=kernels.ExpSquaredKernel([1.0], ndim=1))
     rng = np.random.default_rng(0)
     s = np.concatenate([rng.uniform(0, 700, 200000), rng.uniform(0, 3, 200000), [0.0, 1e-300, 1e-12, 699.999, 700.0, 750.0, 1e6, np.inf]])
     out = np.empty_like(s)
-    _lib.check(gp._lib.apgp_debug_exp_neg(gp._h, _lib.ptr(s), s.size, _lib.ptr(out)), "apgp_debug_exp_neg")
+    fn = getattr(gp._lib, entry)
+    _lib.check(fn(gp._h, _lib.ptr(s), s.size, _lib.ptr(out)), entry)
     ref = np.exp(-s)
     live = s < 700.0
     rel = np.abs(out[live] - ref[live]) / ref[live]
     assert rel.max() < 4.5e-16, rel.max()
     assert np.all(out[~live] == 0.0)
     nan_out = np.empty(1)
-    _lib.check(gp._lib.apgp_debug_exp_neg(gp._h, _lib.ptr(np.array([np.nan])), 1, _lib.ptr(nan_out)), "apgp_debug_exp_neg")
+    _lib.check(fn(gp._h, _lib.ptr(np.array([np.nan])), 1, _lib.ptr(nan_out)), entry)
     assert np.isnan(nan_out[0])            # NaN queries must stay NaN (approx.py:185 maps them to -inf)
 
 
