@@ -129,6 +129,10 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ t
 // above needs 10 plus an FP64 compare for the range check, done here on the integer pipe), <= 2 ulp.  Used where the
 // exponential IS the work and the kernel is bound by instruction issue next to the FP64 pipe (sampler, mean-only
 // predict); |r| <= ln2/512, so the first dropped term r^5/120 is below 4e-17.
+// RANGE_CHECK = false (callers whose arguments are finite by construction, i.e. prior-gated sampler proposals): the
+// exponent is clamped at 2^-1022 with one integer max instead of the four-instruction range test, so arguments beyond
+// ~708 return a positive number below 4.5e-308 instead of an exact 0.
+template <bool RANGE_CHECK = true>
 __device__ __forceinline__ double exp_neg256(double s, const double* __restrict__ tab) {
   const double x = -s;
   const double t = fma(x, 369.32993046757464 /*256/ln2*/, 6755399441055744.0);
@@ -141,6 +145,7 @@ __device__ __forceinline__ double exp_neg256(double s, const double* __restrict_
   const double pm1 = fma(r * r, q, r);                      // e^r - 1
   const double T = tab[n & 255];
   double res = fma(T, pm1, T);
+  if (!RANGE_CHECK) return __hiloint2double(__double2hiint(res) + (max(n >> 8, -1022) << 20), __double2loint(res));
   res = __hiloint2double(__double2hiint(res) + ((n >> 8) << 20), __double2loint(res));
   // s in [700, +inf] -> 0 (keeps 2^k normal); NaN has a larger high word and falls through to propagate
   const unsigned hs = (unsigned)__double2hiint(s);

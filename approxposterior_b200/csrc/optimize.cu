@@ -18,6 +18,15 @@
 // registers and takes the same branches; vectors (simplex, direction set) live in shared memory and are updated
 // element-wise by threads i < n; an objective evaluation is a CTA-cooperative function that returns the same
 // value to every thread.
+//
+// Licence note: nelder_mead_dev, powell_dev, bracket_dev and brent_dev restate algorithms of SciPy 1.18
+// (scipy/optimize/_optimize.py), which is distributed under the BSD 3-Clause licence --
+// Copyright (c) 2001-2002 Enthought, Inc. 2003, SciPy Developers.  All rights reserved.  Redistribution and use in
+// source and binary forms, with or without modification, are permitted provided that the copyright notice, the list
+// of conditions and the disclaimer of the BSD 3-Clause licence are retained (full text in
+// approxposterior_b200/_optimizers.py); neither the name of the copyright holder nor the names of its contributors
+// may be used to endorse or promote products derived from this software without specific prior written permission.
+// THIS SOFTWARE IS PROVIDED "AS IS", WITHOUT WARRANTIES OF ANY KIND.
 #include "apgp_internal.h"
 #include "chol_small.cuh"
 #include "chol_group.cuh"

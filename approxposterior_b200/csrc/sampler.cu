@@ -45,10 +45,21 @@ struct Smem {
 // inner product loop of eval_rows over the training points; XS is the [d+1][Npad] SoA block (row d = alphaA).
 // Two query rows x two training points per trip: every operand load is shared by at least two evaluations,
 // and all addressing is 32-bit offset arithmetic (the kernel is issue-bound, not FP64-bound).
+// D > 0: the dimension is a compile-time constant (the distance loop unrolls and the two query rows live in registers);
+// D = 0: generic run-time d.
+template <int D>
 __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const double* __restrict__ al,
-                                          const double* __restrict__ q0, const double* __restrict__ q1,
-                                          const double* __restrict__ etab, int N, int Npad, int d, int lane,
+                                          const double* __restrict__ q0s, const double* __restrict__ q1s,
+                                          const double* __restrict__ etab, int N, int Npad, int d_rt, int lane,
                                           double& acc0, double& acc1) {
+  const int d = D ? D : d_rt;
+  double q0r[D ? D : 1], q1r[D ? D : 1];
+  if (D) {
+#pragma unroll
+    for (int c = 0; c < (D ? D : 1); ++c) { q0r[c] = q0s[c]; q1r[c] = q1s[c]; }
+  }
+  const double* q0 = D ? q0r : q0s;
+  const double* q1 = D ? q1r : q1s;
   int j = lane;
   // four training points per trip: eight independent exponential chains per thread (the loop is bound by the dependent
   // latency of the chain, ~10 FP64 operations deep, not by issue slots or the FP64 pipe: ncu 50 % / 71 % with two
@@ -57,6 +68,7 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
   for (; j + 96 < N; j += 128) {
     double s00 = 0.0, s01 = 0.0, s02 = 0.0, s03 = 0.0, s10 = 0.0, s11 = 0.0, s12 = 0.0, s13 = 0.0;
     int off = j;
+#pragma unroll
     for (int c = 0; c < d; ++c, off += Npad) {
       const double xa = xs[off], xb = xs[off + 32], xc = xs[off + 64], xd = xs[off + 96];
       const double qa = q0[c], qb = q1[c];
@@ -71,14 +83,15 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
       t = xd - qb; s13 = fma(t, t, s13);
     }
     const double a0 = al[j], a1 = al[j + 32], a2 = al[j + 64], a3 = al[j + 96];
-    const double e00 = exp_neg256(s00, etab), e01 = exp_neg256(s01, etab), e02 = exp_neg256(s02, etab), e03 = exp_neg256(s03, etab);
-    const double e10 = exp_neg256(s10, etab), e11 = exp_neg256(s11, etab), e12 = exp_neg256(s12, etab), e13 = exp_neg256(s13, etab);
+    const double e00 = exp_neg256<false>(s00, etab), e01 = exp_neg256<false>(s01, etab), e02 = exp_neg256<false>(s02, etab), e03 = exp_neg256<false>(s03, etab);
+    const double e10 = exp_neg256<false>(s10, etab), e11 = exp_neg256<false>(s11, etab), e12 = exp_neg256<false>(s12, etab), e13 = exp_neg256<false>(s13, etab);
     acc0 = fma(e00, a0, acc0); acc0 = fma(e01, a1, acc0); acc0 = fma(e02, a2, acc0); acc0 = fma(e03, a3, acc0);
     acc1 = fma(e10, a0, acc1); acc1 = fma(e11, a1, acc1); acc1 = fma(e12, a2, acc1); acc1 = fma(e13, a3, acc1);
   }
   for (; j + 32 < N; j += 64) {
     double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;      // s[row][point]
     int off = j;
+#pragma unroll
     for (int c = 0; c < d; ++c, off += Npad) {
       const double xa = xs[off], xb = xs[off + 32];
       const double qa = q0[c], qb = q1[c];
@@ -89,20 +102,21 @@ __device__ __forceinline__ void eval_pair(const double* __restrict__ xs, const d
       t = xb - qb; s11 = fma(t, t, s11);
     }
     const double a0 = al[j], a1 = al[j + 32];
-    acc0 = fma(exp_neg256(s00, etab), a0, acc0); acc0 = fma(exp_neg256(s01, etab), a1, acc0);
-    acc1 = fma(exp_neg256(s10, etab), a0, acc1); acc1 = fma(exp_neg256(s11, etab), a1, acc1);
+    acc0 = fma(exp_neg256<false>(s00, etab), a0, acc0); acc0 = fma(exp_neg256<false>(s01, etab), a1, acc0);
+    acc1 = fma(exp_neg256<false>(s10, etab), a0, acc1); acc1 = fma(exp_neg256<false>(s11, etab), a1, acc1);
   }
   for (; j < N; j += 32) {
     double s0 = 0.0, s1 = 0.0;
     int off = j;
+#pragma unroll
     for (int c = 0; c < d; ++c, off += Npad) {
       const double x = xs[off];
       const double d0 = x - q0[c], d1 = x - q1[c];
       s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
     }
     const double a = al[j];
-    acc0 = fma(exp_neg256(s0, etab), a, acc0);
-    acc1 = fma(exp_neg256(s1, etab), a, acc1);
+    acc0 = fma(exp_neg256<false>(s0, etab), a, acc0);
+    acc1 = fma(exp_neg256<false>(s1, etab), a, acc1);
   }
 }
 
@@ -121,8 +135,18 @@ __device__ void eval_rows(const SamplerParams& p, const Smem& sm, int np, int r0
     if (ok0 | ok1) {
       const double* q0 = sm.sq + i0 * d;
       const double* q1 = sm.sq + i1 * d;
-      if (sm.xs) eval_pair(sm.xs, sm.xs + d * Npad, q0, q1, sm.etab, Neff, Npad, d, lane, acc0, acc1);
-      else eval_pair(p.Xs, p.alphaA, q0, q1, sm.etab, p.N, Npad, d, lane, acc0, acc1);
+      if (sm.xs) {
+        const double* al = sm.xs + d * Npad;
+        switch (d) {                       // the shared-memory path is the hot one: specialise small dimensions (the kernel
+                                           // is capped at 64 registers by its 1024-thread launch bound: larger d would spill)
+          case 1: eval_pair<1>(sm.xs, al, q0, q1, sm.etab, Neff, Npad, d, lane, acc0, acc1); break;
+          case 2: eval_pair<2>(sm.xs, al, q0, q1, sm.etab, Neff, Npad, d, lane, acc0, acc1); break;
+          case 3: eval_pair<3>(sm.xs, al, q0, q1, sm.etab, Neff, Npad, d, lane, acc0, acc1); break;
+          default: eval_pair<0>(sm.xs, al, q0, q1, sm.etab, Neff, Npad, d, lane, acc0, acc1); break;
+        }
+      } else {
+        eval_pair<0>(p.Xs, p.alphaA, q0, q1, sm.etab, p.N, Npad, d, lane, acc0, acc1);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);

@@ -167,3 +167,31 @@ def test_reference_run_uses_the_engine_for_every_hot_call(tmp_path):
             else:
                 assert lp_b[i] == -np.inf and np.isnan(blob_b[i])
         assert apx.__version__ == "0.4"
+
+
+# ------------------------------------------------------------------------------------------ CPU: engine shim, host parts
+@needs_ref
+def test_engine_shim_installs_and_serves_the_emcee_surface_on_cpu(tmp_path):
+    """compat.install() without a GPU: the reference imports, george.GP is the engine's class (creating one would need
+    the device), and the emcee shim -- emcee 3.0's signature on the engine's NumPy-RNG sampler -- reproduces the
+    reference's own burn-in known answer (tests/test_Burnin.py:17-91, scalar log_prob_fn with args) and MCSE test."""
+    from approxposterior_b200 import compat
+    with _Reference(compat, tmp_path) as ref:
+        import approxposterior_b200
+        assert sys.modules["george"].GP is approxposterior_b200.GP
+        assert sys.modules["george"].kernels.ExpSquaredKernel is approxposterior_b200.kernels.ExpSquaredKernel
+        assert int(sys.modules["emcee"].__version__.split(".")[0]) > 2
+        ref.run("test_Import", "test_import")
+        ref.run("test_Burnin", "testBurnin")
+        ref.run("test_MCSE", "testMCSE")
+        ref.run("test_TestFns", "testTestFns")
+        be = sys.modules["emcee"].backends.HDFBackend(str(tmp_path / "chain.h5"))
+        be.reset(8, 2)
+        s = sys.modules["emcee"].EnsembleSampler(8, 2, lambda t: -0.5 * float(np.sum(np.asarray(t) ** 2)), backend=be)
+        np.random.seed(1)
+        for _ in s.sample(initial_state=np.random.randn(8, 2), iterations=30):
+            pass
+        assert s.get_chain().shape == (30, 8, 2) and (tmp_path / "chain.npz").exists()
+        with pytest.raises(NotImplementedError):
+            for _ in s.sample(initial_state=np.random.randn(8, 2), iterations=3, thin_by=2):
+                pass
