@@ -491,7 +491,7 @@ int apgp_grad_log_likelihood(apgp_handle* h, int fit_amp, double* grad) {
   for (int i = 0; i < P; ++i) grad[i] = 0.0;
   if (!h->factored) return APGP_NOT_COMPUTED;      // george: zeros when quiet and not computed
   Guard g(h->device);
-  CUI(h->bscal.reserve((2 + APGP_MAX_DIM) * 8));
+  CUI(h->bscal.reserve(grad_loglik_doubles(h->Np, d) * 8));
   int nl = 0;
   CUI(launch_grad_loglik(h->X.as<double>(), h->N, d, h->Np, h->Linv.as<double>(), h->alpha.as<double>(),
                          h->hyper.as<double>(), fit_amp, h->work.as<double>(), h->bscal.as<double>(), h->stream, &nl));

@@ -99,7 +99,8 @@ int chol_group_cluster(int Np, int R, int num_sms);
 size_t chol_group_ws_bytes(int Np, int R);
 int launch_loglik_group(const double* X, const double* y, int N, int d, int Np, const double* hyper, int R, int num_sms,
                         void* ws_bytes, double* ll, cudaStream_t st);
-// gradient pieces: Kinv = Linv^T Linv (lower), then tr-products
+// gradient pieces: Kinv = Linv^T Linv (lower), then tr-products; grad_dev needs grad_loglik_doubles(Np, d) doubles
+size_t grad_loglik_doubles(int Np, int d);
 int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv, const double* alpha,
                        const double* hyper_dev, int fit_amp, double* work /*[Np*Np]*/, double* grad_dev, cudaStream_t st,
                        int* launches);

@@ -358,9 +358,13 @@ __global__ void loglik_finish_kernel(FactorBatch fb, double* __restrict__ ll) {
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restrict__ X, int N, int d, int Np,
                                                           const double* __restrict__ Kinv,
                                                           const double* __restrict__ alpha,
-                                                          const double* __restrict__ hyper, double* __restrict__ out) {
+                                                          const double* __restrict__ hyper, double* __restrict__ part) {
+  // part: [ntiles][2 + d] per-tile partial sums (slot 0 = this tile's share of sum(alpha), tile 0 only); they are added
+  // in tile order by grad_finish_kernel, so the gradient does not depend on the order the tiles happen to finish in
+  // (the first version met in atomicAdds and differed in the last bits from run to run and from GPU to GPU)
   __shared__ double red[256];
   int t = blockIdx.x;
+  double* out = part + (size_t)t * (2 + d);
   int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
   while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
   while (bi * (bi + 1) / 2 > t) --bi;
@@ -390,17 +394,25 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restri
     red[threadIdx.x] = accs[c];
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) atomicAdd(&out[1 + c], red[0]);
+    if (threadIdx.x == 0) out[1 + c] = red[0];
     __syncthreads();
   }
+  if (threadIdx.x == 0) out[0] = 0.0;
   if (t == 0) {
     double s = 0.0;
     for (int i = threadIdx.x; i < N; i += 256) s += alpha[i];
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) atomicAdd(&out[0], red[0]);
+    if (threadIdx.x == 0) out[0] = red[0];
   }
+}
+__global__ void grad_finish_kernel(const double* __restrict__ part, int ntiles, int d, double* __restrict__ out) {
+  const int c = threadIdx.x;
+  if (c >= 2 + d) return;
+  double s = 0.0;
+  for (int t = 0; t < ntiles; ++t) s += part[(size_t)t * (2 + d) + c];
+  out[c] = s;
 }
 
 
@@ -757,6 +769,8 @@ int launch_loglik_finish(const FactorBatch& fb, double* ll, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+size_t grad_loglik_doubles(int Np, int d) { const size_t nb = Np / T; return (size_t)(2 + d) * (1 + nb * (nb + 1) / 2); }
+
 int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv, const double* alpha,
                        const double* hyper_dev, int fit_amp, double* work, double* grad_dev, cudaStream_t st,
                        int* launches) {
@@ -766,9 +780,11 @@ int launch_grad_loglik(const double* X, int N, int d, int Np, const double* Linv
   // Kinv (lower tiles) = Linv^T Linv
   GemmDesc g{Linv, Np, 1, Linv, Np, 0, work, Np, 1.0, nb, nb, nb, 3, 0, 0, 0};
   gemm_tile_kernel<<<dim3(nb * nb, 1), GT, TILE_SMEM, st>>>(g);
-  cudaMemsetAsync(grad_dev, 0, sizeof(double) * (2 + d), st);
-  grad_reduce_kernel<<<nb * (nb + 1) / 2, 256, 0, st>>>(X, N, d, Np, work, alpha, hyper_dev, grad_dev);
-  if (launches) *launches += 2;
+  // grad_dev: [2 + d] result, followed by [ntiles][2 + d] per-tile partials (grad_loglik_doubles(Np, d) in all)
+  const int ntiles = nb * (nb + 1) / 2;
+  grad_reduce_kernel<<<ntiles, 256, 0, st>>>(X, N, d, Np, work, alpha, hyper_dev, grad_dev + (2 + d));
+  grad_finish_kernel<<<1, 64, 0, st>>>(grad_dev + (2 + d), ntiles, d, grad_dev);
+  if (launches) *launches += 3;
   return (int)cudaGetLastError();
 }
 

@@ -111,10 +111,7 @@ def test_two_handles_on_two_devices_in_one_process():
         gl = gp.grad_log_likelihood(y)                                           # tiled GEMM path
         outs.append((mu, var, u, m2, ch, ll, g, xs, fs, ps, fn, gl))
     for k, (a, b) in enumerate(zip(*outs)):
-        if k == len(outs[0]) - 1:       # grad_log_likelihood: its tile partials meet in atomicAdds (order not fixed)
-            np.testing.assert_allclose(a, b, rtol=1e-12)
-        else:
-            assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
 
 
 def _comm_worker(rank, ws, idq, outq):
