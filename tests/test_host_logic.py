@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(_lib.LIB_PATH), "build libapgp.so first (__graft_entry__.build())"
     lib = ctypes.CDLL(_lib.LIB_PATH)
     header = open(os.path.join(ROOT, "include", "apgp.h")).read()
-    declared = set(re.findall(r"\b(apgp_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(apgp_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
