@@ -19,6 +19,7 @@
 // and without -fmad.
 #pragma once
 #include <cuda_runtime.h>
+#include "common.cuh"
 
 namespace apgp {
 
@@ -42,6 +43,41 @@ __device__ long long g_prof[16];
 //    FAST_PIVOT: pivots by rsqrt (<= 1 ulp, ~75 cycles) instead of IEEE sqrt + divide (~190 cycles): used by the
 //    optimiser objectives, where the pivot chain is the critical path; the factorisation behind predict keeps the
 //    correctly rounded pair (its errors are amplified by cond(K) into alpha and L^{-1}).
+// Left-looking update of block column JB on the FP64 tensor pipe:
+//   A[i][JB + c] -= sum_{k0 <= k < k1} L[i][k] L[JB + c][k]     for the rows i >= JB and the rhs rows, c < bwB
+// as one DMMA.8x8x4 chain per 8 rows (two accumulator pairs, so consecutive k4 steps do not wait on each other): an
+// m8 tile of rows times the 8 columns of the block, k running over the finished columns.  The per-(row, column) FMA
+// dot products this replaces were 14.4 k of the 36 k cycles of a factorisation at N = 70 (profiles/r01_optimizers.md).
+// warp / nwarps: the calling warps' index and count; k0, k1 multiples of 8.  Packed rows: row i at K + i (i + 1) / 2;
+// rhs row q at r + q * ldr.  Entries above the diagonal inside the block (JB + c > i) are not stored and not written.
+__device__ __forceinline__ void chol_update_dmma(double* __restrict__ K, double* __restrict__ r, int N, int nrhs, int ldr,
+                                                 int JB, int bwB, int k0, int k1, int warp, int nwarps) {
+  const int lane = threadIdx.x & 31, rsub = lane >> 2, kq = lane & 3;
+  const int nmat = N - JB, nrows = nmat + nrhs, ntile = (nrows + 7) >> 3;
+  const bool bvalid = rsub < bwB;
+  const double* Lc = K + (JB + rsub) * (JB + rsub + 1) / 2;
+  for (int mt = warp; mt < ntile; mt += nwarps) {
+    const int vr = mt * 8 + rsub;
+    double* Li = nullptr;
+    if (vr < nmat) Li = K + (JB + vr) * (JB + vr + 1) / 2;
+    else if (vr < nrows) Li = r + (vr - nmat) * ldr;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    for (int k = k0; k < k1; k += 8) {
+      const double a0 = Li ? Li[k + kq] : 0.0, b0 = bvalid ? Lc[k + kq] : 0.0;
+      const double a1 = Li ? Li[k + 4 + kq] : 0.0, b1 = bvalid ? Lc[k + 4 + kq] : 0.0;
+      dmma884(c0, c1, a0, b0);
+      dmma884(e0, e1, a1, b1);
+    }
+    c0 += e0; c1 += e1;
+    if (Li) {
+      const int col = 2 * kq;
+      const bool tri = vr < nmat;                      // matrix rows store only columns <= their own index
+      if (col < bwB && !(tri && col > vr)) Li[JB + col] -= c0;
+      if (col + 1 < bwB && !(tri && col + 1 > vr)) Li[JB + col + 1] -= c1;
+    }
+  }
+}
+
 template <int NT, int BAR>
 __device__ __forceinline__ void chol_sync() {
   if (BAR == 0) __syncthreads();
@@ -57,23 +93,7 @@ __device__ __forceinline__ void chol_packed_blocked_classic(double* __restrict__
     const int bw = (N - J0 < CHOL_B) ? (N - J0) : CHOL_B;
     PROF_T(t_p1);
     if (J0 > 0) {
-      // items = (row, column) dot products of length J0, one item per thread pass; 32-bit index math
-      // (N < 256, so i(i+1)/2 < 2^15).  (Splitting short item lists over 2-8 lanes + shuffles measured slower.)
-      const int nitems = (N - J0 + nrhs) * CHOL_B;              // rows J0..N-1 and the rhs rows, CHOL_B columns each
-      for (int it = tid; it < nitems; it += NT) {
-        const int i = J0 + (it >> 3), c = it & (CHOL_B - 1);
-        if (c >= bw || (i < N && J0 + c > i)) continue;
-        const double* Li = (i < N) ? K + i * (i + 1) / 2 : r + (i - N) * ldr;
-        const double* Lc = K + (J0 + c) * (J0 + c + 1) / 2;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;             // J0 is a multiple of 8
-#pragma unroll 2
-        for (int k = 0; k < J0; k += 4) {
-          s0 = fma(Li[k], Lc[k], s0); s1 = fma(Li[k + 1], Lc[k + 1], s1);
-          s2 = fma(Li[k + 2], Lc[k + 2], s2); s3 = fma(Li[k + 3], Lc[k + 3], s3);
-        }
-        double* dst = (i < N) ? K + i * (i + 1) / 2 + J0 + c : r + (i - N) * ldr + J0 + c;
-        *dst -= ((s0 + s1) + (s2 + s3));
-      }
+      chol_update_dmma(K, r, N, nrhs, ldr, J0, bw, 0, J0, tid >> 5, NT / 32);
       PROF_ADD(4, t_p1);
       chol_sync<NT, BAR>();
     }
@@ -155,21 +175,7 @@ __device__ __forceinline__ void chol_packed_blocked_lookahead(double* __restrict
   // (N < 256, so i(i+1)/2 < 2^15); k0, k1 multiples of 8.  (Splitting short item lists over 2-8 lanes + shuffles
   // measured slower.)
   auto update = [&](int JB, int bwB, int k0, int k1, int t0, int nthr) {
-    const int nitems = (N - JB + nrhs) * CHOL_B;
-    for (int it = tid - t0; it < nitems; it += nthr) {
-      const int i = JB + (it >> 3), c = it & (CHOL_B - 1);
-      if (c >= bwB || (i < N && JB + c > i)) continue;
-      const double* Li = (i < N) ? K + i * (i + 1) / 2 : r + (i - N) * ldr;
-      const double* Lc = K + (JB + c) * (JB + c + 1) / 2;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
-      for (int k = k0; k < k1; k += 4) {
-        s0 = fma(Li[k], Lc[k], s0); s1 = fma(Li[k + 1], Lc[k + 1], s1);
-        s2 = fma(Li[k + 2], Lc[k + 2], s2); s3 = fma(Li[k + 3], Lc[k + 3], s3);
-      }
-      double* dst = (i < N) ? K + i * (i + 1) / 2 + JB + c : r + (i - N) * ldr + JB + c;
-      *dst -= ((s0 + s1) + (s2 + s3));
-    }
+    chol_update_dmma(K, r, N, nrhs, ldr, JB, bwB, k0, k1, (tid - t0) >> 5, nthr / 32);
   };
   for (int J0 = 0; J0 < N; J0 += CHOL_B) {
     const int bw = (N - J0 < CHOL_B) ? (N - J0) : CHOL_B;
