@@ -91,6 +91,15 @@ def defaultGP(theta, y, order=None, white_noise=-12, fitAmp=False):
 DEVICE_OPTIMIZER = True      # module default for optimizeGP(engine=None)
 
 
+def _is_default_prior(fn):
+    """This module's defaultHyperPrior, or the reference's function of the same name and body (gpUtils.py:22-43) when
+    the reference package calls optimizeGP through ``compat.accelerate()``: both are the |p[1:]| <= 20 box the device
+    objective applies itself."""
+    if fn is defaultHyperPrior:
+        return True
+    return getattr(fn, "__name__", "") == "defaultHyperPrior" and (getattr(fn, "__module__", "") or "").split(".")[-1] == "gpUtils"
+
+
 def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=None, p0=None,
                gpHyperPrior=defaultHyperPrior, batched=True, engine=None):
     """Maximise the marginal likelihood over nGPRestarts starts (reference gpUtils.py:184-257).
@@ -121,7 +130,7 @@ def optimizeGP(gp, theta, y, seed=None, nGPRestarts=1, method="powell", options=
     if engine is None:
         engine = "device" if DEVICE_OPTIMIZER else "lockstep"
     on_device = (engine == "device" and use_batch and _opt.supported(method, options)
-                 and (gpHyperPrior is defaultHyperPrior or gpHyperPrior is None)
+                 and (_is_default_prior(gpHyperPrior) or gpHyperPrior is None)
                  and hasattr(gp, "minimize_nll") and gp.can_minimize_nll())
 
     from . import dist as _dist

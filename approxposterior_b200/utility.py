@@ -87,6 +87,18 @@ def JonesUtility(theta, y, gp, priorFn, zeta=0.01):
 
 
 _KIND = {AGPUtility: "agp", BAPEUtility: "bape", JonesUtility: "jones"}
+ASSUME_BOX_PRIOR = False     # set by compat.accelerate(box_prior=True): a plain-function prior is the box over `bounds`
+
+
+def _kind_by_name(fn):
+    """The reference's own utility functions (approxposterior.utility.{AGP,BAPE,Jones}Utility), recognised by name when
+    the reference package calls this minimiser through ``compat.accelerate()``: same formulas (utility.py:99-250), so
+    they are evaluated by the fused predict + utility kernel instead of one Python call per point."""
+    name = getattr(fn, "__name__", "")
+    mod = getattr(fn, "__module__", "") or ""
+    if mod.split(".")[-1] == "utility" and name in ("AGPUtility", "BAPEUtility", "JonesUtility"):
+        return {"AGPUtility": "agp", "BAPEUtility": "bape", "JonesUtility": "jones"}[name]
+    return None
 
 
 def utilityBatch(thetas, y, gp, priorFn, kind, bounds=None, zeta=0.01):
@@ -177,6 +189,7 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
     """
     if str(method).lower() == "nelder-mead" and options is None:
         options = {"adaptive": True}
+    _box_hint = bounds                              # before the reference's rule below drops it
     if str(method).lower() in [" l-bfgs-b", "tnc"]:
         pass
     else:
@@ -203,9 +216,11 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
     if _start is not None:          # engine extension: polish a known-good candidate (scanUtility)
         starts[0] = np.asarray(_start, dtype=np.float64).ravel()
 
-    kind = _KIND.get(fn) or getattr(fn, "device_kind", None)
+    kind = _KIND.get(fn) or getattr(fn, "device_kind", None) or _kind_by_name(fn)
     fn_batch = getattr(fn, "batch", None)      # any objective may bring its own batched form
     box = getattr(priorFn, "bounds", None)
+    if box is None and ASSUME_BOX_PRIOR and _box_hint is not None:
+        box = [(float(a), float(b)) for a, b in _box_hint]      # the caller vouches: priorFn is the box over `bounds`
     if engine is None:
         engine = "device" if DEVICE_OPTIMIZER else "lockstep"
     if (engine == "device" and batched and kind is not None and box is not None and hasattr(gp, "minimize_utility")

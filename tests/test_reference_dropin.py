@@ -137,6 +137,27 @@ def test_reference_optimizer_path_dependent_on_engine(module, function, tmp_path
 
 @pytest.mark.gpu
 @needs_ref
+@pytest.mark.parametrize("module,function", [("test_OptimizeGP", "testGPOptAmp"), ("test_OptimizeGP", "testGPOptNoAmp"),
+                                             ("test_findNewPoint", "testFindNoAmp"), ("test_MAP", "testMAPAmp"),
+                                             ("test_1DBayesOpt", "test_1DBO"), ("test_2DBayesOpt", "test_2DBO"),
+                                             ("test_APRun", "testRun")])
+def test_reference_tests_on_engine_accelerated(module, function, tmp_path):
+    """compat.accelerate(): the reference's source files are still untouched, but its two multistart drivers resolve to
+    the engine's batched ones (every optGP restart in one device launch, utility restarts in lock step).  The
+    reference's own optimiser-level known answers must still come out."""
+    from approxposterior_b200 import compat, gpUtils
+    with _Reference(compat, tmp_path) as ref:
+        compat.accelerate()
+        gpUtils.optimizeGP.last_stats = None
+        ref.run(module, function)
+        import approxposterior
+        assert approxposterior.gpUtils.optimizeGP is gpUtils.optimizeGP
+        if module != "test_findNewPoint":                      # (findNextPoint(computeLnLike=False) never refits)
+            assert gpUtils.optimizeGP.last_stats is not None and gpUtils.optimizeGP.last_stats["scheduler"] == "device"
+
+
+@pytest.mark.gpu
+@needs_ref
 def test_reference_run_uses_the_engine_for_every_hot_call(tmp_path):
     """The reference's ApproxPosterior.run (README configuration, shortened) on the engine: the GP object the
     reference holds is the engine's, the kernels were launched, and the batched _gpll seam of the emcee shim
