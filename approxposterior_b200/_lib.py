@@ -45,6 +45,7 @@ _SIGNATURES = {
     "apgp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "apgp_destroy": (C.c_int, [C.c_void_p]),
     "apgp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "apgp_reset": (C.c_int, [C.c_void_p]),
     "apgp_synchronize": (C.c_int, [C.c_void_p]),
     "apgp_launch_count": (C.c_longlong, [C.c_void_p]),
     "apgp_set_training": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),

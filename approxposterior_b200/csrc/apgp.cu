@@ -147,6 +147,22 @@ int apgp_destroy(apgp_handle* h) {
   return APGP_OK;
 }
 
+int apgp_reset(apgp_handle* h) {
+  if (!h) return fail(APGP_ERR_ARG, "null handle");
+  Guard g(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (!h->own_stream) { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  h->N = h->d = h->Np = h->Npad = 0;
+  h->has_training = h->has_hyper = h->factored = false;
+  h->mean = 0; h->amp = 1; h->white_noise = -12; h->logdet = 0; h->loglik = 0;
+  h->plan_Npad = h->plan_G = h->plan_d = -1;
+  h->variant = 2; h->variant_eff = 2; h->group = -1;            // tuning knobs back to their defaults (as apgp_create)
+  if (const char* v = getenv("APGP_PREDICT_VARIANT")) { int vv = atoi(v); h->variant = (vv >= 0 && vv <= 2) ? vv : 2; }
+  if (const char* gv = getenv("APGP_PREDICT_GROUP")) h->group = atoi(gv);
+  if (h->comm) { comm_destroy(h->comm); h->comm = nullptr; h->comm_rank = 0; h->comm_world = 1; }
+  return APGP_OK;
+}
+
 int apgp_set_stream(apgp_handle* h, void* s) {
   if (!h) return fail(APGP_ERR_ARG, "null handle");
   Guard g(h->device);

@@ -34,6 +34,10 @@ def _default_device():
     return 0
 
 
+_HANDLE_POOL = {}            # device ordinal -> idle apgp handles (reset, buffers kept)
+_HANDLE_POOL_MAX = 4
+
+
 def _is_torch(a):
     return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
 
@@ -59,8 +63,12 @@ class GP(object):
         self._y = None
         self._device = _default_device() if device is None else int(device)
         self._lib = _lib.load()
-        h = C.c_void_p()
-        _lib.check(self._lib.apgp_create(C.byref(h), self._device), "apgp_create")
+        pool = _HANDLE_POOL.get(self._device)
+        if pool:
+            h = pool.pop()                   # a recycled handle: buffers, stream and pinned staging already exist
+        else:
+            h = C.c_void_p()
+            _lib.check(self._lib.apgp_create(C.byref(h), self._device), "apgp_create")
         self._h = h
         self._logdet = np.nan
         self._loglik = -np.inf
@@ -71,7 +79,13 @@ class GP(object):
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             try:
-                self._lib.apgp_destroy(h)
+                pool = _HANDLE_POOL.setdefault(self._device, [])
+                # the reference builds a fresh george.GP for every new design point (approx.py:712-717): keep a few
+                # handles alive and reset them instead of destroying / re-creating streams, pinned memory and buffers
+                if len(pool) < _HANDLE_POOL_MAX and self._lib.apgp_reset(h) == 0:
+                    pool.append(h)
+                else:
+                    self._lib.apgp_destroy(h)
             except Exception:
                 pass
             self._h = None

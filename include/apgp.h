@@ -51,6 +51,10 @@ int apgp_version(void);
 int apgp_create(apgp_handle** out, int device);
 int apgp_destroy(apgp_handle* h);
 int apgp_set_stream(apgp_handle* h, void* cuda_stream);           /* cudaStream_t; NULL = library-owned stream */
+/* Forget the training set, hyper-parameters and factorisation but keep every device buffer, the stream and the pinned
+ * staging area: lets a caller that builds a fresh george.GP per design point (approx.py:712-717) recycle handles
+ * instead of paying stream creation, cudaHostAlloc and a dozen cudaMallocs each time. */
+int apgp_reset(apgp_handle* h);
 int apgp_synchronize(apgp_handle* h);
 long long apgp_launch_count(const apgp_handle* h);                /* kernels launched so far by this handle */
 
