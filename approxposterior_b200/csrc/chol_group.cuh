@@ -11,16 +11,26 @@
 // Work split.  The lower triangle of K is cut into 64x64 tiles; tile (i, j) belongs to CTA  (i(i+1)/2 + j) mod C  for
 // the whole factorisation (owner computes: build, every trailing update, the panel solve, and -- for diagonal tiles --
 // the 64x64 factorisation).  Only PANEL results cross CTAs, so step k needs two flags:
-//   A_k  "diagonal block k factored":  D_k^{-1} and z_k are in global memory        (one writer, flagA)
-//   B_k  "panel k solved":             every L_ik = A_ik D_k^{-T} is in global memory (C writers, cntB)
+//   A_k  "diagonal block k factored":  L_kk, its reciprocal pivots, the inverses of its eight 8x8 diagonal blocks and
+//        z_k are in global memory                                                    (one writer, flagA)
+//   B_k  "panel k solved":             every L_ik = A_ik L_kk^{-T} is in global memory (C writers, cntB)
 // Look-ahead: after B_k a CTA first updates its tiles of column k+1 (the owner of (k+1, k+1) then factors it at once
 // and raises A_{k+1}), and only then applies step k to the rest of its trailing tiles -- that deferred work overlaps
 // the next block's serial pivot chain on the owner.
 //
-// Inside a CTA (256 threads): two tile workers of 4 warps each (warp tile 32x32, DMMA.8x8x4 from padded shared tiles
-// staged with cp.async.cg, so a worker's loads overlap the other's MMAs); the 64x64 diagonal factorisation uses all
-// 256 threads (chol_small.cuh: 8-wide register-blocked, with r_k and the 64 unit vectors riding along as right-hand
-// sides so that z_k = D^{-1} r_k and D^{-1} itself come out of the same pass).
+// Inside a CTA (256 threads).  The restart's matrix lives in L2-resident global memory TILE-MAJOR: every 64x64 tile is one
+// contiguous [64][68] block (the shared-memory image), so an operand tile is ONE bulk TMA copy.
+//   build     two workers of 4 warps, one tile each: inputs pre-scaled and transposed in shared memory, one column and
+//             sixteen consecutive rows per thread and pass (16 independent chains, LDS.128 broadcasts), table exponential;
+//             the next tile's inputs travel in registers meanwhile;
+//   diagonal  all 256 threads (chol_small.cuh: 8-wide register-blocked, r_k riding along as a right-hand side so that
+//             z_k = L_kk^{-1} r_k comes out of the same pass); 64 threads then invert the eight 8x8 diagonal blocks;
+//   panel     two workers, one tile each: X = P L_kk^{-T} blockwise on the tensor pipe (cg_trsm_dmma: per 8 rows a
+//             warp-private chain of DMMA.8x8x4 against the finished columns, the inverted 8x8 block applied by two more);
+//   updates   all 8 warps as one TMA-fed software pipeline (cg_update_phase): A, B and C tiles by bulk copies one update
+//             ahead, warp tile 32x16, one CTA barrier per update; the DMMA loop itself runs at the tensor-pipe rate
+//             (4.1 k cycles per 64x64x64 update).
+// Measured per phase with the -DAPGP_PROF_CG build (tools/profile_chol_group_phases.py, profiles/r02_chol_group_phases.md).
 //
 // The flags only ever grow (epoch-based targets), so repeated evaluations by the same cluster -- the device
 // optimisers call this once per objective evaluation -- need no reset.  All partial sums are added in block order:
@@ -38,7 +48,10 @@ constexpr int CG_LD = 68;                // padded shared leading dimension (con
 constexpr int CG_THREADS = 256;
 constexpr int CG_WT = 128;               // threads per tile worker
 constexpr int CG_TILE = CG_T * CG_LD;    // doubles per staged tile
-constexpr size_t CG_SMEM_DOUBLES = (size_t)4 * CG_TILE;          // 2 workers x (A, B)
+constexpr int CG_AUX = CG_T + 8 * 64;    // per worker: z_k [64] + the 8 inverted 8x8 diagonal blocks of L_kk (panel solve)
+constexpr int CG_CONST = 64 + APGP_MAXD; // exponential table 2^(j/64) + per-dimension input scales sqrt(1 / (2 M_i))
+constexpr int CG_NTILES = 5;             // tile buffers: 2 x (A, B) + the C tile of the update pipeline
+constexpr size_t CG_SMEM_DOUBLES = (size_t)CG_NTILES * CG_TILE + 2 * CG_AUX + CG_CONST;   // + 2 x aux + constants
 constexpr int CG_DIAG_LDR = CG_T + 1;
 // the diagonal factorisation aliases the tile buffers: packed block + (1 + 64) right-hand sides + pivots
 static_assert((size_t)(CG_T * (CG_T + 1) / 2 + (CG_T + 1) * CG_DIAG_LDR + CG_T) <= CG_SMEM_DOUBLES, "diag scratch fits");
@@ -48,7 +61,7 @@ struct CholGroup {
   int C, rank;                           // cluster size, this CTA's rank in it
   const double* X;                       // [N][d] training inputs (global, read-only for the kernel's lifetime)
   const double* y;                       // [N]
-  double* K;                             // this restart's [Np][Np] row-major workspace (lower tiles used)
+  double* K;                             // this restart's matrix, tile-major (cg_tile_ptr): nb(nb+1)/2 tiles of [64][CG_LD]
   double* Dinv;                          // [nb][64][64]
   double* r;                             // [Np]
   double* part;                          // [2][nb][4]: per block sum z^2, sum log diag, bad pivot (double-buffered by epoch)
@@ -63,14 +76,14 @@ struct GroupWs {
 };
 inline size_t cg_ws_bytes(int Np, int R) {
   const size_t nb = Np / CG_T;
-  return (size_t)R * ((size_t)Np * Np + nb * CG_T * CG_T + Np + 2 * nb * 4) * sizeof(double) + ((size_t)R * 16 + 255) / 256 * 256 + 256;
+  return (size_t)R * (nb * (nb + 1) / 2 * CG_TILE + nb * CG_T * CG_T + Np + 2 * nb * 4) * sizeof(double) + ((size_t)R * 16 + 255) / 256 * 256 + 256;
 }
 inline GroupWs cg_ws_carve(void* ws_bytes, int Np, int R) {
   const size_t nb = Np / CG_T;
   GroupWs ws;
   char* base = static_cast<char*>(ws_bytes);
   ws.flags = reinterpret_cast<unsigned long long*>(base); base += ((size_t)R * 16 + 255) / 256 * 256;
-  ws.K = reinterpret_cast<double*>(base); ws.sK = (size_t)Np * Np; base += (size_t)R * ws.sK * 8;
+  ws.K = reinterpret_cast<double*>(base); ws.sK = nb * (nb + 1) / 2 * CG_TILE; base += (size_t)R * ws.sK * 8;
   ws.Dinv = reinterpret_cast<double*>(base); ws.sDinv = nb * CG_T * CG_T; base += (size_t)R * ws.sDinv * 8;
   ws.r = reinterpret_cast<double*>(base); ws.sR = Np; base += (size_t)R * ws.sR * 8;
   ws.part = reinterpret_cast<double*>(base); ws.sPart = 2 * nb * 4;
@@ -86,7 +99,12 @@ __device__ __forceinline__ CholGroup cg_make(const GroupWs& ws, int rr, int N, i
 }
 __device__ __forceinline__ int cg_cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return (int)r; }
 
-__device__ __forceinline__ int cg_owner(int i, int j, int C) { return (i * (i + 1) / 2 + j) % C; }
+__device__ __forceinline__ int cg_owner(int i, int j, int C) { return (i * (i + 1) / 2 + j) & (C - 1); }   // C: power of two
+// Global layout of a restart's matrix: TILE-MAJOR.  Tile (i, j), j <= i, is the contiguous block number i(i+1)/2 + j, stored
+// as the shared-memory image [64][CG_LD] (padding included), so one bulk TMA copy moves a whole operand tile.
+__device__ __forceinline__ double* cg_tile_ptr(const CholGroup& g, int i, int j) {
+  return g.K + (size_t)(i * (i + 1) / 2 + j) * CG_TILE;
+}
 
 // ---- cross-CTA flags ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long cg_ld_acquire(const unsigned long long* p) {
@@ -119,53 +137,162 @@ __device__ __forceinline__ void cg_stage_tile(double* dst, const double* src, in
 }
 __device__ __forceinline__ void cg_stage_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-struct CgAcc { double v[4][4][2]; };
+// -DAPGP_PROF: thread 0 of the first restart's CTAs (ranks 0 and 1) accumulates SM cycles per phase into g_cgprof
+// (printed by launch_loglik_group when APGP_PROF_PRINT is set): 0 build, 1 diag load, 2 diag factor, 3 diag store +
+// publish, 4 deferred updates, 5 wait A, 6 panel, 7 publish + wait B, 8 urgent updates, 9 final, 10 total;
+// update pipeline: 11 wait + barrier, 12 next-tile search + staging issue + C fetch, 13 DMMA loop, 14 subtract + store;
+// (21 next-tile search, 22 TMA issue, then 12 = C fetch only)
+// panel: 15 staging wait (first slot also L_kk), 16 solve, 17 r update, 18 write-back; build: 19 staging, 20 entries
+#ifdef APGP_PROF_CG
+__device__ long long g_cgprof[2][24];
+#define CGP_T(var) long long var = clock64()
+#define CGP_ADD(slot, t0) do { if (threadIdx.x == 0 && blockIdx.x < 2) { const long long _n = clock64(); g_cgprof[blockIdx.x][slot] += _n - (t0); (t0) = _n; } } while (0)
+#else
+#define CGP_T(var) do {} while (0)
+#define CGP_ADD(slot, t0) do {} while (0)
+#endif
 
-// acc = As(64x64, [m][k]) * Bs(64x64, [n][k])^T ; warp (wm, wn) of the worker owns rows wm*32.., cols wn*32..
-__device__ __forceinline__ void cg_tile_mma(const double* As, const double* Bs, CgAcc& acc, int wm, int wn, int lane) {
+
+// Panel solve on the FP64 tensor pipe: X = P L^{-T} for one 64x64 panel tile P (shared, row-major, leading dimension
+// CG_LD, overwritten by X), L the factored diagonal block (shared, same layout), inv the 8 inverted 8x8 diagonal blocks
+// of L ([J][n][k], computed once by the block's owner).  Blocked by 8 columns, as a warp-private chain per 8 rows:
+//   X_J = (P_J - sum_{I<J} X_I L_JI^T) inv_J^T
+// the sum as one DMMA.8x8x4 chain over the finished columns (two accumulator pairs), the multiplication by the inverted
+// block as two more DMMAs after a quad shuffle from the accumulator layout to the A-operand layout.  A warp carries the
+// m8 blocks mb0 and mb0 + 4 side by side (two independent chains); rows never cross warps, so __syncwarp suffices.
+// The one-thread-per-row substitution this replaces (2016 dependent-ish FMAs per row, 64 registers of row, a fully
+// unrolled 60 KB instruction stream) measured 25 k cycles per round of tiles; this form is ~2 k.
+__device__ __forceinline__ void cg_trsm_dmma(double* Ps, const double* __restrict__ Ls,
+                                             const double* __restrict__ inv, int mb0, int lane) {
+  const int m = lane >> 2, q = lane & 3;
+  const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2;
+  const bool odd = q & 1;
+  double* pr[2] = {Ps + ((mb0)*8 + m) * CG_LD, Ps + ((mb0 + 4) * 8 + m) * CG_LD};
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int J = 0; J < CG_T / 8; ++J) {
+    const double* lr = Ls + (8 * J + m) * CG_LD + q;
+    double c[2][2][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { acc.v[i][j][0] = 0.0; acc.v[i][j][1] = 0.0; }
-  const double* ap = As + (wm * 32 + (lane >> 2)) * CG_LD + (lane & 3);
-  const double* bp = Bs + (wn * 32 + (lane >> 2)) * CG_LD + (lane & 3);
-#pragma unroll 4
-  for (int k4 = 0; k4 < CG_T / 4; ++k4) {
-    double a[4], b[4];
+    for (int h = 0; h < 2; ++h) { c[h][0][0] = c[h][0][1] = c[h][1][0] = c[h][1][1] = 0.0; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { a[i] = ap[i * 8 * CG_LD + k4 * 4]; b[i] = bp[i * 8 * CG_LD + k4 * 4]; }
+    for (int k4 = 0; k4 < 2 * J; ++k4) {
+      const double b = lr[4 * k4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int h = 0; h < 2; ++h) dmma884(c[h][k4 & 1][0], c[h][k4 & 1][1], pr[h][4 * k4 + q], b);
+    }
+    const double b_lo = inv[J * 64 + m * 8 + q], b_hi = inv[J * 64 + m * 8 + 4 + q];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+    for (int h = 0; h < 2; ++h) {
+      const double2 pv = *reinterpret_cast<const double2*>(pr[h] + 8 * J + 2 * q);
+      const double t0 = pv.x - (c[h][0][0] + c[h][1][0]), t1 = pv.y - (c[h][0][1] + c[h][1][1]);
+      const double u0 = __shfl_sync(0xffffffffu, t0, src0), u1 = __shfl_sync(0xffffffffu, t1, src0);
+      const double v0 = __shfl_sync(0xffffffffu, t0, src1), v1 = __shfl_sync(0xffffffffu, t1, src1);
+      const double a_lo = odd ? u1 : u0, a_hi = odd ? v1 : v0;
+      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+      dmma884(x0, x1, a_lo, b_lo);
+      dmma884(y0, y1, a_hi, b_hi);
+      double2 xv; xv.x = x0 + y0; xv.y = x1 + y1;
+      *reinterpret_cast<double2*>(pr[h] + 8 * J + 2 * q) = xv;
+    }
+    __syncwarp();
   }
 }
 
-// Panel solve by substitution: one thread owns one row of a 64x64 panel tile and overwrites it with
-//   x = a L^{-T}   (L: the factored diagonal block, row-major in shared memory with leading dimension CG_LD;
-//                   inv: reciprocal pivots 1 / L_cc)
-// in 8-wide column blocks, exactly the structure of chol_small.cuh: the contribution of the finished columns goes into 8
-// independent accumulators (no dependent chain), the 8x8 triangular remainder is solved in registers.  The row lives in
-// registers for the whole solve (64 doubles); L is read as warp-wide broadcasts.  ~2000 FMAs per row.
-__device__ __forceinline__ void cg_trsm_row(double (&x)[CG_T], const double* __restrict__ Ls, const double* __restrict__ inv) {
-#pragma unroll
-  for (int J = 0; J < CG_T / 8; ++J) {
-    double u[8];
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) u[cc] = x[8 * J + cc];
-#pragma unroll
-    for (int c2 = 0; c2 < 8 * J; ++c2) {
-      const double xv = x[c2];
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) u[cc] = fma(-xv, Ls[(8 * J + cc) * CG_LD + c2], u[cc]);
+// Trailing updates  C_ij -= L_i,kc L_j,kc^T  for this CTA's tiles of the block columns [j0, j1), as ONE software
+// pipeline run by all 8 warps.  Every operand arrives by bulk TMA (the global matrix is tile-major, so a tile is one
+// 34 KB copy issued by one lane, completion on an mbarrier): while the tensor pipe works on update t, the A tile of
+// update t + 1 -- and its B tile when the block column changes; A and B are double-buffered independently -- and the C
+// tile of update t land in shared memory; one CTA barrier per update.  Warp tile 32x16 (8 DMMA chains per warp, k
+// ascending: same bits as any other split of the tile).  History (cycles per update and CTA at N = 1024, against 4.1 k of
+// tensor-pipe time): two workers staging, multiplying and read-modify-writing in sequence 8.3 k; this pipeline with
+// per-thread cp.async staging 7.0 k (16 LDGSTS per thread block issue for 1.4 k); TMA with the C tile fetched into
+// registers by LDG 6.3 k (0.6 k of LDG issue back-pressure in every warp).
+__device__ __forceinline__ bool cg_next_tile(int& i, int& j, int j1, int nb, int C, int me) {
+  for (;;) {
+    if (++i >= nb) { ++j; i = j; }
+    if (j >= j1) return false;
+    if (cg_owner(i, j, C) == me) return true;
+  }
+}
+__device__ __forceinline__ void cg_update_phase(const CholGroup& g, double* sm, int kc, int j0, int j1) {
+  const int tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31;
+  const int wm = w8 >> 2, wn = w8 & 3;
+  const int nb = g.nb, C = g.C, me = g.rank;
+  if (j1 > nb) j1 = nb;
+  __shared__ __align__(8) uint64_t full[3];            // operand pairs 0 / 1, C tile
+  int i = j0 - 1, j = j0;
+  bool have = (j0 < j1) && cg_next_tile(i, j, j1, nb, C, me);
+  if (!have) return;                                   // uniform across the CTA
+  if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 1); mbar_fence_init(); }
+  fence_proxy_async();                                 // tiles written through the generic proxy (here, or by peers and
+  __syncthreads();                                     // already acquired) and the buffers' last contents -> bulk copies
+  double* const Cb = sm + 4 * CG_TILE;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&full[0], 2u * CG_TILE * 8u);
+    bulk_g2s(sm, cg_tile_ptr(g, i, kc), CG_TILE * 8, &full[0]);
+    bulk_g2s(sm + CG_TILE, cg_tile_ptr(g, j, kc), CG_TILE * 8, &full[0]);
+  }
+  int abuf = 0, bsel = 0;
+  uint32_t ph0 = 0, ph1 = 0, phc = 0;
+  CGP_T(t_u);
+  while (have) {
+    const int ci = i, cj = j;
+    if (abuf == 0) { mbar_wait(&full[0], ph0); ph0 ^= 1u; } else { mbar_wait(&full[1], ph1); ph1 ^= 1u; }
+    __syncthreads();                                   // everyone is done with update t - 1: its buffers are free
+    CGP_ADD(11, t_u);
+    have = cg_next_tile(i, j, j1, nb, C, me);
+    const bool newB = have && (j != cj);
+    double* Ct = cg_tile_ptr(g, ci, cj);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&full[2], CG_TILE * 8u);
+      bulk_g2s(Cb, Ct, CG_TILE * 8, &full[2]);
+      if (have) {
+        mbar_arrive_expect_tx(&full[abuf ^ 1], (newB ? 2u : 1u) * CG_TILE * 8u);
+        bulk_g2s(sm + (size_t)(abuf ^ 1) * 2 * CG_TILE, cg_tile_ptr(g, i, kc), CG_TILE * 8, &full[abuf ^ 1]);
+        if (newB) bulk_g2s(sm + (size_t)(bsel ^ 1) * 2 * CG_TILE + CG_TILE, cg_tile_ptr(g, j, kc), CG_TILE * 8, &full[abuf ^ 1]);
+      }
     }
+    CGP_ADD(12, t_u);
+    const double* As = sm + (size_t)abuf * 2 * CG_TILE;
+    const double* Bs = sm + (size_t)bsel * 2 * CG_TILE + CG_TILE;
+    double acc[4][2][2];
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      double v = u[cc];
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c3 = 0; c3 < cc; ++c3) v = fma(-x[8 * J + c3], Ls[(8 * J + cc) * CG_LD + 8 * J + c3], v);
-      x[8 * J + cc] = v * inv[8 * J + cc];
+      for (int b = 0; b < 2; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    const double* ap = As + (wm * 32 + (lane >> 2)) * CG_LD + (lane & 3);
+    const double* bp = Bs + (wn * 16 + (lane >> 2)) * CG_LD + (lane & 3);
+#pragma unroll 4
+    for (int k4 = 0; k4 < CG_T / 4; ++k4) {
+      double av[4], bv[2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = ap[a * 8 * CG_LD + k4 * 4];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) bv[b] = bp[b * 8 * CG_LD + k4 * 4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) dmma884(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
     }
+    CGP_ADD(13, t_u);
+    mbar_wait(&full[2], phc); phc ^= 1u;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int off = (wm * 32 + a * 8 + (lane >> 2)) * CG_LD + wn * 16 + b * 8 + 2 * (lane & 3);
+        double2 o = *reinterpret_cast<const double2*>(Cb + off);
+        o.x -= acc[a][b][0]; o.y -= acc[a][b][1];
+        *reinterpret_cast<double2*>(Ct + off) = o;
+      }
+    CGP_ADD(14, t_u);
+    abuf ^= 1;
+    if (newB) bsel ^= 1;
+  }
+  __syncthreads();
+  if (tid == 0) {                                      // every phase of the barriers has been waited for: hand the words back
+#pragma unroll
+    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" :: "r"(smem_u32(&full[b])) : "memory");
   }
 }
 
@@ -176,8 +303,7 @@ __device__ __forceinline__ void cg_trsm_row(double (&x)[CG_T], const double* __r
 template <bool FAST_PIVOT>
 __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, double* sm, unsigned long long epoch) {
   const int tid = threadIdx.x, w = tid >> 7, wtid = tid & 127, warp = (tid >> 5) & 3, lane = tid & 31;
-  const int wm = warp >> 1, wn = warp & 1;
-  const int nb = g.nb, Np = g.Np, C = g.C, me = g.rank, d = g.d;
+  const int nb = g.nb, C = g.C, me = g.rank, d = g.d;
   double* As = sm + (size_t)w * 2 * CG_TILE;
   double* Bs = As + CG_TILE;
   const unsigned long long baseA = epoch * (unsigned long long)(nb + 1);
@@ -185,45 +311,117 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
   double* part = g.part + (size_t)(epoch & 1ull) * nb * 4;
   const double mean = hyp[0], amp = hyp[1], noise = hyp[2];
   __shared__ int s_bad;
+  CGP_T(t_all);
+  CGP_T(t_ph);
 
   // ---- build: every CTA forms its own tiles; the owner of (i, 0) also initialises r_i = y_i - mean --------------
+  // K_ij = amp exp(-sum_c (xs_ic - xs_jc)^2) with the inputs pre-scaled by sqrt(1 / (2 M_c)) while they are staged and
+  // the table exponential of the predict kernels (<= 2 ulp): 2 d + 12 FP64 operations per entry.
+  double* etab = sm + CG_NTILES * CG_TILE + 2 * CG_AUX;     // [64] 2^(j/64)
+  double* scl = etab + 64;                          // [d]
+  if (tid < 64) etab[tid] = exp2((double)tid * (1.0 / 64.0));
+  else if (tid < 64 + d) scl[tid - 64] = sqrt(0.5 * hyp[3 + tid - 64]);
+  __syncthreads();
   {
-    int t = 0;
-    for (int i = 0; i < nb; ++i)
-      for (int j = 0; j <= i; ++j) {
-        if (cg_owner(i, j, C) != me) continue;
-        if ((t++ & 1) != w) continue;
-        // stage the two row blocks of X in the worker's buffers: rows i*64.. in As, rows j*64.. in Bs ([row][d])
-        for (int e = wtid; e < CG_T * d; e += CG_WT) {
-          const int rr = e / d, c = e - rr * d;
-          const int gi = i * CG_T + rr, gj = j * CG_T + rr;
-          As[e] = (gi < g.N) ? g.X[(size_t)gi * d + c] : 0.0;
-          Bs[e] = (gj < g.N) ? g.X[(size_t)gj * d + c] : 0.0;
-        }
-        named_bar_sync(1 + w, CG_WT);
-        double* Kt = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
-        for (int e = wtid; e < CG_T * CG_T; e += CG_WT) {
-          const int rr = e >> 6, cc = e & 63;
-          const int gi = i * CG_T + rr, gj = j * CG_T + cc;
-          double v;
-          if (gi < g.N && gj < g.N) {
-            double s = 0.0;
-            for (int c = 0; c < d; ++c) { const double df = As[rr * d + c] - Bs[cc * d + c]; s += df * df * hyp[3 + c]; }
-            v = amp * exp(-0.5 * s);
-            if (gi == gj) v += noise;
-          } else {
-            v = (gi == gj) ? 1.0 : 0.0;
+    // this worker's tiles in column-major order (the first block columns are needed first).  The raw inputs of the NEXT
+    // tile's row block travel in registers while the current tile is evaluated (staging them at the top of each tile cost
+    // 3.5 k cycles of exposed global-memory latency per tile)
+    int t = 0, staged_j = -1, i = -1, j = 0;
+    auto next_mine = [&]() -> bool {
+      for (;;) {
+        if (++i >= nb) { ++j; i = j; }
+        if (j >= nb) return false;
+        if (cg_owner(i, j, C) == me && (t++ & 1) == w) return true;
+      }
+    };
+    constexpr int NPRE = CG_T * APGP_MAXD / CG_WT;                 // 16 values per thread at d = 32
+    double pre[NPRE];
+    auto fetch = [&](int ib) {                                     // rows ib*64.. of X are one contiguous run of 64 d values
+      const int lim = min(CG_T, g.N - ib * CG_T) * d;
+#pragma unroll
+      for (int m = 0; m < NPRE; ++m) {
+        const int e = wtid + m * CG_WT;
+        pre[m] = (e < lim) ? g.X[(size_t)ib * CG_T * d + e] : 0.0;
+      }
+    };
+    bool have = next_mine();
+    if (have) fetch(i);
+    while (have) {
+      const int ci = i, cj = j;
+      {
+        CGP_T(t_b);
+        // both row blocks TRANSPOSED and pre-scaled: rows ci*64.. in As ([d][64]: a thread reads 16 consecutive rows of
+        // one dimension as 8 warp-wide LDS.128 broadcasts), rows cj*64.. in Bs ([d][64]: the 64 columns of the tile read
+        // conflict-free; kept while the worker stays in block column cj)
+        {
+          int rr = wtid / d, c = wtid - rr * d;
+          const int drr = CG_WT / d, dc = CG_WT - drr * d;
+#pragma unroll
+          for (int m = 0; m < NPRE; ++m) {
+            if (wtid + m * CG_WT < CG_T * d) As[c * CG_T + rr] = pre[m] * scl[c];
+            rr += drr; c += dc;
+            if (c >= d) { c -= d; ++rr; }
           }
-          Kt[(size_t)rr * Np + cc] = v;
         }
-        if (j == 0 && wtid < CG_T) {
-          const int gi = i * CG_T + wtid;
+        if (staged_j != cj) {
+          staged_j = cj;
+          for (int e = wtid; e < CG_T * d; e += CG_WT) {
+            const int c2 = e >> 6, r2 = e & 63;
+            const int gj = cj * CG_T + r2;
+            Bs[e] = (gj < g.N) ? g.X[(size_t)gj * d + c2] * scl[c2] : 0.0;
+          }
+        }
+        have = next_mine();
+        if (have) fetch(i);
+        named_bar_sync(1 + w, CG_WT);
+        CGP_ADD(19, t_b);
+        double* Kt = cg_tile_ptr(g, ci, cj);
+        {
+          // one column per thread, sixteen consecutive rows per pass: sixteen independent distance / exponential chains
+          // (the one-entry-per-pass loop with libdevice exp was bound by its own dependent latency: 27 k cycles per tile)
+          const int cc = wtid & 63, rh = wtid >> 6;
+          const int gj = cj * CG_T + cc;
+#pragma unroll 1
+          for (int pass = 0; pass < 2; ++pass) {
+            const int rbase = rh * 32 + pass * 16;
+            double s16[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s16[u] = 0.0;
+            for (int c = 0; c < d; ++c) {
+              const double bv = Bs[c * CG_T + cc];
+              const double2* ar = reinterpret_cast<const double2*>(As + c * CG_T + rbase);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const double2 av = ar[u];
+                const double d0 = av.x - bv, d1 = av.y - bv;
+                s16[2 * u] = fma(d0, d0, s16[2 * u]); s16[2 * u + 1] = fma(d1, d1, s16[2 * u + 1]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int rr = rbase + u, gi = ci * CG_T + rr;
+              double v;
+              if (gi < g.N && gj < g.N) {
+                v = amp * exp_neg(s16[u], etab);
+                if (gi == gj) v += noise;
+              } else {
+                v = (gi == gj) ? 1.0 : 0.0;
+              }
+              Kt[rr * CG_LD + cc] = v;
+            }
+          }
+        }
+        if (cj == 0 && wtid < CG_T) {
+          const int gi = ci * CG_T + wtid;
           g.r[gi] = (gi < g.N) ? (g.y[gi] - mean) : 0.0;
         }
         named_bar_sync(1 + w, CG_WT);
+        CGP_ADD(20, t_b);
       }
+    }
   }
   __syncthreads();
+  CGP_ADD(0, t_ph);
 
   for (int k = 0; k < nb; ++k) {
     // ---- (1) diagonal block k: factor, invert, z_k, partial sums -- by its owner, all 256 threads -------------------
@@ -231,24 +429,44 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
       double* S = sm;                                   // packed lower triangle
       double* R = S + CG_T * (CG_T + 1) / 2;            // [CG_DIAG_LDR]: r_k -> z_k
       double* dg = R + CG_DIAG_LDR;                     // [64] pivots
-      double* A = g.K + (size_t)k * CG_T * Np + (size_t)k * CG_T;
+      double* A = cg_tile_ptr(g, k, k);
       double* rk = g.r + k * CG_T;
       if (tid == 0) s_bad = 0;
       for (int e = tid; e < CG_T * CG_T; e += CG_THREADS) {
         const int i = e >> 6, j = e & 63;
-        if (j <= i) S[i * (i + 1) / 2 + j] = A[(size_t)i * Np + j];          // own tile: written by this CTA only
+        if (j <= i) S[i * (i + 1) / 2 + j] = A[i * CG_LD + j];          // own tile: written by this CTA only
       }
       if (tid < CG_T) R[tid] = __ldcg(rk + tid);                              // r_k was updated by other CTAs' panels
       __syncthreads();
+      CGP_ADD(1, t_ph);
       chol_packed_blocked<CG_THREADS, FAST_PIVOT>(S, R, dg, CG_T, &s_bad, true, 1, CG_DIAG_LDR);
-      // the factored block goes back row-major (the panel solves read it), its reciprocal pivots into the block's
-      // slot of Dinv -- no explicit inverse: the panels are solved by substitution (cg_trsm_row)
+      CGP_ADD(2, t_ph);
+      // the factored block goes back row-major (the panel solves read it); its reciprocal pivots and the inverses of
+      // its eight 8x8 diagonal blocks go into the block's slot of Dinv ([0, 64): 1 / L_cc; [64, 576): inv[J][n][k]) --
+      // the panel tiles are solved blockwise on the tensor pipe (cg_trsm_dmma), never through a full 64x64 inverse
       double* Dg = g.Dinv + (size_t)k * CG_T * CG_T;
       for (int e = tid; e < CG_T * CG_T; e += CG_THREADS) {
         const int i = e >> 6, j = e & 63;
-        A[(size_t)i * Np + j] = (j <= i) ? S[i * (i + 1) / 2 + j] : 0.0;
+        A[i * CG_LD + j] = (j <= i) ? S[i * (i + 1) / 2 + j] : 0.0;
       }
       if (tid < CG_T) { Dg[tid] = 1.0 / dg[tid]; rk[tid] = R[tid]; }
+      else if (tid < 2 * CG_T) {
+        // thread (J, col): column col of the inverse of diagonal block J by forward substitution (uniform trip counts:
+        // the entries above col are exact zeros)
+        const int J = (tid - CG_T) >> 3, col = tid & 7;
+        double x[8], rinv[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) rinv[rr] = 1.0 / dg[8 * J + rr];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int gr = 8 * J + rr;
+          double acc = (rr == col) ? 1.0 : 0.0;
+#pragma unroll
+          for (int mm = 0; mm < rr; ++mm) acc = fma(-S[gr * (gr + 1) / 2 + 8 * J + mm], x[mm], acc);
+          x[rr] = acc * rinv[rr];
+          Dg[CG_T + J * 64 + rr * 8 + col] = x[rr];
+        }
+      }
       if (tid < 32) {                                                          // block partials, fixed order
         double zz = R[tid] * R[tid] + R[tid + 32] * R[tid + 32];
         double lg = log(dg[tid]) + log(dg[tid + 32]);
@@ -257,100 +475,75 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
         if (tid == 0) { part[k * 4 + 0] = zz; part[k * 4 + 1] = lg; part[k * 4 + 2] = s_bad ? 1.0 : 0.0; }
       }
       if (C > 1) cg_publish_store(g.flagA, baseA + k + 1); else __syncthreads();
+      CGP_ADD(3, t_ph);
     }
     // ---- (2) deferred trailing work of step k-1 (columns >= k+1) overlaps the owner's pivot chain ------------------
     if (k > 0) {
-      int t = 0;
-      for (int j = k + 1; j < nb; ++j)
-        for (int i = j; i < nb; ++i) {
-          if (cg_owner(i, j, C) != me) continue;
-          if ((t++ & 1) != w) continue;
-          cg_stage_tile(As, g.K + (size_t)i * CG_T * Np + (size_t)(k - 1) * CG_T, Np, wtid);
-          cg_stage_tile(Bs, g.K + (size_t)j * CG_T * Np + (size_t)(k - 1) * CG_T, Np, wtid);
-          cg_stage_wait();
-          named_bar_sync(1 + w, CG_WT);
-          CgAcc acc;
-          cg_tile_mma(As, Bs, acc, wm, wn, lane);
-          double* Ct = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int rr = wm * 32 + a * 8 + (lane >> 2), cc = wn * 32 + b * 8 + 2 * (lane & 3);
-              double2* p = reinterpret_cast<double2*>(Ct + (size_t)rr * Np + cc);
-              double2 o = *p; o.x -= acc.v[a][b][0]; o.y -= acc.v[a][b][1]; *p = o;
-            }
-          named_bar_sync(1 + w, CG_WT);
-        }
-      __syncthreads();
+      cg_update_phase(g, sm, k - 1, k + 1, nb);
+      CGP_ADD(4, t_ph);
     }
     if (k == nb - 1) break;
-    // ---- (3) panel k: L_ik = A_ik L_kk^{-T} by substitution (one thread per row), r_i -= L_ik z_k --------------------
+    // ---- (3) panel k: L_ik = A_ik L_kk^{-T} on the tensor pipe (cg_trsm_dmma), r_i -= L_ik z_k ---------------------------
     if (C > 1) cg_wait_ge(g.flagA, baseA + k + 1);
+    CGP_ADD(5, t_ph);
     {
-      // every worker keeps its own copy of L_kk (row-major, ld CG_LD) in its first buffer; reciprocal pivots and z_k
-      // in its second
-      int mine = 0;
-      for (int i = k + 1; i < nb; ++i) mine += (cg_owner(i, k, C) == me);
+      // a worker keeps L_kk (row-major, ld CG_LD) in its first buffer and z_k + the inverted 8x8 diagonal blocks in its
+      // aux area; its panel tiles pass through its second buffer one at a time (cg_trsm_dmma: each of the 4 warps
+      // carries two m8 row blocks)
+      double* aux = sm + CG_NTILES * CG_TILE + w * CG_AUX;
+      int t = 0, mine = 0;
+      for (int i = k + 1; i < nb; ++i) if (cg_owner(i, k, C) == me) mine += ((t++ & 1) == w);
       if (mine > 0) {
-        cg_stage_tile(As, g.K + (size_t)k * CG_T * Np + (size_t)k * CG_T, Np, wtid);
-        if (wtid < CG_T) { Bs[wtid] = __ldcg(g.Dinv + (size_t)k * CG_T * CG_T + wtid); Bs[CG_T + wtid] = __ldcg(g.r + k * CG_T + wtid); }
-        cg_stage_wait();
-        named_bar_sync(1 + w, CG_WT);
-        // the worker's two halves (64 threads each) take alternate tiles of the CTA's share
-        const int half = wtid >> 6, row = wtid & 63;
-        int t = 0;
+        cg_stage_tile(As, cg_tile_ptr(g, k, k), CG_LD, wtid);
+        const double* Dg = g.Dinv + (size_t)k * CG_T * CG_T;
+        if (wtid < CG_T) aux[wtid] = __ldcg(g.r + k * CG_T + wtid);
+        for (int e = wtid; e < 8 * 64; e += CG_WT) aux[CG_T + e] = __ldcg(Dg + CG_T + e);
+        t = 0;
         for (int i = k + 1; i < nb; ++i) {
           if (cg_owner(i, k, C) != me) continue;
-          if ((t++ & 3) != 2 * w + half) continue;
-          double* Arow = g.K + (size_t)(i * CG_T + row) * Np + (size_t)k * CG_T;
-          double x[CG_T];
+          if ((t++ & 1) != w) continue;
+          double* At = cg_tile_ptr(g, i, k);
+          CGP_T(t_p);
+          cg_stage_tile(Bs, At, CG_LD, wtid);
+          cg_stage_wait();
+          named_bar_sync(1 + w, CG_WT);
+          CGP_ADD(15, t_p);
+          double rold[2] = {0.0, 0.0};                     // r_i of this warp's rows: in flight during the solve
+          if ((lane & 3) == 0) {
 #pragma unroll
-          for (int m = 0; m < CG_T / 2; ++m) {
-            const double2 v = __ldcg(reinterpret_cast<const double2*>(Arow) + m);
-            x[2 * m] = v.x; x[2 * m + 1] = v.y;
+            for (int h = 0; h < 2; ++h) rold[h] = __ldcg(g.r + i * CG_T + (warp + 4 * h) * 8 + (lane >> 2));
           }
-          cg_trsm_row(x, As, Bs);
-          double s0 = 0.0, s1 = 0.0;
+          cg_trsm_dmma(Bs, As, aux + CG_T, warp, lane);
+          CGP_ADD(16, t_p);
+          // r_i -= L_ik z_k: four lanes per row, 16 columns each, added in a fixed order
 #pragma unroll
-          for (int m = 0; m < CG_T / 2; ++m) {
-            double2 v; v.x = x[2 * m]; v.y = x[2 * m + 1];
-            reinterpret_cast<double2*>(Arow)[m] = v;
-            s0 = fma(v.x, Bs[CG_T + 2 * m], s0); s1 = fma(v.y, Bs[CG_T + 2 * m + 1], s1);
+          for (int h = 0; h < 2; ++h) {
+            const int row = (warp + 4 * h) * 8 + (lane >> 2), q = lane & 3;
+            const double* xr = Bs + row * CG_LD;
+            double s0 = 0.0;
+#pragma unroll
+            for (int m = 0; m < CG_T / 4; ++m) s0 = fma(xr[q + 4 * m], aux[q + 4 * m], s0);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            if (q == 0) g.r[i * CG_T + row] = rold[h] - s0;
           }
-          double* ri = g.r + i * CG_T + row;
-          *ri = __ldcg(ri) - (s0 + s1);
+          named_bar_sync(1 + w, CG_WT);
+          CGP_ADD(17, t_p);
+          for (int e = wtid; e < CG_T * (CG_T / 2); e += CG_WT) {           // L_ik back to global, coalesced
+            const int rr = e >> 5, c2 = (e & 31) * 2;
+            *reinterpret_cast<double2*>(At + rr * CG_LD + c2) = *reinterpret_cast<const double2*>(Bs + rr * CG_LD + c2);
+          }
+          named_bar_sync(1 + w, CG_WT);                    // the tile buffer is free again
+          CGP_ADD(18, t_p);
         }
-        named_bar_sync(1 + w, CG_WT);                      // the worker's buffers are free again
       }
     }
+    CGP_ADD(6, t_ph);
     if (C > 1) { cg_publish_add(g.cntB); cg_wait_ge(g.cntB, baseB + (unsigned long long)(k + 1) * C); } else __syncthreads();
+    CGP_ADD(7, t_ph);
     // ---- (4) urgent part of step k: column k+1 (the next diagonal block and the next panel's inputs) --------------
-    {
-      int t = 0;
-      const int j = k + 1;
-      for (int i = j; i < nb; ++i) {
-        if (cg_owner(i, j, C) != me) continue;
-        if ((t++ & 1) != w) continue;
-        cg_stage_tile(As, g.K + (size_t)i * CG_T * Np + (size_t)k * CG_T, Np, wtid);
-        cg_stage_tile(Bs, g.K + (size_t)j * CG_T * Np + (size_t)k * CG_T, Np, wtid);
-        cg_stage_wait();
-        named_bar_sync(1 + w, CG_WT);
-        CgAcc acc;
-        cg_tile_mma(As, Bs, acc, wm, wn, lane);
-        double* Ct = g.K + (size_t)i * CG_T * Np + (size_t)j * CG_T;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int rr = wm * 32 + a * 8 + (lane >> 2), cc = wn * 32 + b * 8 + 2 * (lane & 3);
-            double2* p = reinterpret_cast<double2*>(Ct + (size_t)rr * Np + cc);
-            double2 o = *p; o.x -= acc.v[a][b][0]; o.y -= acc.v[a][b][1]; *p = o;
-          }
-        named_bar_sync(1 + w, CG_WT);
-      }
-    }
-    __syncthreads();
+    cg_update_phase(g, sm, k, k + 1, k + 2);
+    CGP_ADD(8, t_ph);
   }
 
   // ---- log-likelihood: block partials in block order (identical bits in every CTA) -----------------------------------
@@ -360,6 +553,8 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
   double ll = -0.5 * zz - lg - 0.5 * g.N * 1.8378770664093454836;
   if (bad != 0.0 || !(ll == ll) || !(fabs(ll) < INFINITY)) ll = -INFINITY;
   __syncthreads();
+  CGP_ADD(9, t_ph);
+  CGP_ADD(10, t_all);
   return ll;
 }
 

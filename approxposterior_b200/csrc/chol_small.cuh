@@ -26,7 +26,7 @@ namespace apgp {
 constexpr int CHOL_B = 8;
 
 // -DAPGP_PROF: thread 0 accumulates SM cycles per phase into g_prof (tools/profile_optimizers.py --prof)
-#ifdef APGP_PROF
+#if defined(APGP_PROF) && !defined(APGP_PROF_CG)
 __device__ long long g_prof[16];
 #define PROF_T(var) long long var = clock64()
 #define PROF_ADD(slot, t0) do { if (threadIdx.x == 0) g_prof[slot] += clock64() - (t0); } while (0)

@@ -17,6 +17,7 @@
 #include "chol_group.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace apgp {
 namespace {
@@ -733,6 +734,20 @@ int launch_loglik_group(const double* X, const double* y, int N, int d, int Np, 
     (void)cudaGetLastError();                // the cluster could not be scheduled: halve it (C = 1 always can)
     C >>= 1;
   }
+#ifdef APGP_PROF_CG
+  if (getenv("APGP_PROF_PRINT")) {
+    cudaStreamSynchronize(st);
+    long long h[2][24];
+    cudaMemcpyFromSymbol(h, g_cgprof, sizeof(h));
+    for (int b = 0; b < 2; ++b) {
+      fprintf(stderr, "[cgprof] N=%d R=%d C=%d cta=%d cycles:", N, R, C, b);
+      for (int i = 0; i < 23; ++i) fprintf(stderr, " %lld", h[b][i]);
+      fprintf(stderr, "\n");
+    }
+    long long z[2][24] = {};
+    cudaMemcpyToSymbol(g_cgprof, z, sizeof(z));
+  }
+#endif
   return (int)ce;
 }
 

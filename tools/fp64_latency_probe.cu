@@ -17,6 +17,17 @@ template <int OP> __global__ void probe(double* out, long long* cyc, double seed
     else if (OP == 5) { __syncthreads(); x += 1e-9; }
     else if (OP == 6) x = log(x) + 3.0;
     else if (OP == 7) x = exp(-x) + 0.5;
+    else if (OP == 8) {        // one dependent DMMA.8x8x4 (accumulator chain)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(x), "+d"(y) : "d"(1e-9), "d"(1e-9));
+    } else if (OP == 9) {      // DMMA whose A operand is the previous DMMA's result (operand chain)
+      double c0 = 0.0, c1 = 0.0;
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(x), "d"(1e-9));
+      x = c0 + 1.0;
+    } else if (OP == 10) {     // DMMA -> 64-bit shuffle -> DMMA round (the panel solve's layout conversion)
+      double c0 = 0.0, c1 = 0.0;
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(x), "d"(1e-9));
+      x = __shfl_sync(0xffffffffu, c0, (threadIdx.x & 28) | ((threadIdx.x & 3) >> 1)) + 1.0;
+    }
   }
   long long t1 = clock64();
   out[threadIdx.x] = x;
@@ -25,10 +36,10 @@ template <int OP> __global__ void probe(double* out, long long* cyc, double seed
 int main() {
   double* out; long long* cyc;
   cudaMalloc(&out, 256 * 8); cudaMalloc(&cyc, 8);
-  const char* names[] = {"DFMA dependent", "rsqrt + DADD", "1/x + DADD", "sqrt + DADD", "STS+LDS round trip + DADD", "__syncthreads (256 thr) + DADD", "log + DADD", "exp + DADD"};
+  const char* names[] = {"DFMA dependent", "rsqrt + DADD", "1/x + DADD", "sqrt + DADD", "STS+LDS round trip + DADD", "__syncthreads (256 thr) + DADD", "log + DADD", "exp + DADD", "DMMA.8x8x4 accumulator chain", "DMMA -> DADD -> DMMA (operand chain)", "DMMA -> SHFL.64 -> DADD -> DMMA"};
   const int n = 4096;
   for (int threads : {32, 256}) {
-    for (int op = 0; op < 8; ++op) {
+    for (int op = 0; op < 11; ++op) {
       for (int rep = 0; rep < 2; ++rep) {
         switch (op) {
           case 0: probe<0><<<1, threads>>>(out, cyc, 1.3, n); break;
@@ -39,6 +50,9 @@ int main() {
           case 5: probe<5><<<1, threads>>>(out, cyc, 1.3, n); break;
           case 6: probe<6><<<1, threads>>>(out, cyc, 1.3, n); break;
           case 7: probe<7><<<1, threads>>>(out, cyc, 1.3, n); break;
+          case 8: probe<8><<<1, threads>>>(out, cyc, 1.3, n); break;
+          case 9: probe<9><<<1, threads>>>(out, cyc, 1.3, n); break;
+          case 10: probe<10><<<1, threads>>>(out, cyc, 1.3, n); break;
         }
         cudaDeviceSynchronize();
       }
