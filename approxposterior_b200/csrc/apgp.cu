@@ -536,7 +536,10 @@ int apgp_loglik_batch(apgp_handle* h, const double* P_host, int R, int P, int fi
   const bool force_tiled = getenv("APGP_LOGLIK_TILED") || (pathv && !strcmp(pathv, "tiled"));
   const bool force_group = pathv && !strcmp(pathv, "group");
   const bool small = loglik_small_smem(N, d) <= 220 * 1024 && !force_tiled && !force_group;
-  const bool group = !small && !force_tiled;
+  // a handful of large matrices: the multi-launch tiled sequence spreads each one over the whole GPU, a cluster is at most
+  // 16 SMs (measured, R = 1: N = 1024 0.51 ms fused vs 0.71 ms tiled, N = 2048 1.85 vs 1.48 ms; R = 8, N = 2048: 2.87 vs 2.73)
+  const bool few_large = Np >= 2048 && R <= 8 && !force_group;
+  const bool group = !small && !force_tiled && !few_large;
   if (grad_host && !small)
     return fail(APGP_ERR_ARG, "apgp_loglik_batch: batched gradients need the shared-memory path (N <= ~224); "
                               "use apgp_grad_log_likelihood per vector");

@@ -25,8 +25,9 @@
 //             the next tile's inputs travel in registers meanwhile;
 //   diagonal  all 256 threads (chol_small.cuh: 8-wide register-blocked, r_k riding along as a right-hand side so that
 //             z_k = L_kk^{-1} r_k comes out of the same pass); 64 threads then invert the eight 8x8 diagonal blocks;
-//   panel     two workers, one tile each: X = P L_kk^{-T} blockwise on the tensor pipe (cg_trsm_dmma: per 8 rows a
-//             warp-private chain of DMMA.8x8x4 against the finished columns, the inverted 8x8 block applied by two more);
+//   panel     all 8 warps on a pair of tiles (cg_panel_phase): X = P L_kk^{-T} blockwise on the tensor pipe (cg_trsm_dmma: per
+//             8 rows a warp-private chain of DMMA.8x8x4 against the finished columns, the inverted 8x8 block applied by two
+//             more), tile pairs fed by bulk TMA one pair ahead, rows written back by the warp that solved them;
 //   updates   all 8 warps as one TMA-fed software pipeline (cg_update_phase): A, B and C tiles by bulk copies one update
 //             ahead, warp tile 32x16, one CTA barrier per update; the DMMA loop itself runs at the tensor-pipe rate
 //             (4.1 k cycles per 64x64x64 update).
@@ -159,30 +160,34 @@ __device__ long long g_cgprof[2][24];
 //   X_J = (P_J - sum_{I<J} X_I L_JI^T) inv_J^T
 // the sum as one DMMA.8x8x4 chain over the finished columns (two accumulator pairs), the multiplication by the inverted
 // block as two more DMMAs after a quad shuffle from the accumulator layout to the A-operand layout.  A warp carries the
-// m8 blocks mb0 and mb0 + 4 side by side (two independent chains); rows never cross warps, so __syncwarp suffices.
+// row block mb (rows 8 mb .. 8 mb + 7) of H different tiles side by side as independent chains; rows never cross warps, so
+// __syncwarp suffices.
 // The one-thread-per-row substitution this replaces (2016 dependent-ish FMAs per row, 64 registers of row, a fully
 // unrolled 60 KB instruction stream) measured 25 k cycles per round of tiles; this form is ~2 k.
-__device__ __forceinline__ void cg_trsm_dmma(double* Ps, const double* __restrict__ Ls,
-                                             const double* __restrict__ inv, int mb0, int lane) {
+template <int H>
+__device__ __forceinline__ void cg_trsm_dmma(double* const (&tiles)[H], const double* __restrict__ Ls,
+                                             const double* __restrict__ inv, int mb, int lane) {
   const int m = lane >> 2, q = lane & 3;
   const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2;
   const bool odd = q & 1;
-  double* pr[2] = {Ps + ((mb0)*8 + m) * CG_LD, Ps + ((mb0 + 4) * 8 + m) * CG_LD};
+  double* pr[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) pr[h] = tiles[h] + (mb * 8 + m) * CG_LD;
 #pragma unroll
   for (int J = 0; J < CG_T / 8; ++J) {
     const double* lr = Ls + (8 * J + m) * CG_LD + q;
-    double c[2][2][2];
+    double c[H][2][2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) { c[h][0][0] = c[h][0][1] = c[h][1][0] = c[h][1][1] = 0.0; }
+    for (int h = 0; h < H; ++h) { c[h][0][0] = c[h][0][1] = c[h][1][0] = c[h][1][1] = 0.0; }
 #pragma unroll
     for (int k4 = 0; k4 < 2 * J; ++k4) {
       const double b = lr[4 * k4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) dmma884(c[h][k4 & 1][0], c[h][k4 & 1][1], pr[h][4 * k4 + q], b);
+      for (int h = 0; h < H; ++h) dmma884(c[h][k4 & 1][0], c[h][k4 & 1][1], pr[h][4 * k4 + q], b);
     }
     const double b_lo = inv[J * 64 + m * 8 + q], b_hi = inv[J * 64 + m * 8 + 4 + q];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < H; ++h) {
       const double2 pv = *reinterpret_cast<const double2*>(pr[h] + 8 * J + 2 * q);
       const double t0 = pv.x - (c[h][0][0] + c[h][1][0]), t1 = pv.y - (c[h][0][1] + c[h][1][1]);
       const double u0 = __shfl_sync(0xffffffffu, t0, src0), u1 = __shfl_sync(0xffffffffu, t1, src0);
@@ -206,7 +211,9 @@ __device__ __forceinline__ void cg_trsm_dmma(double* Ps, const double* __restric
 // ascending: same bits as any other split of the tile).  History (cycles per update and CTA at N = 1024, against 4.1 k of
 // tensor-pipe time): two workers staging, multiplying and read-modify-writing in sequence 8.3 k; this pipeline with
 // per-thread cp.async staging 7.0 k (16 LDGSTS per thread block issue for 1.4 k); TMA with the C tile fetched into
-// registers by LDG 6.3 k (0.6 k of LDG issue back-pressure in every warp).
+// registers by LDG 6.3 k (0.6 k of LDG issue back-pressure in every warp); C by TMA as well 6.0 k; the CTA barrier per
+// update replaced by an mbarrier only the issuing lane waits on 5.3 k (what is left: the two warps of a scheduler leave
+// their DMMA loops together, so their C subtract/store epilogues do not hide behind each other's tensor work).
 __device__ __forceinline__ bool cg_next_tile(int& i, int& j, int j1, int nb, int C, int me) {
   for (;;) {
     if (++i >= nb) { ++j; i = j; }
@@ -219,11 +226,11 @@ __device__ __forceinline__ void cg_update_phase(const CholGroup& g, double* sm, 
   const int wm = w8 >> 2, wn = w8 & 3;
   const int nb = g.nb, C = g.C, me = g.rank;
   if (j1 > nb) j1 = nb;
-  __shared__ __align__(8) uint64_t full[3];            // operand pairs 0 / 1, C tile
+  __shared__ __align__(8) uint64_t full[4];            // operand pairs 0 / 1, C tile; [3]: "update t - 1 finished" (8 warps)
   int i = j0 - 1, j = j0;
   bool have = (j0 < j1) && cg_next_tile(i, j, j1, nb, C, me);
   if (!have) return;                                   // uniform across the CTA
-  if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 1); mbar_fence_init(); }
+  if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 1); mbar_init(&full[3], 8); mbar_fence_init(); }
   fence_proxy_async();                                 // tiles written through the generic proxy (here, or by peers and
   __syncthreads();                                     // already acquired) and the buffers' last contents -> bulk copies
   double* const Cb = sm + 4 * CG_TILE;
@@ -234,16 +241,20 @@ __device__ __forceinline__ void cg_update_phase(const CholGroup& g, double* sm, 
   }
   int abuf = 0, bsel = 0;
   uint32_t ph0 = 0, ph1 = 0, phc = 0;
+  int t = 0;
   CGP_T(t_u);
   while (have) {
     const int ci = i, cj = j;
+    // No CTA barrier inside the pipeline: a warp only waits for its operands; the ISSUING lane alone waits until all 8
+    // warps have finished update t - 1 (whose buffers the copies below refill).  The duty rotates over the warps: a bulk
+    // copy holds its issuing lane for a few hundred cycles, which the warp makes up while its neighbours issue.
     if (abuf == 0) { mbar_wait(&full[0], ph0); ph0 ^= 1u; } else { mbar_wait(&full[1], ph1); ph1 ^= 1u; }
-    __syncthreads();                                   // everyone is done with update t - 1: its buffers are free
     CGP_ADD(11, t_u);
     have = cg_next_tile(i, j, j1, nb, C, me);
     const bool newB = have && (j != cj);
     double* Ct = cg_tile_ptr(g, ci, cj);
-    if (tid == 0) {
+    if (lane == 0 && w8 == (t & 7)) {
+      if (t > 0) mbar_wait(&full[3], (uint32_t)(t - 1) & 1u);
       mbar_arrive_expect_tx(&full[2], CG_TILE * 8u);
       bulk_g2s(Cb, Ct, CG_TILE * 8, &full[2]);
       if (have) {
@@ -286,13 +297,115 @@ __device__ __forceinline__ void cg_update_phase(const CholGroup& g, double* sm, 
         *reinterpret_cast<double2*>(Ct + off) = o;
       }
     CGP_ADD(14, t_u);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[3]);
+    ++t;
     abuf ^= 1;
     if (newB) bsel ^= 1;
   }
   __syncthreads();
   if (tid == 0) {                                      // every phase of the barriers has been waited for: hand the words back
 #pragma unroll
-    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" :: "r"(smem_u32(&full[b])) : "memory");
+    for (int b = 0; b < 4; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" :: "r"(smem_u32(&full[b])) : "memory");
+  }
+}
+
+// Panel k: this CTA's tiles (i, k), i > k:  L_ik = A_ik L_kk^{-T},  r_i -= L_ik z_k.  All 8 warps work on a PAIR of tiles
+// at a time (warp w owns rows 8w .. 8w+7 of both: the solve is a warp-private dependent chain of ~4 k cycles, so two
+// independent chains per warp and eight warps side by side finish two tiles in little more than the latency of one), the
+// pairs pass through two buffer pairs fed by bulk TMA one pair ahead, and every warp writes its own rows back as soon as
+// they are solved; one CTA barrier per pair.  History (cycles per tile at N = 1024): two workers of four warps, a tile each,
+// staged by cp.async and written back after a worker barrier 7.0 k (staging 2.4 k + solve 6.7 k + r update 1.9 k +
+// write-back 1.4 k per round of two tiles, in sequence); one tile at a time on 8 warps with TMA prefetch 6.7 k.
+template <int H>
+__device__ __forceinline__ void cg_panel_tiles(const CholGroup& g, double* const (&Ts)[H], const int (&ti)[H], const double* Lk,
+                                               const double* aux, int k, int w8, int lane) {
+  const int row = w8 * 8 + (lane >> 2), q = lane & 3;
+  double rold[H];                                      // r_i of this lane's rows: in flight during the solve
+#pragma unroll
+  for (int h = 0; h < H; ++h) rold[h] = (q == 0) ? __ldcg(g.r + ti[h] * CG_T + row) : 0.0;
+  cg_trsm_dmma<H>(Ts, Lk, aux + CG_T, w8, lane);
+  fence_proxy_async();                                 // the solved rows (st.shared) before a later bulk copy refills the buffer
+#pragma unroll
+  for (int h = 0; h < H; ++h) {                        // r_i -= L_ik z_k: four lanes per row, 16 columns each, fixed order
+    const double* xr = Ts[h] + row * CG_LD;
+    double s0 = 0.0;
+#pragma unroll
+    for (int m = 0; m < CG_T / 4; ++m) s0 = fma(xr[q + 4 * m], aux[q + 4 * m], s0);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    if (q == 0) g.r[ti[h] * CG_T + row] = rold[h] - s0;
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h) {                        // the warp's 8 rows of L_ik back to global (512 B per row)
+    double* At = cg_tile_ptr(g, ti[h], k);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int off = (w8 * 8 + rr) * CG_LD + 2 * lane;
+      *reinterpret_cast<double2*>(At + off) = *reinterpret_cast<const double2*>(Ts[h] + off);
+    }
+  }
+}
+__device__ __forceinline__ void cg_panel_phase(const CholGroup& g, double* sm, int k) {
+  const int tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31;
+  const int nb = g.nb, C = g.C, me = g.rank;
+  int i = k;
+  auto next_mine = [&]() -> int { while (++i < nb) if (cg_owner(i, k, C) == me) return i; return -1; };
+  int ia = next_mine();
+  if (ia < 0) return;                                  // uniform across the CTA
+  int ib = next_mine();
+  __shared__ __align__(8) uint64_t pfull[3];           // L_kk, tile pairs 0 / 1
+  double* const Lk = sm;
+  double* const aux = sm + CG_NTILES * CG_TILE;        // z_k [64], inverted 8x8 diagonal blocks [8][8][8]
+  if (tid == 0) { mbar_init(&pfull[0], 1); mbar_init(&pfull[1], 1); mbar_init(&pfull[2], 1); mbar_fence_init(); }
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&pfull[0], CG_TILE * 8u);
+    bulk_g2s(Lk, cg_tile_ptr(g, k, k), CG_TILE * 8, &pfull[0]);
+    mbar_arrive_expect_tx(&pfull[1], (ib >= 0 ? 2u : 1u) * CG_TILE * 8u);
+    bulk_g2s(sm + CG_TILE, cg_tile_ptr(g, ia, k), CG_TILE * 8, &pfull[1]);
+    if (ib >= 0) bulk_g2s(sm + 2 * CG_TILE, cg_tile_ptr(g, ib, k), CG_TILE * 8, &pfull[1]);
+  }
+  {
+    const double* Dg = g.Dinv + (size_t)k * CG_T * CG_T;
+    if (tid < CG_T) aux[tid] = __ldcg(g.r + k * CG_T + tid);
+    for (int e = tid; e < 8 * 64; e += CG_THREADS) aux[CG_T + e] = __ldcg(Dg + CG_T + e);
+  }
+  mbar_wait(&pfull[0], 0u);
+  int buf = 0;
+  uint32_t ph[2] = {0u, 0u};
+  CGP_T(t_p);
+  while (ia >= 0) {
+    const int ca = ia, cb = ib;
+    double* const T0 = sm + (size_t)(1 + 2 * buf) * CG_TILE;
+    if (buf == 0) { mbar_wait(&pfull[1], ph[0]); ph[0] ^= 1u; } else { mbar_wait(&pfull[2], ph[1]); ph[1] ^= 1u; }
+    __syncthreads();                                   // aux staged (first trip); everyone is done with the previous pair
+    ia = (cb >= 0) ? next_mine() : -1;
+    ib = (ia >= 0) ? next_mine() : -1;
+    if (ia >= 0 && tid == 0) {
+      double* const N0 = sm + (size_t)(1 + 2 * (buf ^ 1)) * CG_TILE;
+      mbar_arrive_expect_tx(&pfull[1 + (buf ^ 1)], (ib >= 0 ? 2u : 1u) * CG_TILE * 8u);
+      bulk_g2s(N0, cg_tile_ptr(g, ia, k), CG_TILE * 8, &pfull[1 + (buf ^ 1)]);
+      if (ib >= 0) bulk_g2s(N0 + CG_TILE, cg_tile_ptr(g, ib, k), CG_TILE * 8, &pfull[1 + (buf ^ 1)]);
+    }
+    CGP_ADD(15, t_p);
+    if (cb >= 0) {
+      double* const Ts[2] = {T0, T0 + CG_TILE};
+      const int ti[2] = {ca, cb};
+      cg_panel_tiles<2>(g, Ts, ti, Lk, aux, k, w8, lane);
+    } else {
+      double* const Ts[1] = {T0};
+      const int ti[1] = {ca};
+      cg_panel_tiles<1>(g, Ts, ti, Lk, aux, k, w8, lane);
+    }
+    CGP_ADD(16, t_p);
+    buf ^= 1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" :: "r"(smem_u32(&pfull[b])) : "memory");
   }
 }
 
@@ -302,7 +415,7 @@ __device__ __forceinline__ void cg_update_phase(const CholGroup& g, double* sm, 
 // or not finite) to every thread of every CTA of the cluster.  Ends with a CTA barrier.
 template <bool FAST_PIVOT>
 __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, double* sm, unsigned long long epoch) {
-  const int tid = threadIdx.x, w = tid >> 7, wtid = tid & 127, warp = (tid >> 5) & 3, lane = tid & 31;
+  const int tid = threadIdx.x, w = tid >> 7, wtid = tid & 127;
   const int nb = g.nb, C = g.C, me = g.rank, d = g.d;
   double* As = sm + (size_t)w * 2 * CG_TILE;
   double* Bs = As + CG_TILE;
@@ -486,58 +599,7 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
     // ---- (3) panel k: L_ik = A_ik L_kk^{-T} on the tensor pipe (cg_trsm_dmma), r_i -= L_ik z_k ---------------------------
     if (C > 1) cg_wait_ge(g.flagA, baseA + k + 1);
     CGP_ADD(5, t_ph);
-    {
-      // a worker keeps L_kk (row-major, ld CG_LD) in its first buffer and z_k + the inverted 8x8 diagonal blocks in its
-      // aux area; its panel tiles pass through its second buffer one at a time (cg_trsm_dmma: each of the 4 warps
-      // carries two m8 row blocks)
-      double* aux = sm + CG_NTILES * CG_TILE + w * CG_AUX;
-      int t = 0, mine = 0;
-      for (int i = k + 1; i < nb; ++i) if (cg_owner(i, k, C) == me) mine += ((t++ & 1) == w);
-      if (mine > 0) {
-        cg_stage_tile(As, cg_tile_ptr(g, k, k), CG_LD, wtid);
-        const double* Dg = g.Dinv + (size_t)k * CG_T * CG_T;
-        if (wtid < CG_T) aux[wtid] = __ldcg(g.r + k * CG_T + wtid);
-        for (int e = wtid; e < 8 * 64; e += CG_WT) aux[CG_T + e] = __ldcg(Dg + CG_T + e);
-        t = 0;
-        for (int i = k + 1; i < nb; ++i) {
-          if (cg_owner(i, k, C) != me) continue;
-          if ((t++ & 1) != w) continue;
-          double* At = cg_tile_ptr(g, i, k);
-          CGP_T(t_p);
-          cg_stage_tile(Bs, At, CG_LD, wtid);
-          cg_stage_wait();
-          named_bar_sync(1 + w, CG_WT);
-          CGP_ADD(15, t_p);
-          double rold[2] = {0.0, 0.0};                     // r_i of this warp's rows: in flight during the solve
-          if ((lane & 3) == 0) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) rold[h] = __ldcg(g.r + i * CG_T + (warp + 4 * h) * 8 + (lane >> 2));
-          }
-          cg_trsm_dmma(Bs, As, aux + CG_T, warp, lane);
-          CGP_ADD(16, t_p);
-          // r_i -= L_ik z_k: four lanes per row, 16 columns each, added in a fixed order
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int row = (warp + 4 * h) * 8 + (lane >> 2), q = lane & 3;
-            const double* xr = Bs + row * CG_LD;
-            double s0 = 0.0;
-#pragma unroll
-            for (int m = 0; m < CG_T / 4; ++m) s0 = fma(xr[q + 4 * m], aux[q + 4 * m], s0);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-            if (q == 0) g.r[i * CG_T + row] = rold[h] - s0;
-          }
-          named_bar_sync(1 + w, CG_WT);
-          CGP_ADD(17, t_p);
-          for (int e = wtid; e < CG_T * (CG_T / 2); e += CG_WT) {           // L_ik back to global, coalesced
-            const int rr = e >> 5, c2 = (e & 31) * 2;
-            *reinterpret_cast<double2*>(At + rr * CG_LD + c2) = *reinterpret_cast<const double2*>(Bs + rr * CG_LD + c2);
-          }
-          named_bar_sync(1 + w, CG_WT);                    // the tile buffer is free again
-          CGP_ADD(18, t_p);
-        }
-      }
-    }
+    cg_panel_phase(g, sm, k);
     CGP_ADD(6, t_ph);
     if (C > 1) { cg_publish_add(g.cntB); cg_wait_ge(g.cntB, baseB + (unsigned long long)(k + 1) * C); } else __syncthreads();
     CGP_ADD(7, t_ph);
