@@ -590,19 +590,31 @@ __device__ double chol_group_loglik(const CholGroup& g, const double* hyp, doubl
       if (C > 1) cg_publish_store(g.flagA, baseA + k + 1); else __syncthreads();
       CGP_ADD(3, t_ph);
     }
-    // ---- (2) deferred trailing work of step k-1 (columns >= k+1) overlaps the owner's pivot chain ------------------
-    if (k > 0) {
-      cg_update_phase(g, sm, k - 1, k + 1, nb);
+    // ---- (2) deferred trailing work of step k-1 (columns >= k+1) and (3) panel k: L_ik = A_ik L_kk^{-T} on the tensor pipe,
+    //      r_i -= L_ik z_k.  They touch different tiles, so their order is free: the CTA that has just factored block k
+    //      solves its panel tiles FIRST (the rest of the cluster needs them to pass flag B) and catches up on the deferred
+    //      work afterwards; everyone else does the deferred work under the owner's pivot chain and the panel after flag A.
+    if (C > 1 && k < nb - 1 && cg_owner(k, k, C) == me) {
+      cg_panel_phase(g, sm, k);
+      CGP_ADD(6, t_ph);
+      cg_publish_add(g.cntB);
+      if (k > 0) cg_update_phase(g, sm, k - 1, k + 1, nb);
       CGP_ADD(4, t_ph);
+      cg_wait_ge(g.cntB, baseB + (unsigned long long)(k + 1) * C);
+      CGP_ADD(7, t_ph);
+    } else {
+      if (k > 0) {
+        cg_update_phase(g, sm, k - 1, k + 1, nb);
+        CGP_ADD(4, t_ph);
+      }
+      if (k == nb - 1) break;
+      if (C > 1) cg_wait_ge(g.flagA, baseA + k + 1);
+      CGP_ADD(5, t_ph);
+      cg_panel_phase(g, sm, k);
+      CGP_ADD(6, t_ph);
+      if (C > 1) { cg_publish_add(g.cntB); cg_wait_ge(g.cntB, baseB + (unsigned long long)(k + 1) * C); } else __syncthreads();
+      CGP_ADD(7, t_ph);
     }
-    if (k == nb - 1) break;
-    // ---- (3) panel k: L_ik = A_ik L_kk^{-T} on the tensor pipe (cg_trsm_dmma), r_i -= L_ik z_k ---------------------------
-    if (C > 1) cg_wait_ge(g.flagA, baseA + k + 1);
-    CGP_ADD(5, t_ph);
-    cg_panel_phase(g, sm, k);
-    CGP_ADD(6, t_ph);
-    if (C > 1) { cg_publish_add(g.cntB); cg_wait_ge(g.cntB, baseB + (unsigned long long)(k + 1) * C); } else __syncthreads();
-    CGP_ADD(7, t_ph);
     // ---- (4) urgent part of step k: column k+1 (the next diagonal block and the next panel's inputs) --------------
     cg_update_phase(g, sm, k, k + 1, k + 2);
     CGP_ADD(8, t_ph);
