@@ -78,6 +78,43 @@ __device__ __forceinline__ void chol_update_dmma(double* __restrict__ K, double*
   }
 }
 
+// The 8x8 diagonal block in registers: D (lower triangle) -> L, inv = 1 / pivots, and ONE row x solved against the block
+// on the way (x[c] = (x[c] - sum_{c2<c} x[c2] L[c][c2]) / L[c][c], as soon as pivot c is known: the factorisation is a
+// dependent chain that leaves most issue slots empty).  The chain is  pivot -> scale L[c+1][c] -> update D[c+1][c+1] ->
+// next pivot: those two operations are issued FIRST after every pivot, and a pivot that is not positive and finite is
+// only recorded (bad = 1-based index of the first one), not replaced, so no compare/select sits on the chain either --
+// the NaNs stay inside a factorisation that is reported as failed.  Measured (tools/fp64_latency_probe.cu, one warp):
+// 1277 cycles per block in program order with the select, 922 in this order, 1036 with the row solve riding along.
+// Every entry sees the same operations in the same order as before: results are bit-identical.
+template <bool FAST_PIVOT>
+__device__ __forceinline__ void chol_block8(double (&D)[CHOL_B][CHOL_B], double (&inv)[CHOL_B], double (&x)[CHOL_B],
+                                            int& bad, int J0) {
+#pragma unroll
+  for (int c = 0; c < CHOL_B; ++c) {
+    const double dj = D[c][c];
+    if (!(dj > 0.0 && dj < INFINITY) && !bad) bad = J0 + c + 1;
+    double iv, sq;
+    if (FAST_PIVOT) { iv = rsqrt(dj); sq = dj * iv; }
+    else { sq = sqrt(dj); iv = 1.0 / sq; }
+    inv[c] = iv;
+    D[c][c] = sq;
+    if (c + 1 < CHOL_B) {                                      // the next pivot's inputs first
+      D[c + 1][c] *= iv;
+      D[c + 1][c + 1] = fma(-D[c + 1][c], D[c + 1][c], D[c + 1][c + 1]);
+    }
+#pragma unroll
+    for (int c2 = c + 2; c2 < CHOL_B; ++c2) D[c2][c] *= iv;
+#pragma unroll
+    for (int c2 = c + 2; c2 < CHOL_B; ++c2)
+#pragma unroll
+      for (int c3 = c + 1; c3 <= c2; ++c3) D[c2][c3] = fma(-D[c2][c], D[c3][c], D[c2][c3]);
+    double v = x[c];
+#pragma unroll
+    for (int c2 = 0; c2 < c; ++c2) v = fma(-x[c2], D[c][c2], v);
+    x[c] = v * iv;
+  }
+}
+
 template <int NT, int BAR>
 __device__ __forceinline__ void chol_sync() {
   if (BAR == 0) __syncthreads();
@@ -103,47 +140,27 @@ __device__ __forceinline__ void chol_packed_blocked_classic(double* __restrict__
     double D[CHOL_B][CHOL_B];
     if (tid < nbelow + nrhs) {
       double inv[CHOL_B];
+      {
+        const double* Dr = K + J0 * (J0 + 1) / 2 + J0;          // row J0 + c of the block starts c (J0 + 1) + c (c - 1) / 2 further
 #pragma unroll
-      for (int c = 0; c < CHOL_B; ++c)
+        for (int c = 0; c < CHOL_B; ++c) {
 #pragma unroll
-        for (int c2 = 0; c2 <= c; ++c2)
-          D[c][c2] = (c < bw) ? K[(size_t)(J0 + c) * (J0 + c + 1) / 2 + J0 + c2] : ((c == c2) ? 1.0 : 0.0);
+          for (int c2 = 0; c2 <= c; ++c2) D[c][c2] = (c < bw) ? Dr[c2] : ((c == c2) ? 1.0 : 0.0);
+          Dr += J0 + c + 1;
+        }
+      }
       PROF_ADD(8, t_p2);
       PROF_T(t_f);
       int bad = 0;                                                // 1-based index of the first failing pivot
-#pragma unroll
-      for (int c = 0; c < CHOL_B; ++c) {
-        double dj = D[c][c];
-        if (!(dj > 0.0 && dj < INFINITY)) { if (!bad) bad = J0 + c + 1; dj = 1.0; }
-        double iv, sq;
-        if (FAST_PIVOT) { iv = rsqrt(dj); sq = dj * iv; }
-        else { sq = sqrt(dj); iv = 1.0 / sq; }
-        inv[c] = iv;
-        D[c][c] = sq;
-#pragma unroll
-        for (int c2 = c + 1; c2 < CHOL_B; ++c2) D[c2][c] *= iv;
-#pragma unroll
-        for (int c2 = c + 1; c2 < CHOL_B; ++c2)
-#pragma unroll
-          for (int c3 = c + 1; c3 <= c2; ++c3) D[c2][c3] = fma(-D[c2][c], D[c3][c], D[c2][c3]);
-      }
-      PROF_ADD(9, t_f);
-      PROF_T(t_r);
-      double* row = (tid < nbelow) ? K + (size_t)(J0 + bw + tid) * (J0 + bw + tid + 1) / 2 + J0
+      double* row = (tid < nbelow) ? K + (J0 + bw + tid) * (J0 + bw + tid + 1) / 2 + J0
                                    : r + (tid - nbelow) * ldr + J0;
       double x[CHOL_B];
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c) x[c] = (c < bw) ? row[c] : 0.0;
-#pragma unroll
-      for (int c = 0; c < CHOL_B; ++c) {
-        double v = x[c];
-#pragma unroll
-        for (int c2 = 0; c2 < c; ++c2) v = fma(-x[c2], D[c][c2], v);
-        x[c] = v * inv[c];
-      }
+      chol_block8<FAST_PIVOT>(D, inv, x, bad, J0);              // factor the block, solve this thread's row on the way
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c) if (c < bw) row[c] = x[c];
-      PROF_ADD(10, t_r);
+      PROF_ADD(9, t_f);
       if (tid == nbelow) {                                       // the first rhs-row thread also publishes the pivots
         if (bad && *badflag == 0) *badflag = bad;
 #pragma unroll
@@ -198,47 +215,27 @@ __device__ __forceinline__ void chol_packed_blocked_lookahead(double* __restrict
     if (ahead && tid >= rowT) update(J1, bw1, 0, J0, rowT, NT - rowT);
     if (tid < nbelow + nrhs) {
       double inv[CHOL_B];
+      {
+        const double* Dr = K + J0 * (J0 + 1) / 2 + J0;          // row J0 + c of the block starts c (J0 + 1) + c (c - 1) / 2 further
 #pragma unroll
-      for (int c = 0; c < CHOL_B; ++c)
+        for (int c = 0; c < CHOL_B; ++c) {
 #pragma unroll
-        for (int c2 = 0; c2 <= c; ++c2)
-          D[c][c2] = (c < bw) ? K[(size_t)(J0 + c) * (J0 + c + 1) / 2 + J0 + c2] : ((c == c2) ? 1.0 : 0.0);
+          for (int c2 = 0; c2 <= c; ++c2) D[c][c2] = (c < bw) ? Dr[c2] : ((c == c2) ? 1.0 : 0.0);
+          Dr += J0 + c + 1;
+        }
+      }
       PROF_ADD(8, t_p2);
       PROF_T(t_f);
       int bad = 0;                                                // 1-based index of the first failing pivot
-#pragma unroll
-      for (int c = 0; c < CHOL_B; ++c) {
-        double dj = D[c][c];
-        if (!(dj > 0.0 && dj < INFINITY)) { if (!bad) bad = J0 + c + 1; dj = 1.0; }
-        double iv, sq;
-        if (FAST_PIVOT) { iv = rsqrt(dj); sq = dj * iv; }
-        else { sq = sqrt(dj); iv = 1.0 / sq; }
-        inv[c] = iv;
-        D[c][c] = sq;
-#pragma unroll
-        for (int c2 = c + 1; c2 < CHOL_B; ++c2) D[c2][c] *= iv;
-#pragma unroll
-        for (int c2 = c + 1; c2 < CHOL_B; ++c2)
-#pragma unroll
-          for (int c3 = c + 1; c3 <= c2; ++c3) D[c2][c3] = fma(-D[c2][c], D[c3][c], D[c2][c3]);
-      }
-      PROF_ADD(9, t_f);
-      PROF_T(t_r);
-      double* row = (tid < nbelow) ? K + (size_t)(J0 + bw + tid) * (J0 + bw + tid + 1) / 2 + J0
+      double* row = (tid < nbelow) ? K + (J0 + bw + tid) * (J0 + bw + tid + 1) / 2 + J0
                                    : r + (tid - nbelow) * ldr + J0;
       double x[CHOL_B];
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c) x[c] = (c < bw) ? row[c] : 0.0;
-#pragma unroll
-      for (int c = 0; c < CHOL_B; ++c) {
-        double v = x[c];
-#pragma unroll
-        for (int c2 = 0; c2 < c; ++c2) v = fma(-x[c2], D[c][c2], v);
-        x[c] = v * inv[c];
-      }
+      chol_block8<FAST_PIVOT>(D, inv, x, bad, J0);              // factor the block, solve this thread's row on the way
 #pragma unroll
       for (int c = 0; c < CHOL_B; ++c) if (c < bw) row[c] = x[c];
-      PROF_ADD(10, t_r);
+      PROF_ADD(9, t_f);
       if (tid == nbelow) {                                       // the first rhs-row thread also publishes the pivots
         if (bad && *badflag == 0) *badflag = bad;
 #pragma unroll

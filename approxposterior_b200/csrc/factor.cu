@@ -423,7 +423,7 @@ __global__ void grad_finish_kernel(const double* __restrict__ part, int ntiles, 
 //      With grad_out != nullptr the CTA goes on to alpha = L^{-T} z, inverts L in place, forms K^{-1} pair by pair
 //      and reduces  dl/dp = 1/2 tr[(alpha alpha^T - K^{-1}) dK/dp]  (george.GP.grad_log_likelihood, gpUtils.py:110):
 //      grad_out[r] = [ sum(alpha), d/dlog_constant, d/dlog M_0 .. ]   (the host drops the amplitude slot if unused).
-__global__ void __launch_bounds__(256) loglik_small_kernel(const double* __restrict__ X, const double* __restrict__ y,
+__global__ void __launch_bounds__(256, 1) loglik_small_kernel(const double* __restrict__ X, const double* __restrict__ y,
                                                            int N, int d, const double* __restrict__ hyper,
                                                            double* __restrict__ ll_out, double* __restrict__ grad_out) {
   extern __shared__ __align__(16) double sm[];

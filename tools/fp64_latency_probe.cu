@@ -29,6 +29,51 @@ template <int OP> __global__ void probe(double* out, long long* cyc, double seed
       x = __shfl_sync(0xffffffffu, c0, (threadIdx.x & 28) | ((threadIdx.x & 3) >> 1)) + 1.0;
     }
   }
+  if (OP >= 11) {      // 8x8 register Cholesky with rsqrt pivots (the diagonal-block chain of chol_small.cuh); OP 12: + row solve
+    double D[8][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int c2 = 0; c2 <= c; ++c2) D[c][c2] = (c == c2) ? 9.0 + x : 0.5 + 0.01 * (c + c2);
+    t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+      double inv[8], xr[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) xr[c] = D[7][c] + 1.0;
+      int bad = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double dj = D[c][c];
+        if (OP <= 12) { if (!(dj > 0.0 && dj < INFINITY)) dj = 1.0; }
+        else if (!(dj > 0.0 && dj < INFINITY)) bad = c + 1;              // recorded, not substituted: off the chain
+        const double iv = rsqrt(dj), sq = dj * iv;
+        inv[c] = iv; D[c][c] = sq;
+        if (OP >= 13 && c + 1 < 8) {                                      // the next pivot's inputs first
+          D[c + 1][c] *= iv;
+          D[c + 1][c + 1] = fma(-D[c + 1][c], D[c + 1][c], D[c + 1][c + 1]);
+        }
+#pragma unroll
+        for (int c2 = c + 1 + (OP >= 13 ? 1 : 0); c2 < 8; ++c2) D[c2][c] *= iv;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+          for (int c3 = c + 1; c3 <= c2; ++c3)
+            if (!(OP >= 13 && c2 == c + 1 && c3 == c + 1)) D[c2][c3] = fma(-D[c2][c], D[c3][c], D[c2][c3]);
+        if (OP == 12 || OP == 14) {
+          double v = xr[c];
+#pragma unroll
+          for (int c2 = 0; c2 < c; ++c2) v = fma(-xr[c2], D[c][c2], v);
+          xr[c] = v * iv;
+        }
+      }
+      // feed the result back so the next factorisation depends on this one, and keep the matrix positive definite
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int c2 = 0; c2 <= c; ++c2) D[c][c2] = (c == c2) ? 9.0 + 1e-3 * D[c][c2] + ((OP == 12 || OP == 14) ? 1e-9 * xr[c] : 0.0) + (bad ? 1.0 : 0.0) : 0.5 + 1e-3 * D[c][c2];
+    }
+    x = D[7][7] + D[3][1];
+  }
   long long t1 = clock64();
   out[threadIdx.x] = x;
   if (threadIdx.x == 0) cyc[0] = t1 - t0;
@@ -36,10 +81,10 @@ template <int OP> __global__ void probe(double* out, long long* cyc, double seed
 int main() {
   double* out; long long* cyc;
   cudaMalloc(&out, 256 * 8); cudaMalloc(&cyc, 8);
-  const char* names[] = {"DFMA dependent", "rsqrt + DADD", "1/x + DADD", "sqrt + DADD", "STS+LDS round trip + DADD", "__syncthreads (256 thr) + DADD", "log + DADD", "exp + DADD", "DMMA.8x8x4 accumulator chain", "DMMA -> DADD -> DMMA (operand chain)", "DMMA -> SHFL.64 -> DADD -> DMMA"};
+  const char* names[] = {"DFMA dependent", "rsqrt + DADD", "1/x + DADD", "sqrt + DADD", "STS+LDS round trip + DADD", "__syncthreads (256 thr) + DADD", "log + DADD", "exp + DADD", "DMMA.8x8x4 accumulator chain", "DMMA -> DADD -> DMMA (operand chain)", "DMMA -> SHFL.64 -> DADD -> DMMA", "8x8 register Cholesky (rsqrt pivots)", "8x8 register Cholesky + one row solve", "8x8 Cholesky, next pivot first, no select", "8x8 Cholesky, next pivot first + row solve"};
   const int n = 4096;
   for (int threads : {32, 256}) {
-    for (int op = 0; op < 11; ++op) {
+    for (int op = 0; op < 15; ++op) {
       for (int rep = 0; rep < 2; ++rep) {
         switch (op) {
           case 0: probe<0><<<1, threads>>>(out, cyc, 1.3, n); break;
@@ -53,6 +98,10 @@ int main() {
           case 8: probe<8><<<1, threads>>>(out, cyc, 1.3, n); break;
           case 9: probe<9><<<1, threads>>>(out, cyc, 1.3, n); break;
           case 10: probe<10><<<1, threads>>>(out, cyc, 1.3, n); break;
+          case 11: probe<11><<<1, threads>>>(out, cyc, 1.3, n); break;
+          case 12: probe<12><<<1, threads>>>(out, cyc, 1.3, n); break;
+          case 13: probe<13><<<1, threads>>>(out, cyc, 1.3, n); break;
+          case 14: probe<14><<<1, threads>>>(out, cyc, 1.3, n); break;
         }
         cudaDeviceSynchronize();
       }
