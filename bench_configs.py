@@ -238,8 +238,8 @@ def run_cfg1(args, bench):
                            roofline={"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                                      "traffic": None, "kernel": "minimize_nll_kernel (device Powell, one CTA per restart, N=70)",
                                      "note": "latency-bound: 3 CTAs, each a serial chain of ~150-700 Cholesky evaluations; the "
-                                             "fraction of the FP64 peak is not the figure of merit here, the 18 us per "
-                                             "evaluation is (profiles/r01_optimizers.md)",
+                                             "fraction of the FP64 peak is not the figure of merit here, the 14 us per "
+                                             "evaluation is (profiles/r02_device_optimizers_profile_block8.jsonl)",
                                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"},
                            cpu_baseline=None if args.no_cpu else cfg1_reference(bounded=True)))
 
