@@ -13,9 +13,10 @@ methods, keyword names, defaults, cache files and (as long as no utility restart
     (``scanCandidates=``);
   * optGP's restarts (approx.py:222-225) share one batched Cholesky per optimiser round.
 
-Deviations from the reference, all deliberate and listed in DESIGN.md: emcee's HDF5 backend is
-replaced by an ``.npz`` chain cache (h5py is not available offline); ``bayesOpt(cache=True)`` no
-longer dies on the missing ``self.gpPar`` (approx.py:709-710).
+Deviations from the reference, all deliberate and listed in DESIGN.md: emcee's HDF5 chain files are
+written by the package's own minimal HDF5 writer (``hdf5min``, emcee's layout; h5py is not available
+offline) next to an ``.npz`` twin; ``bayesOpt(cache=True)`` no longer dies on the missing ``self.gpPar``
+(approx.py:709-710).
 """
 import time
 
@@ -307,7 +308,7 @@ class ApproxPosterior(object):
             engine = "device" if box is not None else "host-rng"
         backend = None
         if cache:
-            bname = str(runName) + ".npz"          # reference writes runName.h5 through emcee's HDFBackend
+            bname = str(runName) + ".h5"           # as the reference (approx.py:830); written by hdf5min, with an .npz twin
             self.backends.append(bname)
             backend = bname
         samplerKwargs["log_prob_fn"] = self._gpll_batch

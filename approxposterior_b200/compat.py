@@ -9,8 +9,8 @@ package (dflemin3/approxposterior v0.4) imports and runs on ``libapgp.so``:
   emcee           ``EnsembleSampler`` with emcee 3.0's constructor signature (scalar ``log_prob_fn(theta,
                   *args, **kwargs)`` returning ``lp`` or ``(lp, blob)``), ``run_mcmc`` / ``sample`` /
                   ``get_chain`` / ``get_log_prob`` / ``get_blobs`` / ``get_autocorr_time``,
-                  ``backends.HDFBackend(name).reset(nwalkers, ndim)`` (an ``.npz`` chain cache: h5py is not
-                  available offline), ``autocorr.integrated_time`` and ``__version__ = "3.0.2"`` --
+                  ``backends.HDFBackend(name).reset(nwalkers, ndim)`` (the chain is written to ``name`` in emcee's
+                  HDF5 layout by ``hdf5min``: h5py is not available offline), ``autocorr.integrated_time`` and ``__version__ = "3.0.2"`` --
                   approx.py:832-847, mcmcUtils.py:198, tests/test_Import.py.
 
 The sampler follows emcee 3.0.x's NumPy RNG flow draw for draw (``sampler.EnsembleSampler``'s "host-rng"
@@ -45,8 +45,9 @@ _OPTIONS = {"box_prior_sampler": False}
 
 class HDFBackend(object):
     """``emcee.backends.HDFBackend(filename)``: the reference only constructs it, calls ``reset`` and hands it
-    to the sampler (approx.py:832-839).  Chains are written as ``<filename minus .h5>.npz`` with emcee's array
-    names (chain, log_prob, blobs, accepted)."""
+    to the sampler (approx.py:832-839).  Chains are written to ``filename`` in emcee's HDF5 layout by
+    ``approxposterior_b200.hdf5min`` (group ``mcmc``: chain, log_prob, blobs, accepted + attributes) and to an
+    ``.npz`` twin with the same array names."""
 
     def __init__(self, filename, name="mcmc", read_only=False, **kwargs):
         self.filename = str(filename)

@@ -172,8 +172,16 @@ class EnsembleSampler(object):
             self._blobs = cat([self._blobs, blobs]); self.naccepted = self.naccepted + nacc
         self.iteration += int(nsteps)
         if self.backend is not None:
-            np.savez(str(self.backend), chain=_host(self._chain), log_prob=_host(self._logp), blobs=_host(self._blobs),
-                     accepted=self.naccepted)
+            # the reference's chain cache (approx.py:829-833: emcee.backends.HDFBackend(runName + ".h5")): the same
+            # group / dataset / attribute layout written by hdf5min (h5py is not installable here), plus an .npz twin
+            base = str(self.backend)
+            for ext in (".h5", ".npz"):
+                if base.endswith(ext):
+                    base = base[:-len(ext)]
+            chain_h, logp_h, blobs_h = _host(self._chain), _host(self._logp), _host(self._blobs)
+            np.savez(base + ".npz", chain=chain_h, log_prob=logp_h, blobs=blobs_h, accepted=self.naccepted)
+            from . import hdf5min
+            hdf5min.write_emcee_backend(base + ".h5", chain_h, logp_h, blobs=blobs_h, accepted=self.naccepted)
         return _State(_host(self._chain[-1]), _host(self._logp[-1]), _host(self._blobs[-1]))
 
     def sample(self, initial_state, iterations=1, **kwargs):

@@ -260,8 +260,14 @@ def test_approx_posterior_driver_on_oracle_gp(tmp_path):
     assert len(ap.marginalMeans) == 2
     chain = ap.sampler.get_chain()
     assert chain.shape == (300, 10, 2) and np.all(np.abs(chain) <= 5)
-    for f in ("apAPFModelCache.npz", "apAPGP.npz", "apAPTiming.npz", "apConvergenceCache.npz", "ap1.npz"):
+    for f in ("apAPFModelCache.npz", "apAPGP.npz", "apAPTiming.npz", "apConvergenceCache.npz", "ap1.npz", "ap0.h5", "ap1.h5"):
         assert (tmp_path / f).exists(), f
+    # the chain cache of the last iteration, in emcee's HDFBackend layout (reference approx.py:829-833)
+    from approxposterior_b200 import hdf5min
+    assert ap.backends == [str(tmp_path / "ap0.h5"), str(tmp_path / "ap1.h5")]
+    h5 = hdf5min.read_emcee_backend(str(tmp_path / "ap1.h5"))
+    assert np.array_equal(h5["chain"], chain) and np.array_equal(h5["log_prob"], ap.sampler.get_log_prob())
+    assert int(h5["attrs"]["iteration"]) == 300 and int(h5["attrs"]["nwalkers"]) == 10 and int(h5["attrs"]["ndim"]) == 2
     cache = np.load(tmp_path / "apAPFModelCache.npz")
     assert np.array_equal(cache["theta"], ap.theta) and np.array_equal(cache["y"], ap.y)
     # _gpll conventions (approx.py:167-188)

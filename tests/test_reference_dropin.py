@@ -213,6 +213,9 @@ def test_engine_shim_installs_and_serves_the_emcee_surface_on_cpu(tmp_path):
         for _ in s.sample(initial_state=np.random.randn(8, 2), iterations=30):
             pass
         assert s.get_chain().shape == (30, 8, 2) and (tmp_path / "chain.npz").exists()
+        from approxposterior_b200 import hdf5min                      # the file the reference asked for, emcee's layout
+        h5 = hdf5min.read_emcee_backend(str(tmp_path / "chain.h5"))
+        assert np.array_equal(h5["chain"], s.get_chain()) and int(h5["attrs"]["iteration"]) == 30
         with pytest.raises(NotImplementedError):
             for _ in s.sample(initial_state=np.random.randn(8, 2), iterations=3, thin_by=2):
                 pass
