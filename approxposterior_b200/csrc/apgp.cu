@@ -55,6 +55,7 @@ struct apgp_handle {
   int variant = 2;       // requested tiling: 2 = 256x64 (fastest measured, profiles/), 1 = 128x128, 0 = 64x256
   int variant_eff = 2;   // tiling the current factorisation was packed for
   int group = -1;        // CTAs per query tile in the variance kernel: 0 = one tile per CTA, -1 = automatic, G = fixed
+  bool predict_few = true;   // calls of at most PREDICT_FEW_MAX queries: one CTA per query (APGP_PREDICT_FEW=0: tiled kernels)
   bool has_training = false, has_hyper = false, factored = false;
   double mean = 0, amp = 1, white_noise = -12;
   double log_metric[APGP_MAX_DIM];
@@ -73,6 +74,7 @@ struct apgp_handle {
   DevBuf s_p0, s_chain, s_logp, s_blob, s_nacc, s_ri, s_rz, s_rr, s_rl;
   DevBuf o_in, o_x, o_f, o_stats;      // device optimiser staging
   DevBuf g_arrive, g_part, g_plan;     // grouped variance kernel: barrier counters, partial sums, work-split tables
+  DevBuf few_ws;                       // few-query predict: per-split partial sums, means, arrival counters
   int plan_Npad = -1, plan_G = -1, plan_d = -1;   // what g_plan currently holds
 };
 
@@ -120,6 +122,7 @@ int apgp_create(apgp_handle** out, int device) {
   if (v) { int vv = atoi(v); h->variant = (vv >= 0 && vv <= 2) ? vv : 2; }
   const char* gv = getenv("APGP_PREDICT_GROUP");
   if (gv) h->group = atoi(gv);
+  if (const char* fv = getenv("APGP_PREDICT_FEW")) h->predict_few = atoi(fv) != 0;
   *out = h;
   return APGP_OK;
 }
@@ -131,7 +134,7 @@ int apgp_destroy(apgp_handle* h) {
   DevBuf* bufs[] = {&h->X, &h->y, &h->K, &h->Dinv, &h->r, &h->Linv, &h->work, &h->scal, &h->info, &h->hyper, &h->Xs,
                     &h->alphaA, &h->alpha, &h->LinvF, &h->scratch, &h->qscale, &h->stage_in, &h->stage_out, &h->ap_k, &h->ap_l, &h->ap_u, &h->ap_x, &h->bK,
                     &h->bDinv, &h->br, &h->bscal, &h->binfo, &h->bhyper, &h->bll, &h->bgrad, &h->s_p0, &h->s_chain, &h->s_logp,
-                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->gws, &h->ac_part, &h->ac_f, &h->ac_stage, &h->c_hdr, &h->c_send, &h->c_recv};
+                    &h->s_blob, &h->s_nacc, &h->s_ri, &h->s_rz, &h->s_rr, &h->s_rl, &h->o_in, &h->o_x, &h->o_f, &h->o_stats, &h->g_arrive, &h->g_part, &h->g_plan, &h->few_ws, &h->gws, &h->ac_part, &h->ac_f, &h->ac_stage, &h->c_hdr, &h->c_send, &h->c_recv};
   for (DevBuf* b : bufs) b->release();
   if (h->comm) comm_destroy(h->comm);
   if (h->pin) cudaFreeHost(h->pin);
@@ -156,9 +159,10 @@ int apgp_reset(apgp_handle* h) {
   h->has_training = h->has_hyper = h->factored = false;
   h->mean = 0; h->amp = 1; h->white_noise = -12; h->logdet = 0; h->loglik = 0;
   h->plan_Npad = h->plan_G = h->plan_d = -1;
-  h->variant = 2; h->variant_eff = 2; h->group = -1;            // tuning knobs back to their defaults (as apgp_create)
+  h->variant = 2; h->variant_eff = 2; h->group = -1; h->predict_few = true;   // tuning knobs back to their defaults (as apgp_create)
   if (const char* v = getenv("APGP_PREDICT_VARIANT")) { int vv = atoi(v); h->variant = (vv >= 0 && vv <= 2) ? vv : 2; }
   if (const char* gv = getenv("APGP_PREDICT_GROUP")) h->group = atoi(gv);
+  if (const char* fv = getenv("APGP_PREDICT_FEW")) h->predict_few = atoi(fv) != 0;
   if (h->comm) { comm_destroy(h->comm); h->comm = nullptr; h->comm_rank = 0; h->comm_world = 1; }
   return APGP_OK;
 }
@@ -353,6 +357,15 @@ static void fill_predict_params(apgp_handle* h, PredictParams& p) {
 static int predict_launch(apgp_handle* h, PredictParams& p, int want_var, cudaStream_t st, int* nl, long long Qplan) {
   const int d = h->d;
   if (!want_var) { CUI(launch_predict_mean(p, h->num_sms, st, nl)); return APGP_OK; }
+  // a handful of queries in the whole call: one CTA per query (APGP_PREDICT_FEW=0 keeps them on the tiled kernels)
+  if (Qplan <= PREDICT_FEW_MAX && p.Q == Qplan && (size_t)h->N * 8 <= 96 * 1024 && h->predict_few) {
+    if (h->few_ws.cap < predict_few_ws_bytes()) {
+      CUI(h->few_ws.reserve(predict_few_ws_bytes()));
+      CU(cudaMemsetAsync(h->few_ws.p, 0, predict_few_ws_bytes(), st));
+    }
+    CUI(launch_predict_few(p, h->Linv.as<double>(), h->Np, h->few_ws.p, st, nl));
+    return APGP_OK;
+  }
   const int G = (h->group == 0) ? 1 : predict_group_size(h->Npad, h->num_sms, h->variant_eff, h->group, d, Qplan);
   if (G > 1) {
     CUI(h->scratch.reserve(predict_group_scratch_bytes(h->Npad, h->num_sms, G)));

@@ -50,6 +50,10 @@ int predict_variant_bn(int variant);   // block-row height BN of the LinvF tilin
 
 // returns cudaError_t as int; *launches incremented by the number of kernel launches issued
 int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int variant, int* launches);
+// at most PREDICT_FEW_MAX queries: one CTA per query against the explicit row-major inverse (pure latency path)
+constexpr long long PREDICT_FEW_MAX = 16;
+size_t predict_few_ws_bytes();
+int launch_predict_few(const PredictParams& p, const double* Linv, int ld, void* ws, cudaStream_t st, int* launches);
 int launch_exp_neg_test(const double* s, int n, double* out, cudaStream_t st, int variant = 0);
 int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, int* launches);
 size_t predict_scratch_bytes(int Npad, int num_sms, int variant);

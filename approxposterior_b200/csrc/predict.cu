@@ -657,6 +657,103 @@ predict_mean_kernel(const __grid_constant__ PredictParams p, int JCH) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// A HANDFUL of queries (the reference's own scalar loops call george.GP.predict(y, x.reshape(1, -1), return_var=True) once
+// per objective evaluation, utility.py:131,178,224; the lock-step optimiser rounds ask for a few points): S CTAs per query,
+// k* in shared memory, v = A L^-1 k* by one warp per pair of rows of the explicit row-major inverse (rows dealt round the
+// S x 8 warps so the triangle is balanced; 8 independent loads in flight per lane: the kernel is bound by the latency of
+// streaming L^-1 once from L2).  Per-CTA partial sums of |v|^2 meet in a small global buffer; the CTA that arrives last adds
+// them in split order (deterministic) and writes mean, variance and utility.  Pure latency path: the tiled DMMA kernels need
+// 0.5 ms (N = 2048) to 2.8 ms (N = 4096) to fill and drain their pipeline for one 256-query tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int FEW_THREADS = 256;
+constexpr int FEW_WARPS = FEW_THREADS / 32;
+constexpr int FEW_MAX_SPLIT = 32;
+__device__ __forceinline__ double few_row_dot(const double* __restrict__ Li, const double* __restrict__ E, int i, int lane) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = lane;
+  for (; j + 96 <= i; j += 128) {
+    s0 = fma(Li[j], E[j], s0); s1 = fma(Li[j + 32], E[j + 32], s1);
+    s2 = fma(Li[j + 64], E[j + 64], s2); s3 = fma(Li[j + 96], E[j + 96], s3);
+  }
+  for (; j <= i; j += 32) s0 = fma(Li[j], E[j], s0);
+  return (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(FEW_THREADS)
+predict_few_kernel(const __grid_constant__ PredictParams p, const double* __restrict__ Linv, int ld, int S,
+                   double* __restrict__ part /*[Q][S]*/, double* __restrict__ mu_ws /*[Q]*/, int* __restrict__ count /*[Q]*/) {
+  extern __shared__ __align__(16) double E[];          // [N] k* / A
+  __shared__ double red[FEW_WARPS];
+  __shared__ double qs[APGP_MAXD];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = p.d, N = p.N, Npad = p.Npad;
+  const int sp = blockIdx.x;
+  const long long q = blockIdx.y;
+  if (tid < d) qs[tid] = p.Xq[q * d + tid] * p.qscale[tid];
+  __syncthreads();
+  double mpart = 0.0;
+  for (int j = tid; j < N; j += FEW_THREADS) {
+    double s = 0.0;
+    for (int i = 0; i < d; ++i) { const double t = p.Xs[(size_t)i * Npad + j] - qs[i]; s = fma(t, t, s); }
+    const double e = exp(-s);
+    E[j] = e;
+    if (sp == 0) mpart = fma(e, p.alphaA[j], mpart);
+  }
+  if (sp == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mpart += __shfl_xor_sync(0xffffffffu, mpart, o);
+    if (lane == 0) red[warp] = mpart;
+  }
+  __syncthreads();                                     // publishes E (and the mean partials)
+  if (sp == 0 && tid == 0) {
+    double mu = p.mean;
+#pragma unroll
+    for (int w = 0; w < FEW_WARPS; ++w) mu += red[w];
+    mu_ws[q] = mu;
+  }
+  double acc = 0.0;
+  const int stride = S * FEW_WARPS;
+  for (int i = sp * FEW_WARPS + warp; i < N; i += 2 * stride) {       // two rows per trip: independent load streams
+    const int i2 = i + stride;
+    double a = few_row_dot(Linv + (size_t)i * ld, E, i, lane);
+    double b = (i2 < N) ? few_row_dot(Linv + (size_t)i2 * ld, E, i2, lane) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    const double va = p.amp * a, vb = p.amp * b;
+    acc = fma(va, va, acc);                            // identical in all lanes of the warp
+    acc = fma(vb, vb, acc);
+  }
+  __syncthreads();                                     // red is free again
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < FEW_WARPS; ++w) tot += red[w];
+    part[q * S + sp] = tot;
+    __threadfence();
+    s_last = (atomicAdd(&count[q], 1) == S - 1);
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    __threadfence();
+    double tot = 0.0;
+    for (int k = 0; k < S; ++k) tot += __ldcg(part + q * S + k);
+    const double mu = __ldcg(mu_ws + q);
+    const double var = p.amp - tot;
+    count[q] = 0;                                      // re-armed for the next launch on this stream
+    if (p.mu) p.mu[q] = mu;
+    if (p.var) p.var[q] = var;
+    if (p.util) {
+      bool ok = true;
+      if (p.has_box)
+        for (int i = 0; i < d; ++i) { const double x = p.Xq[q * d + i]; ok = ok && (x >= p.lo[i]) && (x <= p.hi[i]); }
+      p.util[q] = ok ? utility_eval(p.utility_kind, mu, var, p.ybest, p.zeta) : INFINITY;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Packers (run once per factorisation)
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_linv_kernel(const double* __restrict__ Linv, int ld, int N, int Npad, int BN, double amp,
@@ -848,6 +945,28 @@ int launch_predict_var(const PredictParams& p, int num_sms, cudaStream_t st, int
   if (variant == 2) return launch_var_t<256, 64, 4>(p, num_sms, st);
   if (variant == 1) return launch_var_t<128, 128, 5>(p, num_sms, st);
   return launch_var_t<64, 256, 4>(p, num_sms, st);
+}
+
+size_t predict_few_ws_bytes() { return (size_t)PREDICT_FEW_MAX * (FEW_MAX_SPLIT + 1) * 8 + PREDICT_FEW_MAX * sizeof(int); }
+// ws: predict_few_ws_bytes() bytes, zeroed once when allocated (the kernel re-arms its counters itself)
+int launch_predict_few(const PredictParams& p, const double* Linv, int ld, void* ws, cudaStream_t st, int* launches) {
+  if (p.Q <= 0) return 0;
+  const size_t smem = (size_t)p.N * 8;
+  static PerDeviceOnce attr;
+  if (attr.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(predict_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr.mark();
+  }
+  int S = p.N / 64;                                    // ~8 rows per warp and split: N = 70 -> 1, 512 -> 8, >= 2048 -> 32
+  if (S < 1) S = 1;
+  if (S > FEW_MAX_SPLIT) S = FEW_MAX_SPLIT;
+  double* part = static_cast<double*>(ws);
+  double* mu_ws = part + PREDICT_FEW_MAX * FEW_MAX_SPLIT;
+  int* count = reinterpret_cast<int*>(mu_ws + PREDICT_FEW_MAX);
+  predict_few_kernel<<<dim3((unsigned)S, (unsigned)p.Q), FEW_THREADS, smem, st>>>(p, Linv, ld, S, part, mu_ws, count);
+  if (launches) ++*launches;
+  return (int)cudaGetLastError();
 }
 
 int launch_predict_mean(const PredictParams& p, int num_sms, cudaStream_t st, int* launches) {
