@@ -194,6 +194,12 @@ int apgp_set_group(apgp_handle* h, int group) {
   return APGP_OK;
 }
 
+int apgp_set_predict_few(apgp_handle* h, int enable) {
+  if (!h) return fail(APGP_ERR_ARG, "apgp_set_predict_few");
+  h->predict_few = enable != 0;
+  return APGP_OK;
+}
+
 int apgp_set_variant(apgp_handle* h, int variant) {
   if (!h || variant < 0 || variant > 2) return fail(APGP_ERR_ARG, "apgp_set_variant");
   h->variant = variant; h->factored = false;

@@ -132,6 +132,10 @@ class GP(object):
         with groups the K* panels in flight stay in L2 instead of streaming through HBM."""
         _lib.check(self._lib.apgp_set_group(self._h, int(group)), "apgp_set_group")
 
+    def set_predict_few(self, enable=True):
+        """Calls of at most 16 queries use the few-query kernel (default) or, with ``enable=False``, the tiled kernels."""
+        _lib.check(self._lib.apgp_set_predict_few(self._h, 1 if enable else 0), "apgp_set_predict_few")
+
     # ------------------------------------------------------------------ factorisation
     def _parse(self, t):
         t = np.asarray(t, dtype=np.float64)

@@ -222,6 +222,10 @@ int apgp_set_variant(apgp_handle* h, int variant);
  * through HBM): 0 = one tile per CTA, -1 = automatic (by training-set size, and by the number of query tiles of the
  * call: a few-tile call is spread over more CTAs for latency), 2..64 = fixed group size.  Default -1. */
 int apgp_set_group(apgp_handle* h, int group);
+/* predict calls of at most 16 queries (the reference asks for ONE point per call: utility.py:131,178,224) run a few-query
+ * kernel -- several CTAs per query against the explicit inverse -- instead of a 256-query tile of the DMMA kernels:
+ * enable != 0 (default) / 0 = always the tiled kernels.  Environment: APGP_PREDICT_FEW, read by apgp_create / apgp_reset. */
+int apgp_set_predict_few(apgp_handle* h, int enable);
 
 #ifdef __cplusplus
 }

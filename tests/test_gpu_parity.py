@@ -640,3 +640,40 @@ def test_sampler_training_set_partitioned_over_the_cluster(N, d, nw, nens, monke
     np.testing.assert_allclose(out["chain"], orc_run["chain"], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(out["log_prob"], orc_run["log_prob"], rtol=1e-9, atol=1e-9)
     assert np.array_equal(out["naccepted"], orc_run["naccepted"])
+
+
+@pytest.mark.parametrize("N,d,amp", [(70, 2, None), (300, 5, 2.5), (1100, 3, None), (2048, 5, 4.0)])
+def test_few_query_predict_kernel(N, d, amp):
+    """Calls of at most 16 queries (the reference's one-point-per-call loops, utility.py:131,178,224) run
+    predict_few_kernel -- several CTAs per query against the explicit inverse, partial sums added in split order --
+    instead of a 256-query DMMA tile: same mean / variance / utility as the oracle (1e-9) and as the tiled kernels."""
+    X, y, logM, _ = synthetic_gp_problem(N, d, seed=N + d)
+    gp, orc = make_pair(X, y, logM, amp=amp)
+    rng = np.random.default_rng(5)
+    A = amp if amp is not None else 1.0
+    bounds = [(-3.0, 3.0)] * d
+    for Q in (1, 7, 16):
+        q = rng.uniform(-2.5, 2.5, size=(Q, d))
+        q[-1] = X[3]                                          # a training input: variance ~ noise level
+        if Q > 1:
+            q[0, 0] = 3.5                                     # outside the box: utility +inf
+        outs = {}
+        for few in (True, False):
+            gp.set_predict_few(few)
+            n0 = gp.launch_count
+            outs[few] = [np.array(v) for v in gp.predict_utility(y, q, "bape", bounds=bounds)]
+            assert gp.launch_count == n0 + 1
+        gp.set_predict_few(True)
+        mu_o, var_o = orc.predict(y, q, return_var=True)
+        for mu, var, util in outs.values():
+            check_mean(mu, mu_o, orc, y, q)
+            assert np.all(np.abs(var - var_o) <= 1e-9 * A + 1e-9 * np.abs(var_o))
+        (mu1, var1, u1), (mu0, var0, u0) = outs[True], outs[False]
+        assert np.all(np.abs(mu1 - mu0) <= 1e-10 * np.abs(mu0) + 1e-10 * np.max(np.abs(y)))
+        assert np.all(np.abs(var1 - var0) <= 1e-10 * A)
+        assert np.array_equal(np.isinf(u1), np.isinf(u0)) and (Q == 1 or np.isposinf(u1[0]))
+    # repeated calls re-arm the arrival counters: identical bits
+    q = rng.uniform(-2.5, 2.5, size=(5, d))
+    a = [np.array(v) for v in gp.predict(y, q, return_var=True)]
+    b = [np.array(v) for v in gp.predict(y, q, return_var=True)]
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
