@@ -16,8 +16,15 @@ for N, d, amp in ((70, 2, None), (200, 3, 2.0), (300, 5, None)):
     gp.predict(y, q, return_cov=False, return_var=True)
     gp.predict(y, q, return_cov=False, return_var=False)
     gp.predict_utility(y, q, "jones", bounds=[(-5, 5)] * d)
+    gp.predict(y, q[:1], return_cov=False, return_var=True)          # few-query kernel (S CTAs per query, arrival counter)
+    gp.predict_utility(y, q[:7], "bape", bounds=[(-5, 5)] * d)
     P = np.vstack([gp.get_parameter_vector() + 0.1 * i for i in range(5)])
     gp.log_likelihood_batch(P, y)
+    if N > 224:                                                       # fused cluster log-likelihood at every cluster size
+        for C in ("1", "2", "4"):
+            os.environ["APGP_CHOL_CLUSTER"] = C
+            gp.log_likelihood_batch(P, y)
+        del os.environ["APGP_CHOL_CLUSTER"]
     gp.log_likelihood_batch(P, y, return_grad=(N <= 224))
     gp.grad_log_likelihood(y)
     gp.append_point(rng.uniform(-5, 5, size=d), 0.3)
