@@ -109,7 +109,23 @@ def test_two_handles_on_two_devices_in_one_process():
         xs, fs, _ = gp.minimize_utility(y, Xq[:4], "bape", bounds=bounds, options={"adaptive": True})   # optimisers
         ps, fn, _ = gp.minimize_nll(P, y, method="powell", options={"maxiter": 1})
         gl = gp.grad_log_likelihood(y)                                           # tiled GEMM path
-        outs.append((mu, var, u, m2, ch, ll, g, xs, fs, ps, fn, gl))
+        mf, vf = gp.predict(y, Xq[:3], return_cov=False, return_var=True)        # few-query kernel
+        tau, win = gp.integrated_time(ch)                                        # autocorrelation kernel
+        outs.append((mu, var, u, m2, ch, ll, g, xs, fs, ps, fn, gl, mf, vf, tau, win))
+    # the cluster kernels (N beyond one CTA's shared memory): log-likelihood batch and the cluster-cooperative optimiser
+    from approxposterior_b200 import GP, kernels
+    Xb = rng.uniform(-5, 5, size=(260, 3))
+    yb = -0.5 * np.sum(Xb * Xb, axis=1) / 4.0
+    big = []
+    for dev in (1, 0):
+        gp = GP(kernel=kernels.ExpSquaredKernel([3.0, 3.0, 3.0], ndim=3), fit_mean=True, mean=float(np.median(yb)),
+                white_noise=-12.0, device=dev)
+        gp.compute(Xb, y=yb)
+        P = np.array([gp.get_parameter_vector(), gp.get_parameter_vector() + 0.2, gp.get_parameter_vector() - 0.1])
+        llb = gp.log_likelihood_batch(P, yb)
+        ps, fn, _ = gp.minimize_nll(P[:2], yb, method="powell", options={"maxiter": 1})
+        big.append((llb, ps, fn))
+    outs = [o + b for o, b in zip(outs, big)]
     for k, (a, b) in enumerate(zip(*outs)):
         assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
 
