@@ -678,17 +678,65 @@ int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* o, const double* p
     p.p0 = p0; p.chain = chain; p.logp = logp; p.blob = blob; p.naccept = naccept;
     p.r_inds = o->replay_inds; p.r_zz = o->replay_zz; p.r_rint = o->replay_rint; p.r_logu = o->replay_logu;
   }
-  int nl = 0;
-  CUI(launch_sampler(p, h->stream, &nl));
-  h->launches += nl;
-  if (on_host) {
-    CU(cudaMemcpyAsync(chain, p.chain, nst * W * d * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(logp, p.logp, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(blob, p.blob, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(naccept, p.naccept, W * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+  // Host results of more than a few MB: the chain runs as up to 8 launches (whole stored rows each; the kernel resumes
+  // from the previous piece's last stored row with the draws indexed by the global step, so the chain is the same bit
+  // for bit) and piece k's rows cross PCIe on the copy stream while piece k+1 samples.  APGP_SAMPLER_PIECES overrides.
+  int pieces = 1;
+  if (on_host && !replay && nst >= 2) {
+    const size_t out_bytes = nst * W * (size_t)(d + 2) * 8;
+    if (out_bytes >= ((size_t)4 << 20)) pieces = nst < 8 ? (int)nst : 8;
+    if (const char* pv = getenv("APGP_SAMPLER_PIECES")) { const int v = atoi(pv); if (v >= 1) pieces = v > (int)nst ? (int)nst : v; }
   }
-  return APGP_OK;
+  if (pieces <= 1) {
+    int nl = 0;
+    CUI(launch_sampler(p, h->stream, &nl));
+    h->launches += nl;
+    if (on_host) {
+      CU(cudaMemcpyAsync(chain, p.chain, nst * W * d * 8, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(logp, p.logp, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(blob, p.blob, nst * W * 8, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(naccept, p.naccept, W * 4, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+    return APGP_OK;
+  }
+  { int st_ = ensure_pipeline(h); if (st_ != APGP_OK) return st_; }
+  double* const dchain = h->s_chain.as<double>();
+  double* const dlogp = h->s_logp.as<double>();
+  double* const dblob = h->s_blob.as<double>();
+  std::vector<cudaEvent_t> ev((size_t)pieces, nullptr);
+  std::vector<size_t> row0((size_t)pieces + 1, 0);
+  for (int k = 0; k <= pieces; ++k) row0[k] = nst * (size_t)k / pieces;
+  int rc = APGP_OK;
+  auto cleanup = [&]() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); };
+  p.nsteps_total = o->nsteps;
+  for (int k = 0; k < pieces && rc == APGP_OK; ++k) {            // every piece is queued before the host blocks in a copy
+    const size_t r0 = row0[k], r1 = row0[k + 1];
+    p.step_base = (int)(r0 * o->thin);
+    p.nsteps = (k == pieces - 1) ? o->nsteps - p.step_base : (int)((r1 - r0) * o->thin);
+    p.p0 = k == 0 ? h->s_p0.as<double>() : dchain + (r0 - 1) * W * d;
+    p.chain = dchain + r0 * W * d; p.logp = dlogp + r0 * W; p.blob = dblob + r0 * W;
+    int nl = 0;
+    if (launch_sampler(p, h->stream, &nl)) { rc = fail(APGP_ERR_CUDA, "apgp_sampler_run: launch failed"); break; }
+    h->launches += nl;
+    if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev[k], h->stream) != cudaSuccess)
+      rc = fail(APGP_ERR_CUDA, "apgp_sampler_run: event");
+  }
+  for (int k = 0; k < pieces && rc == APGP_OK; ++k) {
+    const size_t r0 = row0[k], nr = row0[k + 1] - r0;
+    if (cudaStreamWaitEvent(h->copy_out, ev[k], 0) != cudaSuccess ||
+        cudaMemcpyAsync(chain + r0 * W * d, dchain + r0 * W * d, nr * W * d * 8, cudaMemcpyDeviceToHost, h->copy_out) != cudaSuccess ||
+        cudaMemcpyAsync(logp + r0 * W, dlogp + r0 * W, nr * W * 8, cudaMemcpyDeviceToHost, h->copy_out) != cudaSuccess ||
+        cudaMemcpyAsync(blob + r0 * W, dblob + r0 * W, nr * W * 8, cudaMemcpyDeviceToHost, h->copy_out) != cudaSuccess)
+      rc = fail(APGP_ERR_CUDA, "apgp_sampler_run: copy");
+  }
+  if (rc == APGP_OK && cudaMemcpyAsync(naccept, p.naccept, W * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+    rc = fail(APGP_ERR_CUDA, "apgp_sampler_run: copy");
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->copy_out);
+  cleanup();
+  if (rc == APGP_OK && cudaGetLastError() != cudaSuccess) rc = fail(APGP_ERR_CUDA, "apgp_sampler_run: device error");
+  return rc;
 }
 
 // ---- multi-GPU: one handle per GPU, NCCL over NVLink (comm.cu) ------------------------------------------------------

@@ -165,6 +165,11 @@ struct SamplerParams {
   const int* r_rint;       // [nens][nsteps][2][nwalk/2]
   const double* r_logu;    // [nens][nsteps][2][nwalk/2]
   int thin;                // store every `thin` steps (>=1)
+  // a chain run as several launches (apgp_sampler_run pipelines the D2H of one piece under the next piece's kernel):
+  // this launch covers steps [step_base, step_base + nsteps) of a chain of nsteps_total steps (0: nsteps) -- the
+  // counter-based draws and the replay rows are indexed by the GLOBAL step, chain / logp / blob point at this piece's
+  // first row, p0 is the previous piece's last stored row, naccept keeps counting (zeroed when step_base == 0)
+  int step_base, nsteps_total;
 };
 int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches);
 

@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
 
   Philox rng; rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
   const bool replay = p.r_zz != nullptr;
+  const int nst_tot = p.nsteps_total ? p.nsteps_total : p.nsteps;     // draws are indexed by the chain's global step
 
   for (int step0 = 0; step0 < p.nsteps; step0 += SB) {
     const int sb = min(SB, p.nsteps - step0);
@@ -282,14 +283,14 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
     if (replay) {
       for (int idx = tid; idx < sb * nw; idx += blockDim.x) {
         const int s = idx / nw, w = idx - s * nw;
-        sm.colour[idx] = p.r_inds[((size_t)e * p.nsteps + step0 + s) * nw + w];
+        sm.colour[idx] = p.r_inds[((size_t)e * nst_tot + p.step_base + step0 + s) * nw + w];
       }
     } else {
       // uniformly random half/half colouring (same law as emcee's shuffle of arange(nw) % 2): every walker
       // draws a key, the nw/2 smallest keys are colour 0.  Fully parallel -- no serial Fisher-Yates.
       for (int idx = tid; idx < sb * nw; idx += blockDim.x) {
         const int s = idx / nw, w = idx - s * nw;
-        uint32_t o[4]; rng.gen((uint32_t)e, (uint32_t)(step0 + s), 0x10000u, (uint32_t)w, o);
+        uint32_t o[4]; rng.gen((uint32_t)e, (uint32_t)(p.step_base + step0 + s), 0x10000u, (uint32_t)w, o);
         sm.key[idx] = ((uint64_t)o[0] << 32) | o[1];
       }
       __syncthreads();
@@ -313,10 +314,10 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const __grid_constant__ S
     }
     for (int idx = tid; idx < sb * 2 * Ns; idx += blockDim.x) {   // stretch factor, partner, accept threshold
       const int s = idx / (2 * Ns), rem = idx - s * 2 * Ns, split = rem / Ns, i = rem - split * Ns;
-      const int step = step0 + s;
+      const int step = p.step_base + step0 + s;
       double zz, lu; int r;
       if (replay) {
-        const size_t off = (((size_t)e * p.nsteps + step) * 2 + split) * Ns + i;
+        const size_t off = (((size_t)e * nst_tot + step) * 2 + split) * Ns + i;
         zz = p.r_zz[off]; r = p.r_rint[off]; lu = p.r_logu[off];
       } else {
         uint32_t o[4], o2[4];
@@ -461,7 +462,7 @@ int launch_sampler(const SamplerParams& p, cudaStream_t st, int* launches) {
   const int pairs = split ? (Ns + 1) / 2 : ((Ns + C - 1) / C + 1) / 2;      // split mode: every CTA evaluates all proposals
   int nwarps = Ns < 8 ? (Ns < 1 ? 1 : Ns) : (pairs < 8 ? 8 : (pairs > 32 ? 32 : pairs));
   if (const char* wv = getenv("APGP_SAMPLER_WARPS")) { int w = atoi(wv); if (w >= 1 && w <= 32) nwarps = w; }
-  cudaMemsetAsync(p.naccept, 0, sizeof(int) * (size_t)p.nens * p.nwalk, st);
+  if (p.step_base == 0) cudaMemsetAsync(p.naccept, 0, sizeof(int) * (size_t)p.nens * p.nwalk, st);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.nens * C)); cfg.blockDim = dim3((unsigned)(nwarps * 32));
   cfg.dynamicSmemBytes = smem; cfg.stream = st;

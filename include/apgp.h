@@ -137,7 +137,10 @@ typedef struct apgp_sampler_opts {
  * as driven from approx.py:839-847.  p0 [nens*nwalkers][d];
  * chain [nsteps/thin][nens*nwalkers][d], logp/blob [nsteps/thin][nens*nwalkers], naccept [nens*nwalkers] int32.
  * One CTA per ensemble, or -- few ensembles with enough work per half-step -- a thread-block cluster of 2/4/8 CTAs
- * per ensemble (same chains bit for bit).  nwalkers * (24 ndim + 72) bytes must fit one CTA's shared memory. */
+ * per ensemble (same chains bit for bit).  nwalkers * (24 ndim + 72) bytes must fit one CTA's shared memory.
+ * on_host=1 with more than 4 MB of results: the chain runs as up to 8 launches (whole stored rows each; the kernel
+ * resumes from the previous piece's last stored row, draws indexed by the global step: the same chain bit for bit) and
+ * the rows of one piece cross PCIe while the next piece samples.  APGP_SAMPLER_PIECES=k overrides (1: one launch). */
 int apgp_sampler_run(apgp_handle* h, const apgp_sampler_opts* opts, const double* p0, double* chain, double* logp,
                      double* blob, int* naccept, int on_host);
 

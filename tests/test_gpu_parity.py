@@ -569,6 +569,42 @@ def test_sampler_cluster_replicas_give_the_same_chain(cluster, monkeypatch):
     assert np.array_equal(out["naccepted"], ref["naccepted"])
 
 
+@pytest.mark.parametrize("nens,nw,nsteps,thin", [(3, 40, 125, 4), (1, 120, 61, 1), (300, 32, 200, 2)])
+def test_sampler_in_pieces_is_the_same_chain(nens, nw, nsteps, thin, monkeypatch):
+    """apgp_sampler_run(on_host=1) runs long chains as several launches so that one piece's rows cross PCIe while the
+    next piece samples: the kernel resumes from the previous piece's last stored row, the counter-based draws are
+    indexed by the chain's global step and the acceptance counts keep counting.  Any number of pieces -- including the
+    automatic choice for results of more than 4 MB (third case) -- must give the single-launch chain bit for bit
+    (steps left over after the last stored row included: they still count in naccepted), as must the device-resident
+    call, which is never cut."""
+    import torch
+    X, y, logM, _ = synthetic_gp_problem(300, 3, seed=21)
+    gp, _ = make_pair(X, y, logM)
+    bounds = [(-5.0, 5.0)] * 3
+    rng = np.random.default_rng(8)
+    p0 = rng.uniform(-3, 3, size=(nens * nw, 3))
+    p0[1] = [7.0, 0.0, 0.0]                                    # a walker outside the prior box: -inf / nan until it moves
+    monkeypatch.setenv("APGP_SAMPLER_PIECES", "1")
+    ref = gp.run_ensembles(y, p0, nsteps, bounds, nens=nens, seed=77, thin=thin)
+    for pieces in ("2", "5", "1000", None):
+        if pieces is None:
+            monkeypatch.delenv("APGP_SAMPLER_PIECES")
+        else:
+            monkeypatch.setenv("APGP_SAMPLER_PIECES", pieces)
+        l0 = gp.launch_count
+        out = gp.run_ensembles(y, p0, nsteps, bounds, nens=nens, seed=77, thin=thin)
+        launches = gp.launch_count - l0
+        if pieces is not None:
+            assert launches == min(int(pieces), nsteps // thin)
+        elif (nsteps // thin) * nens * nw * 5 * 8 >= 4 << 20:
+            assert launches == 8                                 # the automatic choice cut this one
+        for k in ("chain", "log_prob", "blobs", "naccepted"):
+            assert np.array_equal(ref[k], out[k], equal_nan=True), (pieces, k)
+    dev = gp.run_ensembles(y, p0, nsteps, bounds, nens=nens, seed=77, thin=thin, device_out=True)
+    for k in ("chain", "log_prob", "blobs", "naccepted"):
+        assert np.array_equal(ref[k], dev[k].cpu().numpy(), equal_nan=True), k
+
+
 @pytest.mark.parametrize("N,d,Q,kind", [(300, 3, 200000, "bape"), (1100, 5, 170001, None), (256, 2, 600000, "agp")])
 def test_pipelined_host_predict_equals_device_resident(N, d, Q, kind, monkeypatch):
     """apgp_predict(on_host=1) cuts large calls into slices whose H2D copy, kernel and D2H copies overlap on three
