@@ -326,8 +326,9 @@ def run_cfg2(args, bench):
     evals = float(NENS2 * NW2) * NSTEPS2 * args.steps
     # e2e: the public sharded API with host buffers -- p0 H2D, chain (every 20th step) / log_prob / blobs D2H, one all-gather
     e2e_steps = max(1, min(args.steps, 3))
-    apd.run_ensembles_sharded(gp, y, p0_all, NSTEPS2, bounds, NENS2, seed=5, thin=20)
-    H.barrier()
+    for i in range(3):   # warm-up with the caller's own pattern (the previous result is alive during the next call): at
+        out = apd.run_ensembles_sharded(gp, y, p0_all, NSTEPS2, bounds, NENS2, seed=3 + i, thin=20)   # N > 1 the two sets of
+    H.barrier()          # pinned result blocks then both sit in torch's host cache and no timed call pays a cudaHostAlloc
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         out = apd.run_ensembles_sharded(gp, y, p0_all, NSTEPS2, bounds, NENS2, seed=6 + i, thin=20)
