@@ -354,7 +354,9 @@ def run_cfg2(args, bench):
                                                "tau": None if tau is None else [float(v) for v in tau[0]]}),
                            e2e={"value": float(NENS2 * NW2) * NSTEPS2 * e2e_steps / e2e_s, "unit": "evals/s", "steps": e2e_steps,
                                 "h2d_bytes_per_step": int(nloc * NW2 * 2 * 8),
-                                "d2h_bytes_per_step": int(nst * nloc * NW2 * (2 + 2) * 8 + nloc * NW2 * 4),
+                                # every rank receives the gathered result: at N > 1 the whole chain crosses each rank's PCIe link
+                                "d2h_bytes_per_step": int(nst * (NENS2 if H.world > 1 else nloc) * NW2 * (2 + 2) * 8
+                                                          + (NENS2 if H.world > 1 else nloc) * NW2 * 4),
                                 "api": "dist.run_ensembles_sharded(gp, y, p0 [host], 1000, bounds, 2048, thin=20) -> gathered host "
                                        "chain / log_prob / blobs / naccepted"},
                            gpu_launches=int(launches),
