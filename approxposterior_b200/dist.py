@@ -117,11 +117,11 @@ def _gather_concat_device(t, axis):
     import torch.distributed as dist
     ws = dist.get_world_size()
     t = t.contiguous()
-    buf = torch.empty((ws,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    buf = torch.empty((ws * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)   # rank-major concatenation
     dist.all_gather_into_tensor(buf, t)
     if axis == 0:
-        return buf.reshape((ws * t.shape[0],) + tuple(t.shape[1:]))
-    return torch.cat(list(buf.unbind(0)), dim=axis)
+        return buf
+    return torch.cat(list(buf.reshape((ws,) + tuple(t.shape)).unbind(0)), dim=axis)
 
 
 def _to_host(tensors):

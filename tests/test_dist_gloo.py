@@ -52,7 +52,27 @@ def _worker(rank, ws, port, q):
         x0s = np.array([[2.0, 0.0], [1.0, 1.0], [0.5, 0.25], [0.3, 0.31], [-1.0, 0.0]])
         pb, mb, nfev = apd.optimize_gp_sharded(FakeGP(), None, x0s)
         ok4 = np.array_equal(pb, x0s[3] * 0.5) and np.isclose(mb, -np.sum((x0s[3] - 0.3) ** 2)) and nfev == 35
-        q.put((rank, bool(ok1), bool(ok2), bool(ok3 and ok4)))
+        # the tensor form of the chain gather (the NCCL path of run_ensembles_sharded; CPU tensors over gloo here):
+        # one all-gather into [world, ...], concatenation along the walker axis -- same result as the NumPy form
+        import torch
+        t_loc = torch.arange(4 * 6 * 2, dtype=torch.float64).reshape(4, 6, 2) + 1000.0 * rank
+        g1 = apd._gather_concat_device(t_loc, 1).numpy()
+        ok5 = np.array_equal(g1, apd.gather_concat(t_loc.numpy(), axis=1))
+        n_loc = torch.arange(6, dtype=torch.int32) + 10 * rank
+        ok5 = ok5 and np.array_equal(apd._gather_concat_device(n_loc, 0).numpy(), apd.gather_concat(n_loc.numpy(), axis=0))
+        # run_ensembles_sharded on the host path (no CUDA): contiguous ensemble blocks, rank-dependent seed, walker order
+        class FakeSampler(object):
+            def run_ensembles(self, y, p0, nsteps, bounds, nens=1, seed=0, **kw):
+                W = p0.shape[0]
+                ch = np.broadcast_to(p0[None], (nsteps, W, p0.shape[1])) + float(seed)
+                return dict(chain=ch.copy(), log_prob=np.full((nsteps, W), float(nens)), blobs=np.zeros((nsteps, W)),
+                            naccepted=np.arange(W, dtype=np.int32))
+        p0 = np.arange(4 * 3 * 2, dtype=np.float64).reshape(12, 2)        # 4 ensembles of 3 walkers
+        o = apd.run_ensembles_sharded(FakeSampler(), None, p0, 5, None, 4, seed=2)
+        want = np.concatenate([p0[:6] + 2.0, p0[6:] + 2.0 + 7919.0])
+        ok6 = (o["chain"].shape == (5, 12, 2) and np.array_equal(o["chain"][3], want) and np.all(o["log_prob"] == 2.0)
+               and np.array_equal(o["naccepted"], np.tile(np.arange(6, dtype=np.int32), 2)))
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3 and ok4 and ok5 and ok6)))
     finally:
         dist.destroy_process_group()
 
