@@ -29,7 +29,7 @@ struct DevBuf {
     size_t want = bytes + bytes / 2;
     cudaError_t e = cudaMalloc(&q, want);
     if (e != cudaSuccess) return (int)e;
-    if (p && keep) { e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return (int)e; cudaStreamSynchronize(st); }
+    if (p && keep) { e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) { cudaFree(q); return (int)e; } cudaStreamSynchronize(st); }
     if (p) cudaFree(p);
     p = q; cap = want;
     return 0;
@@ -112,12 +112,15 @@ int apgp_create(apgp_handle** out, int device) {
   h->device = device;
   Guard g(device);
   cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete h; return fail(APGP_ERR_CUDA, "apgp_create: cudaGetDeviceProperties", e); }
   if (prop.major < 10) { delete h; return fail(APGP_ERR_CUDA, "apgp_create: kernels are built for sm_100a only"); }
   h->num_sms = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(APGP_ERR_CUDA, "apgp_create: cudaStreamCreate", e); }
   h->own_stream = true;
-  CU(cudaHostAlloc((void**)&h->pin, apgp_handle::PIN_DOUBLES * 8, cudaHostAllocDefault));
+  e = cudaHostAlloc((void**)&h->pin, apgp_handle::PIN_DOUBLES * 8, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return fail(APGP_ERR_CUDA, "apgp_create: cudaHostAlloc", e); }
   const char* v = getenv("APGP_PREDICT_VARIANT");
   if (v) { int vv = atoi(v); h->variant = (vv >= 0 && vv <= 2) ? vv : 2; }
   const char* gv = getenv("APGP_PREDICT_GROUP");
