@@ -507,3 +507,29 @@ def test_optimizeGP_device_engine_protocol():
         gpUtils.optimizeGP(FakeGP(fits=False), None, y, nGPRestarts=2)
     with pytest.raises(AssertionError):
         gpUtils.optimizeGP(FakeGP(), None, y, nGPRestarts=2, engine="lockstep")
+
+
+def test_shipped_kernels_have_the_claimed_hardware_paths_and_no_spills():
+    """Static check of the built libapgp.so (cuobjdump, no GPU): no kernel spills registers to local memory, the variance
+    kernels and the cluster log-likelihood carry DMMA (FP64 tensor pipe), UBLKCP (bulk TMA) and SYNCS (mbarrier)
+    instructions, the one-CTA Cholesky uses DMMA, the sampler has its cluster barriers (profiles/*_sass_summary.txt)."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import sass_summary
+    finally:
+        sys.path.pop(0)
+    rows = {r["kernel"]: r for r in sass_summary.collect(os.path.join(ROOT, "approxposterior_b200", "libapgp.so"))}
+    assert len(rows) >= 30
+    spilled = [k for k, r in rows.items() if r["local"] != 0]
+    assert not spilled, spilled
+    for k in ("predict_var_group_kernel<256, 64, 4>", "predict_var_kernel<256, 64, 4, 8>", "loglik_group_kernel",
+              "minimize_nll_group_kernel"):
+        r = rows[k]
+        assert r["DMMA"] >= 200 and r["UBLKCP"] >= 8 and r["SYNCS"] >= 20, (k, r)
+    for k in ("loglik_small_kernel", "minimize_nll_kernel", "chol_panel_kernel", "chol_update_kernel", "gemm_tile_kernel"):
+        assert rows[k]["DMMA"] > 0, k
+    assert rows["sampler_kernel"]["CGABAR"] > 0 and rows["sampler_kernel"]["regs"] <= 64

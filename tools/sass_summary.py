@@ -35,8 +35,8 @@ def short(name):
     return name[:cut]
 
 
-def main():
-    so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "approxposterior_b200", "libapgp.so")
+def collect(so):
+    """[{kernel, instr, regs, local, smem, DMMA, UBLKCP, ...}] for every kernel in the shared library."""
     res = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True, check=True).stdout
     usage = {}
     fn = None
@@ -62,20 +62,30 @@ def main():
         if m and cur:
             op = m.group(1)
             counts[cur]["instr"] += 1
-            if op == "UCGABAR_ARV" or op == "UCGABAR_WAIT" or op.startswith("CGABAR") or op.startswith("UCGABAR"):
+            if op.startswith("CGABAR") or op.startswith("UCGABAR"):
                 counts[cur]["CGABAR"] += 1
             elif op in ("ATOM", "ATOMG", "ATOMS"):
                 counts[cur]["ATOM"] += 1
             elif op in COLS:
                 counts[cur][op] += 1
     names = demangle(list(counts))
+    rows = []
+    for fn, c in sorted(counts.items(), key=lambda kv: -kv[1]["instr"]):
+        r = usage.get(fn, (0, 0, 0))
+        row = {"kernel": short(names[fn]), "instr": c["instr"], "regs": r[0], "local": r[1], "smem": r[2]}
+        row.update({k: c[k] for k in COLS})
+        rows.append(row)
+    return rows
+
+
+def main():
+    so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "approxposterior_b200", "libapgp.so")
     print("cuobjdump -sass / -res-usage %s (sm_100a, built by __graft_entry__.build()); static instruction counts per kernel"
           % os.path.relpath(so, ROOT))
     print("%-64s %6s %5s %5s %8s " % ("kernel", "instr", "regs", "local", "smem(st)") + " ".join("%6s" % c for c in COLS))
-    for fn, c in sorted(counts.items(), key=lambda kv: -kv[1]["instr"]):
-        r = usage.get(fn, (0, 0, 0))
-        print("%-64s %6d %5d %5d %8d " % (short(names[fn])[:64], c["instr"], r[0], r[1], r[2]) +
-              " ".join("%6d" % c[k] for k in COLS))
+    for r in collect(so):
+        print("%-64s %6d %5d %5d %8d " % (r["kernel"][:64], r["instr"], r["regs"], r["local"], r["smem"]) +
+              " ".join("%6d" % r[k] for k in COLS))
 
 
 if __name__ == "__main__":
