@@ -155,6 +155,18 @@ def run_reference(args):
                                        "george predict+BAPE, all BLAS threads" % nq},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_bape:
+        # second half of the metric on the CPU arm: one BAPE iteration of the README configuration through the reference's
+        # OWN ApproxPosterior.run (baseline/_ref, unmodified) over the oracle-backed george/emcee shim -- what
+        # `--config cfg1 --impl reference` times; MCMC leg bounded to 2000 of the 2e4 steps
+        try:
+            import bench_configs
+            cb = bench_configs.cfg1_reference(bounded=True)
+            line["bape_iteration"] = {"metric": "BAPE iteration time (README config: m0=50, m=20, nmax=2, 20 walkers x 2e4 steps)",
+                                      "value": cb["value"], "unit": "s per BAPE iteration (20 new design points + GP refits)",
+                                      "higher_is_better": False, "kind": cb["kind"], "cores": cb["cores"], "sample": cb["sample"]}
+        except Exception as e:                                  # never lose the headline line over the secondary leg
+            line["bape_iteration"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     emit_line(line)
 
 
