@@ -32,8 +32,12 @@ def test_reference_arm_line(cfg, metric_has):
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert "workload" in d["config"] and d["gpu_launches"] == 0
-    if cfg in ("cfg3", "cfg5"):
+    if cfg in ("cfg3", "cfg5", "cfg2"):                       # cfg2: one ensemble per core, side by side
         assert cb["cores"] == (os.cpu_count() or 1)
+    if cfg == "cfg3":                                         # the driver's reference record carries both halves of the metric
+        b = d["bape_iteration"]
+        assert "unavailable" not in b, b
+        assert b["value"] > 0 and b["higher_is_better"] is False and b["kind"] in ("reference", "port")
 
 
 def test_other_ranks_of_the_reference_arm_stay_silent():
