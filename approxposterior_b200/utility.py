@@ -165,6 +165,23 @@ def scanUtility(gp, y, kind, bounds, nCandidates=1 << 20, seed=None, zeta=0.01, 
 DEVICE_OPTIMIZER = True      # module default for minimizeObjective(engine=None)
 
 
+def _solve_one(f, t0, redraw, priorFn, bounds, method, options, maxIters):
+    """One restart of the reference's protocol (utility.py:332-366): minimise from t0; while the optimum is not finite or
+    is rejected by the prior, redraw the start and try again, at most maxIters times."""
+    ii = 0
+    while True:
+        if ii >= maxIters:
+            errMsg = "ERROR: Cannot find a valid solution. Current iterations: %d\n" % ii
+            errMsg += "Maximum iterations: %d\n" % maxIters
+            raise RuntimeError(errMsg)
+        tmp = minimize(f, t0, bounds=bounds, method=method, options=options)["x"]
+        if np.all(np.isfinite(tmp)):
+            if np.isfinite(priorFn(tmp)):
+                return tmp, f(tmp)
+        t0 = redraw()
+        ii += 1
+
+
 def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-mead", options=None, bounds=None,
                       theta0=None, args=None, maxIters=100, batched=True, _start=None, engine=None):
     """Multistart local minimisation of ``fn`` (reference utility.py:253-372).
@@ -182,10 +199,11 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
     * ``engine="lockstep"``: the restarts advance in lock step on the host (coroutine restatements of the
       same SciPy algorithms) and each round of objective calls is one fused predict+utility launch.
 
-    RNG consumption: all ``nRestarts`` start points are drawn up front (the restarts run side by side), retries draw
-    afterwards.  The reference draws start r, optimises, redraws on rejection, and only then draws start r+1
-    (utility.py:336,364): the two orders consume ``np.random`` identically as long as NO restart is retried; a seeded
-    run in which a retry happens picks different later starts than the reference would.
+    RNG consumption: the side-by-side engines draw all ``nRestarts`` start points up front and the retries afterwards.
+    The reference draws start r, optimises, redraws on rejection, and only then draws start r+1 (utility.py:336,364):
+    the two orders consume ``np.random`` identically as long as NO restart is retried.  The sequential path
+    (``batched=False``, or an objective without a batched form) draws each start lazily and is the reference's order
+    exactly, retries included (``tests/test_reference_dropin.py::test_sequential_minimize_objective_is_the_references_rng_order``).
     """
     if str(method).lower() == "nelder-mead" and options is None:
         options = {"adaptive": True}
@@ -206,15 +224,10 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
     def draw():
         return np.asarray(sampleFn(1), dtype=np.float64).ravel()
 
-    starts = []
-    for _ in range(nRestarts):
+    def start_point():
         if theta0 is None:
-            starts.append(draw())
-        else:
-            starts.append(np.atleast_1d(theta0 + np.min(theta0) * 1.0e-3 * np.random.randn(ndim)).ravel())
-
-    if _start is not None:          # engine extension: polish a known-good candidate (scanUtility)
-        starts[0] = np.asarray(_start, dtype=np.float64).ravel()
+            return draw()
+        return np.atleast_1d(theta0 + np.min(theta0) * 1.0e-3 * np.random.randn(ndim)).ravel()
 
     kind = _KIND.get(fn) or getattr(fn, "device_kind", None) or _kind_by_name(fn)
     fn_batch = getattr(fn, "batch", None)      # any objective may bring its own batched form
@@ -223,8 +236,26 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
         box = [(float(a), float(b)) for a, b in _box_hint]      # the caller vouches: priorFn is the box over `bounds`
     if engine is None:
         engine = "device" if DEVICE_OPTIMIZER else "lockstep"
-    if (engine == "device" and batched and kind is not None and box is not None and hasattr(gp, "minimize_utility")
-            and _opt.supported(method, options, bounds)):
+    on_device = (engine == "device" and batched and kind is not None and box is not None and hasattr(gp, "minimize_utility")
+                 and _opt.supported(method, options, bounds))
+    use_batch = batched and nRestarts > 1 and (fn_batch is not None or
+                                               (kind is not None and hasattr(gp, "predict_utility")))
+    if not on_device and not use_batch:
+        # one restart after the other, as the reference runs them: start r is drawn only after restart r - 1 (and its
+        # retries) has finished, so np.random is consumed in the reference's order even when a restart is retried
+        out = []
+        for r in range(nRestarts):
+            t0 = np.asarray(_start, dtype=np.float64).ravel() if (r == 0 and _start is not None) else start_point()
+            out.append(_solve_one(lambda x: fn(x, *args), t0, draw, priorFn, bounds, method, options, maxIters))
+        objective = [o[1] for o in out]
+        bestInd = np.argmin(objective)
+        return np.array([o[0] for o in out])[bestInd], objective[bestInd]
+
+    starts = [start_point() for _ in range(nRestarts)]          # side-by-side restarts: all starts up front
+    if _start is not None:          # engine extension: polish a known-good candidate (scanUtility)
+        starts[0] = np.asarray(_start, dtype=np.float64).ravel()
+
+    if on_device:
         # one CTA per restart, the whole multistart in one launch; restarts whose optimum is not finite or is
         # rejected by the prior are redrawn from the prior and re-run (utility.py:342-366), together
         res, objective = [None] * nRestarts, [None] * nRestarts
@@ -250,62 +281,46 @@ def minimizeObjective(fn, y, gp, sampleFn, priorFn, nRestarts=5, method="nelder-
         bestInd = np.argmin(objective)
         return np.array(res)[bestInd], objective[bestInd]
 
-    use_batch = batched and nRestarts > 1 and (fn_batch is not None or
-                                               (kind is not None and hasattr(gp, "predict_utility")))
-
     def solve(f, t0, redraw):
-        ii = 0
-        while True:
-            if ii >= maxIters:
-                errMsg = "ERROR: Cannot find a valid solution. Current iterations: %d\n" % ii
-                errMsg += "Maximum iterations: %d\n" % maxIters
-                raise RuntimeError(errMsg)
-            tmp = minimize(f, t0, bounds=bounds, method=method, options=options)["x"]
-            if np.all(np.isfinite(tmp)):
-                if np.isfinite(priorFn(tmp)):
-                    return tmp, f(tmp)
-            t0 = redraw()
-            ii += 1
+        return _solve_one(f, t0, redraw, priorFn, bounds, method, options, maxIters)
 
-    if use_batch:
-        zeta = 0.01
+    # lock-step restarts on the host: every round of objective calls is one fused predict + utility launch
+    zeta = 0.01
 
-        def batch_fn(thetas):
-            if fn_batch is not None:
-                return fn_batch(np.array(thetas))
-            return utilityBatch(np.array(thetas), y, gp, priorFn, kind, zeta=zeta)
+    def batch_fn(thetas):
+        if fn_batch is not None:
+            return fn_batch(np.array(thetas))
+        return utilityBatch(np.array(thetas), y, gp, priorFn, kind, zeta=zeta)
 
-        if _opt.supported(method, options, bounds):
-            # thread-free lock step: SciPy's algorithm restated as a coroutine per restart
-            make = _opt.nelder_mead_gen if str(method).lower() == "nelder-mead" else _opt.powell_gen
+    if _opt.supported(method, options, bounds):
+        # thread-free lock step: SciPy's algorithm restated as a coroutine per restart
+        make = _opt.nelder_mead_gen if str(method).lower() == "nelder-mead" else _opt.powell_gen
 
-            def restart(t0):
-                ii = 0
-                while True:
-                    if ii >= maxIters:
-                        raise RuntimeError("ERROR: Cannot find a valid solution. Current iterations: %d\n"
-                                           "Maximum iterations: %d\n" % (ii, maxIters))
-                    tmp, _ = yield from make(t0, **(options or {}))
-                    if np.all(np.isfinite(tmp)) and np.isfinite(priorFn(tmp)):
-                        ftmp = yield np.copy(tmp)            # the reference re-evaluates fn at the optimum
-                        return tmp, ftmp
-                    t0 = draw()
-                    ii += 1
+        def restart(t0):
+            ii = 0
+            while True:
+                if ii >= maxIters:
+                    raise RuntimeError("ERROR: Cannot find a valid solution. Current iterations: %d\n"
+                                       "Maximum iterations: %d\n" % (ii, maxIters))
+                tmp, _ = yield from make(t0, **(options or {}))
+                if np.all(np.isfinite(tmp)) and np.isfinite(priorFn(tmp)):
+                    ftmp = yield np.copy(tmp)            # the reference re-evaluates fn at the optimum
+                    return tmp, ftmp
+                t0 = draw()
+                ii += 1
 
-            out, rounds, evals = _opt.run_generators([restart(t0) for t0 in starts], batch_fn)
-            minimizeObjective.last_stats = dict(batches=rounds, evals=evals, scheduler="generators")
-        else:
-            import threading
-            rng_lock = threading.Lock()
-
-            def redraw():
-                with rng_lock:
-                    return draw()
-
-            out, ev = run_lockstep(nRestarts, batch_fn, lambda wid, f: solve(f, starts[wid], redraw))
-            minimizeObjective.last_stats = dict(batches=ev.nbatches, evals=ev.nevals, scheduler="threads")
+        out, rounds, evals = _opt.run_generators([restart(t0) for t0 in starts], batch_fn)
+        minimizeObjective.last_stats = dict(batches=rounds, evals=evals, scheduler="generators")
     else:
-        out = [solve(lambda x: fn(x, *args), t0, draw) for t0 in starts]
+        import threading
+        rng_lock = threading.Lock()
+
+        def redraw():
+            with rng_lock:
+                return draw()
+
+        out, ev = run_lockstep(nRestarts, batch_fn, lambda wid, f: solve(f, starts[wid], redraw))
+        minimizeObjective.last_stats = dict(batches=ev.nbatches, evals=ev.nevals, scheduler="threads")
 
     res = [o[0] for o in out]
     objective = [o[1] for o in out]

@@ -108,6 +108,52 @@ def test_reference_optimizer_path_dependent_on_oracle_shim(module, function, tmp
             pytest.xfail("optimiser-path dependent golden (SURVEY 4.3)")
 
 
+@needs_ref
+@pytest.mark.parametrize("theta0", [None, [0.4, 0.9]])
+def test_sequential_minimize_objective_is_the_references_rng_order(theta0, tmp_path):
+    """the side-by-side engines draw all restart starts up front; the reference draws start r only after
+    restart r - 1 and its retries (utility.py:336,364).  The sequential path (batched=False) follows the reference
+    exactly: with a prior that rejects part of the domain (so that restarts ARE retried) the same seed gives the
+    same optimum, the same objective value and leaves np.random in the same state as the reference's own function."""
+    from oracle import refshim
+    from approxposterior_b200 import utility as mine, likelihood as lh
+    with _Reference(refshim, tmp_path):
+        rut = importlib.import_module("approxposterior.utility")
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        np.random.seed(3)
+        theta = lh.rosenbrockSample(40)
+        y = np.array([lh.rosenbrockLnlike(t) + lh.rosenbrockLnprior(t) for t in theta])
+        gp = rgu.defaultGP(theta, y, white_noise=-12)
+        calls = {"rejected": 0, "seen": []}
+
+        def box(x):                                    # what the utility itself sees
+            return 0.0 if np.all(np.abs(np.asarray(x).ravel()) <= 5.0) else -np.inf
+
+        def prior(x):                                  # what validates an optimum: the box minus a band optima end up in
+            x = np.asarray(x).ravel()
+            calls["seen"].append(x.copy())
+            ok = np.all(np.abs(x) <= 5.0) and not (-1.6 < x[0] < 2.5)
+            calls["rejected"] += 0 if ok else 1
+            return 0.0 if ok else -np.inf
+        kw = dict(nRestarts=4, method="nelder-mead", options={"adaptive": True, "maxiter": 40}, theta0=theta0,
+                  args=(y, gp, box))
+        np.random.seed(11)
+        with np.errstate(all="ignore"):
+            x_ref, f_ref = rut.minimizeObjective(rut.BAPEUtility, y, gp, lh.rosenbrockSample, prior, **kw)
+        state_ref = np.random.get_state()[1].copy()
+        rejected_ref, seen_ref = calls["rejected"], calls["seen"]
+        calls.update(rejected=0, seen=[])
+        np.random.seed(11)
+        with np.errstate(all="ignore"):
+            x_me, f_me = mine.minimizeObjective(rut.BAPEUtility, y, gp, lh.rosenbrockSample, prior, batched=False, **kw)
+        assert rejected_ref > 0, "the prior never rejected an optimum: the test would not see the order"
+        assert calls["rejected"] == rejected_ref
+        assert len(calls["seen"]) == len(seen_ref) and all(np.array_equal(a, b) for a, b in zip(calls["seen"], seen_ref)), \
+            "every optimum handed to the prior, in order: restarts and retries started from the same points"
+        assert np.array_equal(np.asarray(x_me).ravel(), np.asarray(x_ref).ravel()) and f_me == f_ref
+        assert np.array_equal(np.random.get_state()[1], state_ref)
+
+
 # ------------------------------------------------------------------------------------------ GPU: engine-backed shim
 @pytest.mark.gpu
 @needs_ref
