@@ -83,7 +83,8 @@ def JonesUtility(theta, y, gp, priorFn, zeta=0.01):
         z = (mu - yBest - zeta) / std
     else:
         return 0.0
-    return -((mu - yBest - zeta) * ndtr(z) + std * np.exp(-0.5 * z * z) / np.sqrt(2.0 * np.pi))
+    pdf = np.exp(-0.5 * z * z) / np.sqrt(2.0 * np.pi)          # scipy.stats.norm.pdf's own expression: the two terms
+    return -((mu - yBest - zeta) * ndtr(z) + std * pdf)         # cancel in the far tail, so the grouping shows in the bits
 
 
 _KIND = {AGPUtility: "agp", BAPEUtility: "bape", JonesUtility: "jones"}

@@ -1,0 +1,114 @@
+"""Differential tests of this repo's host drivers against the REFERENCE'S OWN functions (CPU).
+
+The reference's pure-Python modules import once `george` / `emcee` resolve to the oracle-backed shim
+(oracle/refshim.py), so its drivers can be called side by side with the mirrors in approxposterior_b200 on the SAME GP
+object and the same seeds.  Everything here must agree bit for bit -- the mirrors claim the reference's protocol,
+RNG consumption included (gpUtils.py:22-110, 184-257; utility.py:69-250; mcmcUtils.py:103-227)."""
+import importlib
+
+import numpy as np
+import pytest
+
+from test_reference_dropin import _Reference, needs_ref
+
+
+def _problem(n=40, seed=3):
+    from approxposterior_b200 import likelihood as lh
+    np.random.seed(seed)
+    theta = lh.rosenbrockSample(n)
+    y = np.array([lh.rosenbrockLnlike(t) + lh.rosenbrockLnprior(t) for t in theta])
+    return theta, y
+
+
+@needs_ref
+@pytest.mark.parametrize("fitAmp", [False, True])
+@pytest.mark.parametrize("method", ["powell", "nelder-mead"])
+def test_optimizeGP_sequential_is_the_references(fitAmp, method, tmp_path):
+    from oracle import refshim
+    from approxposterior_b200 import gpUtils as mine
+    with _Reference(refshim, tmp_path):
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        theta, y = _problem()
+        np.random.seed(5); g_ref = rgu.defaultGP(theta, y, white_noise=-12, fitAmp=fitAmp)
+        np.random.seed(5); g_me = rgu.defaultGP(theta, y, white_noise=-12, fitAmp=fitAmp)
+        np.random.seed(9)
+        with np.errstate(all="ignore"):
+            a = rgu.optimizeGP(g_ref, theta, y, nGPRestarts=3, method=method)
+        s_ref = np.random.get_state()[1].copy()
+        np.random.seed(9)
+        with np.errstate(all="ignore"):
+            b = mine.optimizeGP(g_me, theta, y, nGPRestarts=3, method=method, batched=False)
+        assert np.array_equal(a.get_parameter_vector(), b.get_parameter_vector())
+        assert np.array_equal(np.random.get_state()[1], s_ref)
+        assert a.log_likelihood(y, quiet=True) == b.log_likelihood(y, quiet=True)
+
+
+@needs_ref
+def test_nll_grad_and_hyper_prior_are_the_references(tmp_path):
+    from oracle import refshim
+    from approxposterior_b200 import gpUtils as mine
+    with _Reference(refshim, tmp_path):
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        theta, y = _problem()
+        for fitAmp in (False, True):
+            np.random.seed(5)
+            gp = rgu.defaultGP(theta, y, white_noise=-12, fitAmp=fitAmp)
+            rng = np.random.default_rng(1)
+            p0 = gp.get_parameter_vector()
+            for k in range(12):
+                p = p0 + rng.normal(scale=[0.5, 3.0, 30.0][k % 3], size=p0.size)      # inside and far outside the hyper-prior
+                assert rgu.defaultHyperPrior(p) == mine.defaultHyperPrior(p)
+                for prior in (None, "default"):
+                    pr, pm = (None, None) if prior is None else (rgu.defaultHyperPrior, mine.defaultHyperPrior)
+                    with np.errstate(all="ignore"):
+                        assert rgu._nll(p, gp, y, pr) == mine._nll(p, gp, y, pm)
+                        assert np.array_equal(rgu._grad_nll(p, gp, y, pr), mine._grad_nll(p, gp, y, pm))
+
+
+@needs_ref
+def test_utilities_and_logsubexp_are_the_references(tmp_path):
+    from oracle import refshim
+    from approxposterior_b200 import utility as mine, likelihood as lh
+    with _Reference(refshim, tmp_path):
+        rut = importlib.import_module("approxposterior.utility")
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        theta, y = _problem()
+        np.random.seed(5)
+        gp = rgu.defaultGP(theta, y, white_noise=-12)
+        rng = np.random.default_rng(2)
+        pts = np.vstack([rng.uniform(-5, 5, size=(40, 2)), theta[:5], [[6.0, 0.0], [0.0, -5.5]]])   # incl. training points, outside the prior
+        with np.errstate(all="ignore"):
+            for t in pts:
+                for name in ("AGPUtility", "BAPEUtility", "JonesUtility"):
+                    a = getattr(rut, name)(t, y, gp, lh.rosenbrockLnprior)
+                    b = getattr(mine, name)(t, y, gp, lh.rosenbrockLnprior)
+                    assert np.array_equal(np.asarray(a, dtype=float).ravel(), np.asarray(b, dtype=float).ravel(), equal_nan=True), (name, t)
+            for x1, x2 in rng.normal(scale=20.0, size=(50, 2)):
+                a, b = rut.logsubexp(x1, x2), mine.logsubexp(x1, x2)
+                assert (a == b) or (np.isnan(a) and np.isnan(b))
+        x = np.linspace(0.1, 3.0, 50)
+        p = lambda v: np.exp(-0.5 * v * v) / np.sqrt(2 * np.pi)
+        q = lambda v: np.exp(-0.5 * (v - 0.3) ** 2 / 1.44) / np.sqrt(2 * np.pi * 1.44)
+        assert rut.klNumerical(x, p, q) == mine.klNumerical(x, p, q)
+
+
+@needs_ref
+def test_mcse_and_burnin_are_the_references(tmp_path):
+    """batchMeansMCSE on the same samples; estimateBurnin on the same emcee-flow sampler object (oracle shim)."""
+    from oracle import refshim
+    from approxposterior_b200 import mcmcUtils as mine
+    with _Reference(refshim, tmp_path):
+        rmc = importlib.import_module("approxposterior.mcmcUtils")
+        import emcee                                           # the shim
+        rng = np.random.default_rng(4)
+        samples = rng.normal(size=(5000, 3)).cumsum(axis=0) * 0.01 + rng.normal(size=(5000, 3))
+        assert np.array_equal(rmc.batchMeansMCSE(samples), mine.batchMeansMCSE(samples))
+        assert np.array_equal(rmc.batchMeansMCSE(samples, bins=20, fn=np.square), mine.batchMeansMCSE(samples, bins=20, fn=np.square))
+        np.random.seed(42)
+        lnprob = lambda x: -0.5 * np.sum(x * x)
+        sampler = emcee.EnsembleSampler(10, 2, lnprob)
+        for _ in sampler.sample(np.random.randn(10, 2), iterations=3000):
+            pass
+        for est, thin in ((True, True), (True, False), (False, True), (False, False)):
+            assert tuple(rmc.estimateBurnin(sampler, estBurnin=est, thinChains=thin)) == \
+                tuple(mine.estimateBurnin(sampler, estBurnin=est, thinChains=thin))
