@@ -112,3 +112,73 @@ def test_mcse_and_burnin_are_the_references(tmp_path):
         for est, thin in ((True, True), (True, False), (False, True), (False, False)):
             assert tuple(rmc.estimateBurnin(sampler, estBurnin=est, thinChains=thin)) == \
                 tuple(mine.estimateBurnin(sampler, estBurnin=est, thinChains=thin))
+
+
+def _build_ap(mod, lhmod, rgu, algorithm, n0=20):
+    np.random.seed(3)
+    theta = lhmod.rosenbrockSample(n0)
+    y = np.array([lhmod.rosenbrockLnlike(t) + lhmod.rosenbrockLnprior(t) for t in theta])
+    np.random.seed(5)
+    gp = rgu.defaultGP(theta, y, white_noise=-12)
+    return mod.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lhmod.rosenbrockLnprior, lnlike=lhmod.rosenbrockLnlike,
+                               priorSample=lhmod.rosenbrockSample, bounds=[(-5, 5), (-5, 5)], algorithm=algorithm)
+
+
+@needs_ref
+@pytest.mark.parametrize("algorithm", ["bape", "agp", "alternate"])
+def test_run_is_the_references_run_on_the_same_gp(algorithm, tmp_path):
+    """ApproxPosterior.run of the mirror against the reference's OWN ApproxPosterior.run (approx.py:229-524), both on the
+    oracle-backed george/emcee shim with the same seeds: the same design points and targets, the same burn-in / thinning
+    estimates, the same final chain, bit for bit -- the mirror keeps the reference's protocol and its np.random
+    consumption through findNextPoint, optGP, runMCMC and estimateBurnin."""
+    from oracle import refshim
+    from approxposterior_b200 import approx as mine, likelihood as lh
+    with _Reference(refshim, tmp_path):
+        rap = importlib.import_module("approxposterior.approx")
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        rlh = importlib.import_module("approxposterior.likelihood")
+        def kw():          # fresh dictionaries per run: the reference's validateMCMCKwargs writes into mcmcKwargs
+            return dict(m=4, nmax=2, estBurnin=True, nGPRestarts=2, mcmcKwargs={"iterations": 300}, cache=False, verbose=False,
+                        thinChains=True, onlyLastMCMC=False, seed=21)
+        a = _build_ap(rap, rlh, rgu, algorithm)
+        np.random.seed(21)
+        with np.errstate(all="ignore"):
+            a.run(samplerKwargs={"nwalkers": 10}, **kw())
+        state_ref = np.random.get_state()[1].copy()
+        b = _build_ap(mine, lh, rgu, algorithm)
+        np.random.seed(21)
+        with np.errstate(all="ignore"):
+            b.run(samplerKwargs={"nwalkers": 10, "engine": "host-rng"}, **kw())
+        assert a.theta.shape == (28, 2)
+        assert np.array_equal(a.theta, b.theta) and np.array_equal(a.y, b.y)
+        assert list(a.iburns) == list(b.iburns) and [int(v) for v in a.ithins] == [int(v) for v in b.ithins]
+        assert np.array_equal(a.sampler.get_chain(), b.sampler.get_chain())
+        assert np.array_equal(a.gp.get_parameter_vector(), b.gp.get_parameter_vector())
+        assert np.array_equal(np.random.get_state()[1], state_ref)
+
+
+@needs_ref
+def test_bayesopt_and_findmap_are_the_references(tmp_path):
+    """bayesOpt (approx.py:929-1151, Jones utility) and findMAP (approx.py:857-926) against the reference's own."""
+    from oracle import refshim
+    from approxposterior_b200 import approx as mine, likelihood as lh
+    with _Reference(refshim, tmp_path):
+        rap = importlib.import_module("approxposterior.approx")
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        rlh = importlib.import_module("approxposterior.likelihood")
+        out = []
+        for mod, lhmod in ((rap, rlh), (mine, lh)):
+            ap = _build_ap(mod, lhmod, rgu, "jones", n0=15)
+            np.random.seed(8)
+            with np.errstate(all="ignore"):
+                soln = ap.bayesOpt(nmax=4, verbose=False, cache=False, nGPRestarts=2, nMinObjRestarts=3, findMAP=True, seed=8)
+                m, v = ap.findMAP(nRestarts=3)
+            out.append((ap.theta.copy(), ap.y.copy(), soln, np.asarray(m), np.asarray(v), np.random.get_state()[1].copy()))
+        (ta, ya, sa, ma, va, ra), (tb, yb, sb, mb, vb, rb) = out
+        assert np.array_equal(ta, tb) and np.array_equal(ya, yb)
+        assert sorted(sa.keys()) == sorted(sb.keys())
+        for k in sa:
+            assert np.array_equal(np.asarray(sa[k], dtype=float), np.asarray(sb[k], dtype=float), equal_nan=True), k
+        assert np.array_equal(ma, mb), (ma, mb)
+        assert np.array_equal(np.ravel(va), np.ravel(vb)), (va, vb)
+        assert np.array_equal(ra, rb)
