@@ -182,3 +182,40 @@ def test_bayesopt_and_findmap_are_the_references(tmp_path):
         assert np.array_equal(ma, mb), (ma, mb)
         assert np.array_equal(np.ravel(va), np.ravel(vb)), (va, vb)
         assert np.array_equal(ra, rb)
+
+
+@needs_ref
+def test_cache_files_are_the_references(tmp_path):
+    """N3: the four .npz caches ApproxPosterior.run writes (approx.py:363-364, 430-432, 469-473, 507-514) -- same file
+    names, same keys, same contents as the reference's own run writes (timings aside); the mirror additionally writes the
+    chain files runName{i}.h5 (emcee's HDFBackend layout, hdf5min.py), which the reference delegates to emcee + h5py."""
+    import os
+    from oracle import refshim
+    from approxposterior_b200 import approx as mine, likelihood as lh
+    with _Reference(refshim, tmp_path):
+        rap = importlib.import_module("approxposterior.approx")
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        rlh = importlib.import_module("approxposterior.likelihood")
+        dirs = []
+        for mod, lhmod, extra in ((rap, rlh, {}), (mine, lh, {"engine": "host-rng"})):
+            d = tmp_path / ("ref" if mod is rap else "mirror")
+            d.mkdir()
+            dirs.append(d)
+            ap = _build_ap(mod, lhmod, rgu, "bape")
+            np.random.seed(21)
+            sk = {"nwalkers": 10}
+            sk.update(extra)
+            with np.errstate(all="ignore"):
+                ap.run(m=3, nmax=2, estBurnin=True, nGPRestarts=1, mcmcKwargs={"iterations": 200}, samplerKwargs=sk, cache=True,
+                       verbose=False, thinChains=True, convergenceCheck=True, timing=True, seed=21, runName=str(d / "apRun"))
+        ref_files = sorted(f for f in os.listdir(dirs[0]) if f.endswith(".npz"))
+        assert ref_files == ["apRunAPFModelCache.npz", "apRunAPGP.npz", "apRunAPTiming.npz", "apRunConvergenceCache.npz"]
+        for f in ref_files:
+            A, B = np.load(dirs[0] / f, allow_pickle=True), np.load(dirs[1] / f, allow_pickle=True)
+            assert sorted(A.files) == sorted(B.files), f
+            for k in A.files:
+                if f == "apRunAPTiming.npz":
+                    assert A[k].shape == B[k].shape, (f, k)
+                else:
+                    assert np.array_equal(A[k], B[k]), (f, k)
+        assert (dirs[1] / "apRun0.h5").exists() and (dirs[1] / "apRun1.h5").exists()
