@@ -88,9 +88,14 @@ class _Reference(object):
         return False
 
 
+# the reference's two remaining test modules never reach george / emcee (gmmUtils, klNumerical: out of scope for the
+# engine); with them the CPU half executes EVERY test module the reference ships
+OFF_PATH = [("test_KL", "testKLApproximation"), ("test_GMM", "testGMMFit")]
+
+
 # ------------------------------------------------------------------------------------------ CPU: oracle-backed shim
 @needs_ref
-@pytest.mark.parametrize("module,function", CASES)
+@pytest.mark.parametrize("module,function", CASES + OFF_PATH)
 def test_reference_tests_on_oracle_shim(module, function, tmp_path):
     from oracle import refshim
     with _Reference(refshim, tmp_path) as ref:
