@@ -219,3 +219,32 @@ def test_cache_files_are_the_references(tmp_path):
                 else:
                     assert np.array_equal(A[k], B[k]), (f, k)
         assert (dirs[1] / "apRun0.h5").exists() and (dirs[1] / "apRun1.h5").exists()
+
+
+@needs_ref
+def test_fixture_functions_are_the_references(tmp_path):
+    """likelihood.py's fixtures (the objectives, priors and prior samplers the reference's tests and README use): same
+    values on the same points, same draws and np.random state from the same seed."""
+    from oracle import refshim
+    from approxposterior_b200 import likelihood as mine
+    with _Reference(refshim, tmp_path):
+        rlh = importlib.import_module("approxposterior.likelihood")
+        rng = np.random.default_rng(6)
+        for name, dim in (("rosenbrock", 2), ("sphere", 2), ("testBOFn", 1)):
+            lnlike = {"rosenbrock": "rosenbrockLnlike", "sphere": "sphereLnlike", "testBOFn": "testBOFn"}[name]
+            lnprior = {"rosenbrock": "rosenbrockLnprior", "sphere": "sphereLnprior", "testBOFn": "testBOFnLnPrior"}[name]
+            sample = {"rosenbrock": "rosenbrockSample", "sphere": "sphereSample", "testBOFn": "testBOFnSample"}[name]
+            pts = rng.uniform(-6, 6, size=(60, dim))                        # inside and outside the prior supports
+            with np.errstate(all="ignore"):
+                for t in pts:
+                    t = t if dim > 1 else t[0]
+                    for fn in (lnlike, lnprior):
+                        a, b = getattr(rlh, fn)(t), getattr(mine, fn)(t)
+                        assert np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float), equal_nan=True), (fn, t)
+            for n in (1, 7):
+                np.random.seed(12); a = getattr(rlh, sample)(n); sa = np.random.get_state()[1].copy()
+                np.random.seed(12); b = getattr(mine, sample)(n); sb = np.random.get_state()[1].copy()
+                assert np.array_equal(np.asarray(a), np.asarray(b)) and np.shape(a) == np.shape(b) and np.array_equal(sa, sb), sample
+        with np.errstate(all="ignore"):
+            for t in rng.uniform(-6, 6, size=(20, 2)):
+                assert rlh.rosenbrockLnprob(t) == mine.rosenbrockLnprob(t)
