@@ -248,3 +248,40 @@ def test_fixture_functions_are_the_references(tmp_path):
         with np.errstate(all="ignore"):
             for t in rng.uniform(-6, 6, size=(20, 2)):
                 assert rlh.rosenbrockLnprob(t) == mine.rosenbrockLnprob(t)
+
+
+@needs_ref
+def test_validate_mcmc_kwargs_is_the_references(tmp_path):
+    """mcmcUtils.validateMCMCKwargs (mcmcUtils.py:15-100): the same sampler / mcmc dictionaries, the same prior draws for
+    the initial state, on every branch the reference itself survives (its samplerKwargs=None branch reads a non-existent
+    "dim" key -- SURVEY App. B -- and is the one place the mirror deliberately differs)."""
+    from oracle import refshim
+    from approxposterior_b200 import mcmcUtils as mine, likelihood as lh
+
+    class AP(object):
+        ndim = 2
+        priorSample = staticmethod(lh.rosenbrockSample)
+
+        def _gpll(self, theta, *a, **k):
+            return 0.0, 0.0
+    with _Reference(refshim, tmp_path):
+        rmc = importlib.import_module("approxposterior.mcmcUtils")
+        ap = AP()
+        cases = [({"nwalkers": 12}, None), ({"nwalkers": 8, "ndim": 5, "backend": "x", "log_prob_fn": len}, {"iterations": 50}),
+                 ({}, {"initial_state": np.zeros((40, 2))}), ({"nwalkers": 6}, {"iterations": 7, "initial_state": np.ones((6, 2))})]
+        for sk, mk in cases:
+            out = []
+            for mod in (rmc, mine):
+                np.random.seed(2)
+                s, m = mod.validateMCMCKwargs(ap, dict(sk), None if mk is None else dict(mk), verbose=False)
+                out.append((s, m, np.random.get_state()[1].copy()))
+            (sa, ma, ra), (sb, mb, rb) = out
+            assert sorted(sa) == sorted(sb) and sorted(ma) == sorted(mb)
+            for k in sa:
+                if k == "log_prob_fn":
+                    assert sa[k] == ap._gpll and sb[k] == ap._gpll
+                else:
+                    assert sa[k] == sb[k], k
+            for k in ma:
+                assert np.array_equal(np.asarray(ma[k]), np.asarray(mb[k])), k
+            assert np.array_equal(ra, rb)
