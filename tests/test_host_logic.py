@@ -533,3 +533,36 @@ def test_shipped_kernels_have_the_claimed_hardware_paths_and_no_spills():
     for k in ("loglik_small_kernel", "minimize_nll_kernel", "chol_panel_kernel", "chol_update_kernel", "gemm_tile_kernel"):
         assert rows[k]["DMMA"] > 0, k
     assert rows["sampler_kernel"]["CGABAR"] > 0 and rows["sampler_kernel"]["regs"] <= 64
+
+
+def test_compat_emcee_shim_is_the_oracles_emcee_flow():
+    """compat.py's emcee module (product code: what the unmodified reference imports as `emcee` on the engine) against the
+    oracle's emcee restatement, on a plain Python log-probability (no GP, no GPU): the same NumPy RNG flow -- chain,
+    log-probabilities, blobs, accepted fractions and the final np.random state agree bit for bit; the autocorrelation time
+    (one batched FFT here, emcee's per-walker FFTs there) to rounding."""
+    import sys
+    from oracle import refshim
+    from approxposterior_b200 import compat
+    lnprob = lambda x: (-0.5 * np.sum(x * x) - 0.1 * np.sum(x ** 4), 1.5)
+    outs = []
+    for shim in (refshim, compat):
+        shim.install()
+        try:
+            import emcee
+            assert emcee.__version__.startswith("3.0")
+            np.random.seed(4)
+            s = emcee.EnsembleSampler(10, 3, lnprob, blobs_dtype=[("lnprior", float)])
+            for _ in s.sample(np.random.randn(10, 3), iterations=400):
+                pass
+            blobs = s.get_blobs()                              # structured ("lnprior") on the engine shim, plain on the oracle's
+            blobs = blobs["lnprior"] if getattr(blobs.dtype, "names", None) else blobs
+            outs.append((s.get_chain().copy(), s.get_log_prob().copy(), np.asarray(blobs, dtype=float).copy(),
+                         np.asarray(s.acceptance_fraction).copy(), s.get_chain(discard=10, thin=3, flat=True).copy(),
+                         np.random.get_state()[1].copy(), np.asarray(s.get_autocorr_time(tol=0))))
+        finally:
+            shim.uninstall()
+            for n in [n for n in sys.modules if n == "emcee" or n.startswith("emcee.")]:
+                del sys.modules[n]
+    for a, b in zip(outs[0][:-1], outs[1][:-1]):
+        assert np.array_equal(a, b)
+    np.testing.assert_allclose(outs[1][-1], outs[0][-1], rtol=1e-13)
