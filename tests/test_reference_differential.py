@@ -158,6 +158,38 @@ def test_run_is_the_references_run_on_the_same_gp(algorithm, tmp_path):
 
 
 @needs_ref
+def test_run_with_non_default_options_is_the_references(tmp_path):
+    """The same comparison on the branches the default call does not take: GP refits every second point only
+    (optGPEveryN), Nelder-Mead for the hyper-parameters, Powell for the utility, no initial fit, no burn-in estimate,
+    convergence check with a loose eps (the run may stop early -- on both sides at the same iteration)."""
+    from oracle import refshim
+    from approxposterior_b200 import approx as mine, likelihood as lh
+    with _Reference(refshim, tmp_path):
+        rap = importlib.import_module("approxposterior.approx")
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        rlh = importlib.import_module("approxposterior.likelihood")
+
+        def kw():
+            return dict(m=5, nmax=3, estBurnin=False, thinChains=False, nGPRestarts=1, mcmcKwargs={"iterations": 150}, cache=False,
+                        verbose=False, seed=4, optGPEveryN=2, gpMethod="nelder-mead", gpOptions={"maxiter": 60}, initGPOpt=False,
+                        nMinObjRestarts=2, minObjMethod="powell", minObjOptions={"maxiter": 3}, convergenceCheck=True, eps=5.0,
+                        kmax=1)
+        a = _build_ap(rap, rlh, rgu, "agp")
+        np.random.seed(4)
+        with np.errstate(all="ignore"):
+            a.run(samplerKwargs={"nwalkers": 8}, **kw())
+        state_ref = np.random.get_state()[1].copy()
+        b = _build_ap(mine, lh, rgu, "agp")
+        np.random.seed(4)
+        with np.errstate(all="ignore"):
+            b.run(samplerKwargs={"nwalkers": 8, "engine": "host-rng"}, **kw())
+        assert a.theta.shape == b.theta.shape and np.array_equal(a.theta, b.theta) and np.array_equal(a.y, b.y)
+        assert np.array_equal(a.sampler.get_chain(), b.sampler.get_chain())
+        assert np.array_equal(a.gp.get_parameter_vector(), b.gp.get_parameter_vector())
+        assert np.array_equal(np.random.get_state()[1], state_ref)
+
+
+@needs_ref
 def test_bayesopt_and_findmap_are_the_references(tmp_path):
     """bayesOpt (approx.py:929-1151, Jones utility) and findMAP (approx.py:857-926) against the reference's own."""
     from oracle import refshim
