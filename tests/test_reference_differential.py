@@ -317,3 +317,40 @@ def test_validate_mcmc_kwargs_is_the_references(tmp_path):
             for k in ma:
                 assert np.array_equal(np.asarray(ma[k]), np.asarray(mb[k])), k
             assert np.array_equal(ra, rb)
+
+
+@needs_ref
+def test_argument_errors_are_the_references(tmp_path):
+    """Constructor / run argument validation (approx.py:84-129, 390-394): the same exception types for the same bad
+    arguments; the same objects accepted."""
+    from oracle import refshim
+    from approxposterior_b200 import approx as mine, likelihood as lh
+    with _Reference(refshim, tmp_path):
+        rap = importlib.import_module("approxposterior.approx")
+        rgu = importlib.import_module("approxposterior.gpUtils")
+        rlh = importlib.import_module("approxposterior.likelihood")
+        theta, y = _problem(12)
+        np.random.seed(5)
+        gp = rgu.defaultGP(theta, y, white_noise=-12)
+        bad_theta = theta.copy(); bad_theta[0, 0] = np.inf
+        bad_y = y.copy(); bad_y[3] = np.nan
+        cases = [dict(theta=None, y=y), dict(theta=theta, y=None), dict(theta=bad_theta, y=y), dict(theta=theta, y=bad_y),
+                 dict(theta=theta, y=y, bounds=[(-5, 5)]), dict(theta=theta, y=y, algorithm="nope"),
+                 dict(theta=theta, y=y, algorithm="BAPE"), dict(theta=theta, y=y, algorithm="jones"), dict(theta=theta, y=y)]
+        for c in cases:
+            res = []
+            for mod, lhmod in ((rap, rlh), (mine, lh)):
+                kw = dict(gp=gp, lnprior=lhmod.rosenbrockLnprior, lnlike=lhmod.rosenbrockLnlike, priorSample=lhmod.rosenbrockSample,
+                          bounds=[(-5, 5), (-5, 5)], algorithm="bape")
+                kw.update(c)
+                try:
+                    ap = mod.ApproxPosterior(**kw)
+                    res.append(("ok", ap.algorithm, ap.theta.shape, ap.y.shape))
+                except Exception as e:                       # noqa: BLE001 -- the comparison is the point
+                    res.append((type(e).__name__,))           # (the reference's "unknown algorithm" text lists "naive", which it
+            assert res[0] == res[1], (c.keys(), res)             # does not accept, instead of "jones": messages are not compared)
+        for mod, lhmod in ((rap, rlh), (mine, lh)):          # convergenceCheck needs an MCMC per iteration
+            ap = mod.ApproxPosterior(theta=theta, y=y, gp=gp, lnprior=lhmod.rosenbrockLnprior, lnlike=lhmod.rosenbrockLnlike,
+                                     priorSample=lhmod.rosenbrockSample, bounds=[(-5, 5), (-5, 5)], algorithm="bape")
+            with pytest.raises(RuntimeError):
+                ap.run(m=1, nmax=1, convergenceCheck=True, onlyLastMCMC=True, verbose=False, cache=False)
